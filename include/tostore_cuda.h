@@ -1,0 +1,209 @@
+/*
+ * tostore_cuda.h — C ABI of libtostore_cuda.so, the B200 (sm_100a) exact
+ * vector-search executor that drops in underneath ToStore's `vectorSearch`.
+ *
+ * This is the boundary the reference's Dart host binds with dart:ffi
+ * (binding source: dart/tostore_cuda_bindings.dart, wiring: INTEGRATION.md) and
+ * that this repo's Python host mirror binds with ctypes. Plain pointers and
+ * sizes only: no C++ types, no exceptions, no torch types, no stdout.
+ *
+ * Reference interfaces replaced / consumed (paths relative to
+ * /root/reference/lib/src, tocreator/tostore @ 130da06):
+ *   - NghGraphEngine.search                 core/ngh_graph_engine.dart:67-135
+ *     (call site core/vector_index_manager.dart:538-548)       -> tsc_search*
+ *   - _exactDistance/_l2Distance/_innerProduct/_cosineSimlarity :908-946
+ *   - result ordering :133-134, vector_index_manager.dart:587
+ *   - VectorIndexManager._toFloat32/_normalizeFloat32/_distanceToScore
+ *     core/vector_index_manager.dart:1385-1423                  -> tsc_vector_search
+ *   - NghRawVectorPage / BTreePageIO page format
+ *     core/ngh_page.dart:310-450, core/btree_page.dart:132-234  -> tsc_index_append_pages
+ *   - tombstones NghNodeFlags.deleted core/ngh_page.dart:104-108,
+ *     deleteBatch core/ngh_graph_engine.dart:411-445            -> tsc_index_set_deleted,
+ *                                                                  tsc_index_apply_graph_pages
+ *   - nodeId -> (partition,page,slot) model/ngh_index_meta.dart:451-490
+ *
+ * Conventions (mirroring lib/src/handler/system_ffi_helper.dart): every buffer
+ * is caller-allocated and caller-freed; int32 status, 0 = success, negative =
+ * tsc_status; handles are opaque uint64 (safe to pass between isolates).
+ * Thread-safe per handle (internal mutex). There is NO CPU fallback: without a
+ * usable CUDA device every compute entry point returns TSC_ERR_CUDA.
+ */
+#ifndef TOSTORE_CUDA_H
+#define TOSTORE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSC_ABI_VERSION 1
+
+typedef enum tsc_status {
+  TSC_OK = 0,
+  TSC_ERR_BAD_HANDLE = -1,
+  TSC_ERR_BAD_ARG = -2,      /* NULL pointer, k == 0, k > k_max, nq > nq_max ... */
+  TSC_ERR_BAD_DIMS = -3,     /* dims == 0, dims too large, page dims mismatch     */
+  TSC_ERR_OOM = -4,          /* host or device allocation failed / capacity full  */
+  TSC_ERR_CUDA = -5,         /* CUDA runtime / driver error, no device            */
+  TSC_ERR_NCCL = -6,         /* NCCL missing or failed                            */
+  TSC_ERR_PAGE = -7,         /* bad magic / header / length / CRC / type          */
+  TSC_ERR_UNSUPPORTED = -8,
+  TSC_ERR_NOT_READY = -9     /* poll: ticket still running                        */
+} tsc_status;
+
+/* VectorDistanceMetric enum order, model/table_schema.dart:2511-2531 */
+enum { TSC_METRIC_L2 = 0, TSC_METRIC_INNER_PRODUCT = 1, TSC_METRIC_COSINE = 2 };
+/* VectorPrecision enum order, model/table_schema.dart:2481-2498 */
+enum { TSC_SRC_F64 = 0, TSC_SRC_F32 = 1, TSC_SRC_I8 = 2 };
+/* storage type of the embedding column in HBM (new; reference has fp32 only) */
+enum { TSC_DEV_F32 = 0, TSC_DEV_BF16 = 1, TSC_DEV_F16 = 2 };
+
+typedef struct tsc_index_desc {
+  uint32_t struct_size;    /* sizeof(tsc_index_desc), for forward compatibility */
+  uint32_t dims;           /* NghIndexMeta.dimensions                            */
+  uint8_t metric;          /* TSC_METRIC_*                                       */
+  uint8_t src_precision;   /* TSC_SRC_*: element type of append_rows / pages     */
+  uint8_t dev_dtype;       /* TSC_DEV_*                                          */
+  uint8_t reserved0;
+  int32_t device_id;       /* CUDA device ordinal that holds this shard          */
+  uint64_t capacity_rows;  /* rows reserved in HBM for this shard                */
+  uint64_t first_node_id;  /* nodeId of shard row 0 (row-range sharding)         */
+  uint32_t k_max;          /* largest topK that will be requested (<= 128)       */
+  uint32_t nq_max;         /* largest query batch per call                       */
+} tsc_index_desc;
+
+typedef struct tsc_stats {
+  uint32_t struct_size;
+  uint32_t dims;
+  uint64_t rows;             /* rows appended ([0, nextNodeId) of this shard)  */
+  uint64_t deleted_rows;
+  uint64_t device_bytes;     /* HBM held by this index                         */
+  uint64_t row_stride_bytes; /* bytes per row in HBM                           */
+  uint64_t searches;         /* completed search calls                         */
+  uint64_t kernel_launches;  /* kernels launched by this index since creation  */
+  double last_search_ms;     /* device time of the last search (CUDA events)   */
+  double last_scan_gbs;      /* algorithmic row bytes / last_search_ms         */
+  uint32_t last_path;        /* 1 = HBM scan, 2 = tcgen05 GEMM                 */
+  uint32_t reserved;
+  /* dominant-kernel accounting since creation / tsc_stats_reset: every scan (or
+   * GEMM) launch is bracketed by CUDA events on its own stream */
+  uint64_t hot_launches;     /* timed launches of the dominant kernel          */
+  double hot_ms_total;       /* sum of their device durations                  */
+  double hot_bytes_total;    /* algorithmic bytes they covered (rows*dims*elem)*/
+  double hot_flops_total;    /* algorithmic flops (GEMM path), else 0          */
+} tsc_stats;
+
+/* ---- library ---- */
+int32_t tsc_version(void);                       /* TSC_ABI_VERSION             */
+int32_t tsc_device_count(void);                  /* >= 0, or negative status    */
+const char *tsc_last_error(void);                /* thread-local static string  */
+const char *tsc_status_name(int32_t status);
+
+/* ---- index lifetime ---- */
+int32_t tsc_index_create(const tsc_index_desc *desc, uint64_t *out_handle);
+int32_t tsc_index_destroy(uint64_t handle);
+int32_t tsc_index_clear(uint64_t handle);        /* drop all rows, keep capacity;
+                                                    clearCacheForIndex hook,
+                                                    vector_index_manager.dart:1192-1202 */
+
+/* ---- corpus ingestion (flush-time hooks, vector_index_manager.dart:378-387) ---- */
+/* rows: dense row-major [n_rows, dims] of src_precision, HOST memory. node ids
+ * [first_node_id, first_node_id+n_rows) must lie inside the shard and be
+ * appended densely (first_node_id <= shard_first + rows). */
+int32_t tsc_index_append_rows(uint64_t handle, uint64_t first_node_id,
+                              const void *rows, uint64_t n_rows);
+/* pages: n_pages consecutive reference raw-vector pages (page_size bytes each,
+ * as stored in rawvec/dir_k/p<n>.ngh after the per-file meta page), HOST
+ * memory. first_logical_page = nodeId / vectorsPerRawPage of the first page.
+ * The library validates magic / header / CRC-32 / page type / dims, strips the
+ * 28-byte headers and decodes f64 / f32 / i8 elements exactly like
+ * NghRawVectorPage.getVectorAsFloat32. live_rows = nextNodeId of the index:
+ * slots at or beyond it (zero-filled tail of the last page) are ignored. */
+int32_t tsc_index_append_pages(uint64_t handle, uint64_t first_logical_page,
+                               const uint8_t *pages, uint64_t n_pages,
+                               uint32_t page_size, uint64_t live_rows);
+/* test / benchmark helper: append n_rows of the deterministic synthetic corpus
+ * (seed, global row index) generated on the device; see DESIGN.md. */
+int32_t tsc_index_append_synthetic(uint64_t handle, uint64_t seed,
+                                   uint64_t first_node_id, uint64_t n_rows);
+
+/* ---- liveness ---- */
+int32_t tsc_index_set_deleted(uint64_t handle, const uint64_t *node_ids,
+                              uint64_t n, uint8_t deleted);
+/* graph pages (graph/dir_k/p<n>.ngh data pages): only the per-slot flags byte is
+ * read; bit 0x01 marks a tombstone. first_logical_page = nodeId / nodesPerGraphPage. */
+int32_t tsc_index_apply_graph_pages(uint64_t handle, uint64_t first_logical_page,
+                                    const uint8_t *pages, uint64_t n_pages,
+                                    uint32_t page_size);
+/* WHERE prefilter: bit (nodeId - first_node_id) of word (..)/64, LSB first,
+ * 1 = row may be returned. NULL clears the filter. */
+int32_t tsc_index_set_filter(uint64_t handle, const uint64_t *bitmap_words,
+                             uint64_t n_words);
+
+/* ---- search ---- */
+/* queries: [nq, dims] fp32, already padded/truncated to dims and, for cosine,
+ * already normalised (exactly what VectorIndexManager hands NghGraphEngine.search).
+ * distance_threshold: NaN = none; results with distance > threshold are dropped.
+ * out_ids [nq*k] (-1 padded), out_dist [nq*k] ascending (NaN padded),
+ * out_counts [nq]. HOST buffers; blocks until the results are written. */
+int32_t tsc_search(uint64_t handle, const float *queries, uint32_t nq, uint32_t k,
+                   double distance_threshold, int64_t *out_ids, double *out_dist,
+                   uint32_t *out_counts);
+/* non-blocking pair so a Dart isolate can yield between polls */
+int32_t tsc_search_submit(uint64_t handle, const float *queries, uint32_t nq,
+                          uint32_t k, double distance_threshold, int64_t *out_ids,
+                          double *out_dist, uint32_t *out_counts,
+                          uint64_t *out_ticket);
+int32_t tsc_search_poll(uint64_t ticket, int32_t *out_done);   /* 0 / 1          */
+int32_t tsc_search_wait(uint64_t ticket);                      /* blocks, frees  */
+/* DEVICE buffers on the index's device, asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*, NULL = the index's own stream). */
+int32_t tsc_search_device(uint64_t handle, const float *d_queries, uint32_t nq,
+                          uint32_t k, double distance_threshold, int64_t *d_out_ids,
+                          double *d_out_dist, uint32_t *d_out_counts,
+                          void *cuda_stream);
+/* Host mirror of VectorIndexManager.vectorSearch's arithmetic around the engine
+ * call (core/vector_index_manager.dart:514-520, :576-587): _toFloat32
+ * (truncate / zero-pad `values[len]` to dims), _normalizeFloat32 for cosine,
+ * search, _distanceToScore. out_* are [k]. */
+int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len,
+                          uint32_t k, double distance_threshold, int64_t *out_ids,
+                          double *out_dist, double *out_score, uint32_t *out_count);
+
+/* ---- row-range sharding across GPUs (one process per GPU) ---- */
+/* Merge n_parts per-shard results ([n_parts, nq, k] ids/dist as produced by
+ * tsc_search_device on each shard and all-gathered by the caller or by
+ * tsc_comm_*) into the global top-k. DEVICE buffers, async on cuda_stream. */
+int32_t tsc_merge_shards(uint64_t handle, const int64_t *d_part_ids,
+                         const double *d_part_dist, uint32_t n_parts, uint32_t nq,
+                         uint32_t k, int64_t *d_out_ids, double *d_out_dist,
+                         uint32_t *d_out_counts, void *cuda_stream);
+/* NCCL communicator owned by the library (libnccl.so.2 is dlopen'ed on first
+ * use). unique_id: 128 bytes, created on rank 0 and distributed by the caller. */
+int32_t tsc_comm_unique_id(uint8_t *out_id128);
+int32_t tsc_comm_init(uint64_t handle, const uint8_t *id128, int32_t n_ranks,
+                      int32_t rank);
+/* search this shard, ncclAllGather the per-shard top-k, merge on every rank.
+ * DEVICE buffers; out_* hold the global result on every rank. */
+int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
+                           uint32_t k, double distance_threshold,
+                           int64_t *d_out_ids, double *d_out_dist,
+                           uint32_t *d_out_counts, void *cuda_stream);
+
+/* ---- observability ---- */
+int32_t tsc_stats_get(uint64_t handle, tsc_stats *out);
+int32_t tsc_stats_reset(uint64_t handle);        /* zero the hot_* accumulators  */
+/* raw device pointers for zero-copy interop (bench / torch.distributed glue) */
+int32_t tsc_index_device_rows(uint64_t handle, void **out_ptr, uint64_t *out_rows,
+                              uint64_t *out_row_stride_bytes);
+
+/* self-test hook: the warp-sliced CRC-32 of the page validator, re-enacted on the
+ * host (no GPU needed); must equal CRC-32/IEEE (Crc32.of, btree_page.dart:64-89). */
+uint32_t tsc_selftest_crc32(const uint8_t *data, uint32_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOSTORE_CUDA_H */

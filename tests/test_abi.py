@@ -1,0 +1,90 @@
+"""CPU tests of the boundary: the C-ABI library loads without a GPU, exports every
+symbol include/tostore_cuda.h declares, fails loudly (no CPU fallback), and the
+product package never touches the oracle."""
+import ctypes as C
+import os
+import re
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "tostore_cuda.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(tsc_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tostore_b200 import _native as N
+    lib = N.lib()
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in tostore_cuda.h but not exported"
+    assert sorted(N.EXPORTS) == syms, "python binding list out of sync with the header"
+    assert lib.tsc_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from tostore_b200 import _native as N
+    assert C.sizeof(N.IndexDesc) == 40          # 4+4+4(4xu8)+4+8+8+4+4
+    assert C.sizeof(N.Stats) == 112
+    assert N.IndexDesc.capacity_rows.offset == 16 and N.IndexDesc.k_max.offset == 32
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import tostore_b200 as t
+    with pytest.raises(t.TscError) as e:
+        t.GpuVectorIndex(128, capacity_rows=16)
+    assert e.value.status == -5                  # TSC_ERR_CUDA, loudly
+    store = t.GpuVectorStore()
+    with pytest.raises(t.TscError):
+        store.createVectorIndex("t", "e", t.VectorFieldConfig(dimensions=8))
+
+
+def test_bad_arguments_are_rejected_before_cuda():
+    from tostore_b200 import _native as N
+    lib = N.lib()
+    h = C.c_uint64(0)
+    assert lib.tsc_index_create(None, C.byref(h)) == N.TSC_ERR_BAD_ARG
+    d = N.IndexDesc(struct_size=C.sizeof(N.IndexDesc), dims=0, metric=0, src_precision=1,
+                    dev_dtype=0, device_id=0, capacity_rows=10, k_max=10, nq_max=1)
+    assert lib.tsc_index_create(C.byref(d), C.byref(h)) == N.TSC_ERR_BAD_DIMS
+    assert b"dims" in lib.tsc_last_error()
+    d.dims, d.metric = 8, 9
+    assert lib.tsc_index_create(C.byref(d), C.byref(h)) == N.TSC_ERR_BAD_ARG
+    d.metric, d.k_max = 0, 1000
+    assert lib.tsc_index_create(C.byref(d), C.byref(h)) == N.TSC_ERR_BAD_ARG
+    assert lib.tsc_index_destroy(12345) == N.TSC_ERR_BAD_HANDLE
+    assert lib.tsc_search(777, None, 1, 1, 0.0, None, None, None) == N.TSC_ERR_BAD_HANDLE
+    assert lib.tsc_status_name(-7) == b"TSC_ERR_PAGE"
+
+
+def test_warp_sliced_crc_matches_crc32_ieee():
+    from tostore_b200 import _native as N
+    lib = N.lib()
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 9, 31, 32, 33, 1000, 16364, 16384, 70001):
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        buf = data.tobytes()
+        assert lib.tsc_selftest_crc32(buf, n) == zlib.crc32(buf), n
+    assert lib.tsc_selftest_crc32(b"123456789", 9) == 0xCBF43926
+
+
+def test_product_path_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "tostore_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                src = open(os.path.join(dp, f)).read()
+                code = "\n".join(l for l in src.splitlines()
+                                 if not l.lstrip().startswith(("#", "//", "*", "/*", '"""')))
+                assert not re.search(r"^\s*(import|from)\s+oracle", code, flags=re.M), f
+                assert "liboracle" not in code and "tso_" not in code.replace("tso_synth_value", ""), f

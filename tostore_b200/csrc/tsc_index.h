@@ -1,0 +1,122 @@
+// tsc_index.h — host-side index object behind the C ABI (include/tostore_cuda.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+
+#include "../../include/tostore_cuda.h"
+
+namespace tsc {
+
+void set_error(const char *fmt, ...);
+
+#define TSC_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      tsc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                     __LINE__);                                                     \
+      return TSC_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+struct ScanConfig {
+  int grid = 0;        // CTAs (multiple of the SM count)
+  int warps = 8;       // warps per CTA
+  int rows = 0;        // R rows per stage (0 = auto)
+  int stages = 0;      // S (0 = auto)
+  int stage_target = 8192;  // bytes per stage aimed for when R is auto
+};
+
+struct Index {
+  std::mutex mu;
+  tsc_index_desc desc{};
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  // geometry of the embedding block in HBM: dense row-major [capacity, ld]
+  uint32_t elem_bytes = 4;
+  uint32_t ld = 0;          // elements per row incl. zero padding to 16 bytes
+  uint32_t row_bytes = 0;
+  uint32_t qld = 0;         // padded query length (== ld)
+  uint8_t *d_rows = nullptr;
+  uint64_t capacity = 0, rows = 0;
+
+  // liveness: deleted (tombstones) and filter (WHERE) bitmaps -> live
+  uint64_t mask_words = 0;  // 32-bit words
+  uint32_t *d_deleted = nullptr, *d_filter = nullptr, *d_live = nullptr;
+  bool has_deleted = false, has_filter = false, live_dirty = false;
+  uint64_t deleted_rows = 0;
+  int *d_delta = nullptr;
+
+  // search scratch
+  uint32_t k_max = 0, nq_max = 0, kprime_max = 0;
+  float *d_queries = nullptr;      // [nq_max, qld]
+  float *h_queries = nullptr;      // pinned
+  uint64_t *d_cand = nullptr;      // [nq_max][cand_lists][kprime_max]
+  uint64_t cand_lists = 0;
+  int64_t *d_out_ids = nullptr, *h_out_ids = nullptr;
+  double *d_out_dist = nullptr, *h_out_dist = nullptr;
+  uint32_t *d_out_counts = nullptr, *h_out_counts = nullptr;
+  // ingest staging
+  uint8_t *d_stage = nullptr;
+  size_t stage_bytes = 0;
+  uint32_t *d_page_status = nullptr;
+  size_t page_status_cap = 0;
+
+  ScanConfig scan;
+
+  // sharding
+  void *nccl_comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  uint8_t *d_gather_send = nullptr, *d_gather_recv = nullptr;
+
+  // dominant-kernel timing: ring of event pairs, resolved lazily
+  static constexpr int kTimers = 128;
+  cudaEvent_t t_beg[kTimers] = {}, t_end[kTimers] = {};
+  double t_bytes[kTimers] = {}, t_flops[kTimers] = {};
+  int t_head = 0, t_pending = 0;  // pending pairs are [t_head - t_pending, t_head)
+  uint64_t hot_launches = 0;
+  double hot_ms = 0, hot_bytes = 0, hot_flops = 0;
+
+  // stats
+  uint64_t searches = 0, launches = 0;
+  double last_ms = 0, last_gbs = 0;
+  uint32_t last_path = 0;
+  uint64_t device_bytes = 0;
+};
+
+// launchers implemented per translation unit
+int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
+                    uint32_t *out_lists, cudaStream_t st);
+int32_t launch_select(Index *ix, const float *d_q, uint32_t nq, uint32_t k, uint32_t kprime,
+                      const uint64_t *d_cand, uint32_t m, double threshold, int64_t *d_ids,
+                      double *d_dist, uint32_t *d_counts, cudaStream_t st);
+int32_t launch_merge(Index *ix, const int64_t *d_part_ids, const double *d_part_dist,
+                     uint64_t part_stride, uint32_t n_parts, uint32_t nq, uint32_t k,
+                     int64_t *d_ids, double *d_dist, uint32_t *d_counts, cudaStream_t st);
+int32_t scan_configure(Index *ix);
+// bracket one launch of the dominant kernel with events on `st`
+int32_t hot_timer_begin(Index *ix, cudaStream_t st, int *slot);
+int32_t hot_timer_end(Index *ix, cudaStream_t st, int slot, double bytes, double flops);
+int32_t hot_timer_resolve(Index *ix);
+
+inline uint32_t kprime_for(uint32_t k) {
+  // rerankCount = max(2k, 20), core/ngh_graph_engine.dart:115; capped margin for large k
+  uint32_t kp = k <= 64 ? (2 * k > 20 ? 2 * k : 20) : k + 64;
+  return kp;
+}
+
+inline uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace tsc

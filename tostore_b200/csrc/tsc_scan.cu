@@ -1,0 +1,150 @@
+// tsc_scan.cu — host launcher for K1 (tsc_scan.cuh): stage geometry + dispatch.
+#include <stdlib.h>
+
+#include "tsc_index.h"
+#include "tsc_scan.cuh"
+
+namespace tsc {
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  return atoi(v);
+}
+
+int32_t scan_configure(Index *ix) {
+  ix->scan.grid = env_int("TSC_SCAN_CTAS", 1) * ix->sm_count;
+  ix->scan.warps = env_int("TSC_SCAN_WARPS", 8);
+  ix->scan.rows = env_int("TSC_SCAN_ROWS", 0);
+  ix->scan.stages = env_int("TSC_SCAN_STAGES", 0);
+  ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 8192);
+  if (ix->scan.warps < 1 || ix->scan.warps > 16 || ix->scan.grid < 1) {
+    set_error("bad TSC_SCAN_* override");
+    return TSC_ERR_BAD_ARG;
+  }
+  return TSC_OK;
+}
+
+struct ScanPlan {
+  int warps, rows, stages, qb;
+  uint32_t stage_bytes, sort_cap;
+  size_t smem;
+};
+
+static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl) {
+  const size_t budget = ix->smem_optin - 1024;
+  for (int w = ix->scan.warps; w >= 1; w >>= 1) {
+    int r = ix->scan.rows;
+    if (r <= 0) {
+      r = 8;
+      while (r > 1 && (size_t)r * ix->row_bytes > (size_t)ix->scan.stage_target) r >>= 1;
+    }
+    while (r > 1 && r * qb > 16) r >>= 1;
+    uint32_t sort_cap = next_pow2((uint32_t)w * kprime);
+    if (sort_cap < 2) sort_cap = 2;
+    size_t fixed = scan_smem_query_bytes(qb, ix->qld) + scan_smem_sort_bytes(sort_cap);
+    if (fixed >= budget) continue;
+    size_t per_warp = ((budget - fixed) / w) & ~(size_t)127;
+    for (; r >= 1; r >>= 1) {
+      uint32_t stage_bytes = (uint32_t)r * ix->row_bytes;
+      int smax = ix->scan.stages > 0 ? ix->scan.stages : 8;
+      int s = smax;
+      while (s >= 2 && scan_smem_warp_bytes(qb, kprime, s, stage_bytes) > per_warp) s--;
+      if (s >= 2) {
+        pl->warps = w;
+        pl->rows = r;
+        pl->stages = s;
+        pl->qb = qb;
+        pl->stage_bytes = stage_bytes;
+        pl->sort_cap = sort_cap;
+        pl->smem = fixed + (size_t)w * scan_smem_warp_bytes(qb, kprime, s, stage_bytes);
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+template <int METRIC, int DTYPE, int QB, int R>
+static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
+  static bool attr_done[64] = {false};
+  auto kern = scan_topk_kernel<METRIC, DTYPE, QB, R>;
+  if (!attr_done[ix->device & 63]) {
+    TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ix->smem_optin));
+    attr_done[ix->device & 63] = true;
+  }
+  int slot = 0;
+  int32_t rc = hot_timer_begin(ix, st, &slot);
+  if (rc != TSC_OK) return rc;
+  kern<<<ix->scan.grid, pl.warps * 32, pl.smem, st>>>(p);
+  TSC_CUDA(cudaGetLastError());
+  ix->launches++;
+  // algorithmic bytes of one pass: live rows x dims x sizeof(elem)
+  return hot_timer_end(ix, st, slot, (double)p.n_rows * ix->desc.dims * ix->elem_bytes, 0.0);
+}
+
+template <int METRIC, int DTYPE>
+static int32_t dispatch_qr(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
+#define TSC_CASE(QB, R) \
+  if (pl.qb == QB && pl.rows == R) return run_scan<METRIC, DTYPE, QB, R>(ix, p, pl, st);
+  TSC_CASE(1, 1) TSC_CASE(1, 2) TSC_CASE(1, 4) TSC_CASE(1, 8)
+  TSC_CASE(4, 1) TSC_CASE(4, 2) TSC_CASE(4, 4)
+  TSC_CASE(8, 1) TSC_CASE(8, 2)
+#undef TSC_CASE
+  set_error("scan: no kernel for qb=%d rows=%d", pl.qb, pl.rows);
+  return TSC_ERR_UNSUPPORTED;
+}
+
+template <int METRIC>
+static int32_t dispatch_dtype(Index *ix, const ScanParams &p, const ScanPlan &pl,
+                              cudaStream_t st) {
+  switch (ix->desc.dev_dtype) {
+    case TSC_DEV_F32: return dispatch_qr<METRIC, kF32>(ix, p, pl, st);
+    case TSC_DEV_BF16: return dispatch_qr<METRIC, kBF16>(ix, p, pl, st);
+    default: return dispatch_qr<METRIC, kF16>(ix, p, pl, st);
+  }
+}
+
+// Scan the shard once per group of up to 8 queries. d_cand receives
+// [nq][grid][kprime] composites; *out_lists = grid.
+int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
+                    uint32_t *out_lists, cudaStream_t st) {
+  *out_lists = (uint32_t)ix->scan.grid;
+  for (uint32_t q0 = 0; q0 < nq;) {
+    uint32_t left = nq - q0;
+    int qb = left >= 5 ? 8 : (left >= 2 ? 4 : 1);
+    ScanPlan pl;
+    if (!plan_scan(ix, qb, kprime, &pl)) {
+      set_error("scan: dims=%u (row %u B) with k'=%u does not fit shared memory", ix->desc.dims,
+                ix->row_bytes, kprime);
+      return TSC_ERR_BAD_DIMS;
+    }
+    uint32_t n = left < (uint32_t)qb ? left : (uint32_t)qb;
+    ScanParams p{};
+    p.rows = ix->d_rows;
+    p.n_rows = ix->rows;
+    p.row_bytes = ix->row_bytes;
+    p.chunks_per_row = ix->row_bytes / 16;
+    p.queries = d_q + (size_t)q0 * ix->qld;
+    p.qld = ix->qld;
+    p.nq = n;
+    p.live_mask = (ix->has_deleted || ix->has_filter) ? ix->d_live : nullptr;
+    p.kprime = kprime;
+    p.stages = (uint32_t)pl.stages;
+    p.stage_bytes = pl.stage_bytes;
+    p.cand = d_cand + (size_t)q0 * ix->scan.grid * kprime;
+    p.sort_cap = pl.sort_cap;
+    int32_t rc;
+    switch (ix->desc.metric) {
+      case TSC_METRIC_L2: rc = dispatch_dtype<kL2>(ix, p, pl, st); break;
+      case TSC_METRIC_INNER_PRODUCT: rc = dispatch_dtype<kIP>(ix, p, pl, st); break;
+      default: rc = dispatch_dtype<kCos>(ix, p, pl, st); break;
+    }
+    if (rc != TSC_OK) return rc;
+    q0 += n;
+  }
+  return TSC_OK;
+}
+
+}  // namespace tsc

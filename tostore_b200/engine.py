@@ -1,0 +1,214 @@
+"""GpuVectorIndex — thin object wrapper over the C ABI for one shard on one GPU.
+
+Stands where `NghGraphEngine` stands in the reference
+(/root/reference/lib/src/core/ngh_graph_engine.dart:67-135): given an already
+prepared fp32 query it returns (nodeId, fp64 distance) pairs in ascending
+distance order. All compute happens in libtostore_cuda.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import numpy as np
+
+from . import _native as N
+
+METRIC_L2, METRIC_INNER_PRODUCT, METRIC_COSINE = 0, 1, 2
+SRC_F64, SRC_F32, SRC_I8 = 0, 1, 2
+DEV_F32, DEV_BF16, DEV_F16 = 0, 1, 2
+
+_SRC_NP = {SRC_F64: np.float64, SRC_F32: np.float32, SRC_I8: np.int8}
+
+
+class GpuVectorIndex:
+    def __init__(self, dims: int, metric: int = METRIC_COSINE, *, capacity_rows: int,
+                 src_precision: int = SRC_F32, dev_dtype: int = DEV_F32, device_id: int = 0,
+                 first_node_id: int = 0, k_max: int = 32, nq_max: int = 64):
+        self._lib = N.lib()
+        self.dims, self.metric = int(dims), int(metric)
+        self.src_precision, self.dev_dtype = int(src_precision), int(dev_dtype)
+        self.device_id, self.first_node_id = int(device_id), int(first_node_id)
+        self.k_max, self.nq_max = int(k_max), int(nq_max)
+        desc = N.IndexDesc(struct_size=C.sizeof(N.IndexDesc), dims=self.dims, metric=self.metric,
+                           src_precision=self.src_precision, dev_dtype=self.dev_dtype,
+                           device_id=self.device_id, capacity_rows=int(capacity_rows),
+                           first_node_id=self.first_node_id, k_max=self.k_max, nq_max=self.nq_max)
+        h = C.c_uint64(0)
+        N.check(self._lib.tsc_index_create(C.byref(desc), C.byref(h)), "tsc_index_create")
+        self.handle = h.value
+
+    # -- lifetime ------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "handle", 0):
+            self._lib.tsc_index_destroy(self.handle)
+            self.handle = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def clear(self) -> None:
+        N.check(self._lib.tsc_index_clear(self.handle), "tsc_index_clear")
+
+    # -- ingestion -------------------------------------------------------------
+    def append_rows(self, rows, first_node_id: Optional[int] = None) -> None:
+        rows = np.ascontiguousarray(rows, dtype=_SRC_NP[self.src_precision])
+        if rows.ndim != 2 or rows.shape[1] != self.dims:
+            raise ValueError(f"rows must be [n, {self.dims}]")
+        if first_node_id is None:
+            first_node_id = self.first_node_id + self.stats().rows
+        N.check(self._lib.tsc_index_append_rows(self.handle, int(first_node_id),
+                                                rows.ctypes.data, rows.shape[0]),
+                "tsc_index_append_rows")
+
+    def append_pages(self, pages: bytes, first_logical_page: int, page_size: int,
+                     live_rows: int) -> None:
+        buf = np.frombuffer(pages, dtype=np.uint8)
+        if buf.size % page_size:
+            raise ValueError("pages is not a whole number of pages")
+        N.check(self._lib.tsc_index_append_pages(self.handle, int(first_logical_page),
+                                                 buf.ctypes.data, buf.size // page_size,
+                                                 int(page_size), int(live_rows)),
+                "tsc_index_append_pages")
+
+    def append_synthetic(self, seed: int, n_rows: int, first_node_id: Optional[int] = None) -> None:
+        if first_node_id is None:
+            first_node_id = self.first_node_id + self.stats().rows
+        N.check(self._lib.tsc_index_append_synthetic(self.handle, int(seed), int(first_node_id),
+                                                     int(n_rows)),
+                "tsc_index_append_synthetic")
+
+    # -- liveness ----------------------------------------------------------------
+    def set_deleted(self, node_ids, deleted: bool = True) -> None:
+        ids = np.ascontiguousarray(node_ids, dtype=np.uint64)
+        N.check(self._lib.tsc_index_set_deleted(self.handle, ids.ctypes.data, ids.size,
+                                                1 if deleted else 0), "tsc_index_set_deleted")
+
+    def apply_graph_pages(self, pages: bytes, first_logical_page: int, page_size: int) -> None:
+        buf = np.frombuffer(pages, dtype=np.uint8)
+        N.check(self._lib.tsc_index_apply_graph_pages(self.handle, int(first_logical_page),
+                                                      buf.ctypes.data, buf.size // page_size,
+                                                      int(page_size)),
+                "tsc_index_apply_graph_pages")
+
+    def set_filter(self, mask) -> None:
+        """mask: bool[rows] (True = row may be returned) or None to clear."""
+        if mask is None:
+            N.check(self._lib.tsc_index_set_filter(self.handle, None, 0), "tsc_index_set_filter")
+            return
+        m = np.asarray(mask, dtype=bool)
+        padded = np.zeros(((m.size + 63) // 64) * 64, dtype=bool)
+        padded[: m.size] = m
+        words = np.packbits(padded.reshape(-1, 8), axis=1, bitorder="little").reshape(-1)
+        words = words.view(np.uint64).copy()
+        N.check(self._lib.tsc_index_set_filter(self.handle, words.ctypes.data, words.size),
+                "tsc_index_set_filter")
+
+    # -- search --------------------------------------------------------------------
+    def search(self, queries, k: int, threshold: Optional[float] = None):
+        """queries: fp32 [nq, dims] (prepared as the reference prepares them).
+        Returns (ids int64 [nq,k] -1 padded, dist float64 [nq,k], counts uint32 [nq])."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dims:
+            raise ValueError(f"queries must be [nq, {self.dims}]")
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        counts = np.empty(nq, dtype=np.uint32)
+        thr = math.nan if threshold is None else float(threshold)
+        N.check(self._lib.tsc_search(self.handle, q.ctypes.data, nq, k, thr, ids.ctypes.data,
+                                     dist.ctypes.data, counts.ctypes.data), "tsc_search")
+        return ids, dist, counts
+
+    def search_async(self, queries, k: int, threshold: Optional[float] = None):
+        """submit / poll pair; returns a callable `poll()` -> None | (ids, dist, counts)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dims)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        counts = np.empty(nq, dtype=np.uint32)
+        t = C.c_uint64(0)
+        thr = math.nan if threshold is None else float(threshold)
+        N.check(self._lib.tsc_search_submit(self.handle, q.ctypes.data, nq, k, thr,
+                                            ids.ctypes.data, dist.ctypes.data, counts.ctypes.data,
+                                            C.byref(t)), "tsc_search_submit")
+        keep = (q,)
+
+        def poll(block: bool = False):
+            _ = keep
+            if block:
+                N.check(self._lib.tsc_search_wait(t.value), "tsc_search_wait")
+                return ids, dist, counts
+            done = C.c_int32(0)
+            N.check(self._lib.tsc_search_poll(t.value, C.byref(done)), "tsc_search_poll")
+            return (ids, dist, counts) if done.value else None
+
+        return poll
+
+    def search_device(self, d_queries: int, nq: int, k: int, d_ids: int, d_dist: int,
+                      d_counts: int, threshold: Optional[float] = None, stream: int = 0,
+                      sharded: bool = False) -> None:
+        """Raw device pointers (ints); asynchronous on `stream` (0 = index stream)."""
+        thr = math.nan if threshold is None else float(threshold)
+        fn = self._lib.tsc_search_sharded if sharded else self._lib.tsc_search_device
+        N.check(fn(self.handle, d_queries, nq, k, thr, d_ids, d_dist, d_counts, stream or None),
+                "tsc_search_sharded" if sharded else "tsc_search_device")
+
+    def vector_search(self, values, k: int, threshold: Optional[float] = None):
+        """fp64 query of any length -> (ids, dist, score) with the reference's
+        query preparation and score mapping done inside the library."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        ids = np.empty(k, dtype=np.int64)
+        dist = np.empty(k, dtype=np.float64)
+        score = np.empty(k, dtype=np.float64)
+        cnt = C.c_uint32(0)
+        thr = math.nan if threshold is None else float(threshold)
+        N.check(self._lib.tsc_vector_search(self.handle, v.ctypes.data, v.size, k, thr,
+                                            ids.ctypes.data, dist.ctypes.data, score.ctypes.data,
+                                            C.byref(cnt)), "tsc_vector_search")
+        n = cnt.value
+        return ids[:n], dist[:n], score[:n]
+
+    # -- sharding --------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        N.check(N.lib().tsc_comm_unique_id(buf), "tsc_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, n_ranks: int, rank: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        N.check(self._lib.tsc_comm_init(self.handle, buf, n_ranks, rank), "tsc_comm_init")
+
+    def merge_shards(self, d_part_ids: int, d_part_dist: int, n_parts: int, nq: int, k: int,
+                     d_ids: int, d_dist: int, d_counts: int, stream: int = 0) -> None:
+        N.check(self._lib.tsc_merge_shards(self.handle, d_part_ids, d_part_dist, n_parts, nq, k,
+                                           d_ids, d_dist, d_counts, stream or None),
+                "tsc_merge_shards")
+
+    # -- observability -----------------------------------------------------------------
+    def stats(self) -> N.Stats:
+        s = N.Stats(struct_size=C.sizeof(N.Stats))
+        N.check(self._lib.tsc_stats_get(self.handle, C.byref(s)), "tsc_stats_get")
+        return s
+
+    def stats_reset(self) -> None:
+        N.check(self._lib.tsc_stats_reset(self.handle), "tsc_stats_reset")
+
+    def device_rows(self):
+        p, n, stride = C.c_void_p(0), C.c_uint64(0), C.c_uint64(0)
+        N.check(self._lib.tsc_index_device_rows(self.handle, C.byref(p), C.byref(n),
+                                                C.byref(stride)), "tsc_index_device_rows")
+        return p.value, n.value, stride.value

@@ -1,0 +1,239 @@
+"""Host mirror of ToStore's vector API for the GPU path.
+
+Keeps the reference's names, argument meaning and error behaviour for the hot
+path only (citations relative to /root/reference/lib):
+
+  * `VectorData`, `VectorFieldConfig`, `VectorPrecision`, `VectorDistanceMetric`,
+    `VectorIndexConfig`                     src/model/table_schema.dart:2109-2675
+  * `VectorSearchResult`                    src/model/query_result.dart:207-228
+  * `ToStore.vectorSearch(tableName, fieldName:, queryVector:, topK: 10,
+    efSearch:, distanceThreshold:)`         tostore.dart:493-511
+  * `VectorIndexManager.vectorSearch / writeChanges`
+                                            src/core/vector_index_manager.dart:297-589
+
+What is *not* here: tables, B+Trees, WAL, transactions, schema migration. Rows
+become visible to search as soon as they are appended (the reference makes them
+visible at flush); nodeId = insertion order, exactly as
+`meta.nextNodeId++` (src/core/ngh_graph_engine.dart:321-322). The nodeId -> primary
+key B+Tree of the reference (`__nid2pk`) is a dense host-side list here.
+
+The Dart production binding is dart/tostore_cuda_bindings.dart; this module is
+the equivalent host layer in the one host language this image can run.
+"""
+from __future__ import annotations
+
+import enum
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from .engine import GpuVectorIndex
+
+
+class VectorPrecision(enum.IntEnum):       # table_schema.dart:2481-2498 (enum order)
+    float64 = 0
+    float32 = 1
+    int8 = 2
+
+
+class VectorDistanceMetric(enum.IntEnum):  # table_schema.dart:2511-2531 (enum order)
+    l2 = 0
+    innerProduct = 1
+    cosine = 2
+
+
+class DeviceDType(enum.IntEnum):           # new: storage type of the column in HBM
+    float32 = 0
+    bfloat16 = 1
+    float16 = 2
+
+
+@dataclass(frozen=True)
+class VectorData:                          # table_schema.dart:2109-2401
+    values: Sequence[float]
+
+    @staticmethod
+    def fromList(values: Iterable[float]) -> "VectorData":
+        return VectorData(tuple(float(v) for v in values))
+
+    @property
+    def dimensions(self) -> int:
+        return len(self.values)
+
+
+@dataclass(frozen=True)
+class VectorFieldConfig:                   # table_schema.dart:2406-2475
+    dimensions: int
+    precision: VectorPrecision = VectorPrecision.float64
+
+
+@dataclass(frozen=True)
+class VectorIndexConfig:                   # table_schema.dart:2547-2597
+    distanceMetric: VectorDistanceMetric = VectorDistanceMetric.cosine
+    maxDegree: Optional[int] = None        # accepted for API compatibility; the
+    efSearch: Optional[int] = None         # exact scan has no graph and ignores
+    constructionEf: Optional[int] = None   # these four
+    pruneAlpha: Optional[float] = None
+    pqSubspaces: Optional[int] = None
+
+
+@dataclass(frozen=True)
+class VectorSearchResult:                  # query_result.dart:207-228
+    primaryKey: str
+    distance: float
+    score: float
+
+    def toJson(self) -> Dict[str, object]:
+        return {"primaryKey": self.primaryKey, "distance": self.distance, "score": self.score}
+
+
+@dataclass
+class _VectorIndex:
+    table: str
+    fieldName: str
+    field: VectorFieldConfig
+    config: VectorIndexConfig
+    engine: GpuVectorIndex
+    nid2pk: List[Optional[str]] = field(default_factory=list)   # role of `__nid2pk`
+    pk2nid: Dict[str, int] = field(default_factory=dict)        # role of `__pk2nid`
+
+
+class GpuVectorStore:
+    """The slice of `ToStore` / `VectorIndexManager` that serves `vectorSearch`."""
+
+    def __init__(self, device_id: int = 0, capacity_rows: int = 1 << 20,
+                 device_dtype: DeviceDType = DeviceDType.float32, k_max: int = 128):
+        self._device_id = device_id
+        self._capacity = capacity_rows
+        self._dtype = device_dtype
+        self._k_max = k_max
+        self._indexes: Dict[str, List[_VectorIndex]] = {}
+
+    # -- schema -------------------------------------------------------------------------
+    def createVectorIndex(self, tableName: str, fieldName: str, fieldConfig: VectorFieldConfig,
+                          indexConfig: Optional[VectorIndexConfig] = None) -> None:
+        """`TableSchema` vector field + `IndexSchema(type: IndexType.vector)`.
+        Unlike the reference (no validation) bad dims raise."""
+        cfg = indexConfig or VectorIndexConfig()
+        eng = GpuVectorIndex(fieldConfig.dimensions, int(cfg.distanceMetric),
+                             capacity_rows=self._capacity, src_precision=1,
+                             dev_dtype=int(self._dtype), device_id=self._device_id,
+                             k_max=self._k_max, nq_max=64)
+        self._indexes.setdefault(tableName, []).append(
+            _VectorIndex(tableName, fieldName, fieldConfig, cfg, eng))
+
+    def _find(self, tableName: str, fieldName: str) -> Optional[_VectorIndex]:
+        for ix in self._indexes.get(tableName, ()):      # vector_index_manager.dart:484-499
+            if ix.fieldName == fieldName:
+                return ix
+        return None
+
+    # -- writes (VectorIndexManager.writeChanges, :297-466) -----------------------------
+    @staticmethod
+    def _to_float32(values, dims: int) -> np.ndarray:
+        """`_toFloat32` (compute/vector_batch_prepare_compute.dart:79-86): truncate or
+        zero-pad, fp64 -> fp32 round-to-nearest-even."""
+        out = np.zeros(dims, dtype=np.float32)
+        v = np.asarray(values.values if isinstance(values, VectorData) else values,
+                       dtype=np.float64)[:dims]
+        with np.errstate(over="ignore"):
+            out[: v.size] = v.astype(np.float32)
+        return out
+
+    @staticmethod
+    def _store_round_trip(rows: np.ndarray, precision: VectorPrecision) -> np.ndarray:
+        """What the reference keeps on disk for `precision` and reads back as fp32
+        (`setVectorFromFloat32` / `getVectorAsFloat32`, core/ngh_page.dart:368-412)."""
+        if precision == VectorPrecision.int8:
+            c = np.clip(rows.astype(np.float64), -1.0, 1.0) * 127.0
+            q = np.where(c >= 0, np.floor(c + 0.5), np.ceil(c - 0.5))
+            return (q / 127.0).astype(np.float32)
+        return rows                                     # f32 exact; f64 holds the fp32 value
+
+    def batchInsert(self, tableName: str, records: Sequence[Dict[str, object]],
+                    primaryKey: str = "id") -> int:
+        """Insert records; every vector index of the table receives the rows.
+        Records without the vector field or with an empty key are skipped
+        (`prepareVectorBatchChunk`, compute/vector_batch_prepare_compute.dart:34-67)."""
+        n_done = 0
+        for ix in self._indexes.get(tableName, ()):
+            vecs, pks = [], []
+            for rec in records:
+                val = rec.get(ix.fieldName)
+                if val is None:
+                    continue
+                pk = rec.get(primaryKey)
+                if pk is None or str(pk) == "":
+                    continue
+                vecs.append(self._to_float32(val, ix.field.dimensions))
+                pks.append(str(pk))
+            if not vecs:
+                continue
+            rows = self._store_round_trip(np.stack(vecs), ix.field.precision)
+            start = len(ix.nid2pk)                      # startNodeId = meta.nextNodeId
+            ix.engine.append_rows(rows, first_node_id=start)
+            for j, pk in enumerate(pks):
+                ix.nid2pk.append(pk)
+                ix.pk2nid[pk] = start + j
+            n_done = max(n_done, len(vecs))
+        return n_done
+
+    def insert(self, tableName: str, record: Dict[str, object], primaryKey: str = "id") -> int:
+        return self.batchInsert(tableName, [record], primaryKey)
+
+    def delete(self, tableName: str, primaryKeys: Iterable[object]) -> int:
+        """Tombstone rows (deleteBatch, ngh_graph_engine.dart:411-445; mapping
+        tombstone, vector_index_manager.dart:416-434)."""
+        n = 0
+        for ix in self._indexes.get(tableName, ()):
+            nids = []
+            for pk in primaryKeys:
+                nid = ix.pk2nid.pop(str(pk), None)
+                if nid is not None:
+                    ix.nid2pk[nid] = None
+                    nids.append(nid)
+            if nids:
+                ix.engine.set_deleted(nids, True)
+                n = max(n, len(nids))
+        return n
+
+    def setWhereFilter(self, tableName: str, fieldName: str,
+                       primaryKeys: Optional[Iterable[object]]) -> None:
+        """WHERE prefilter (new, additive): restrict the next searches to these keys."""
+        ix = self._find(tableName, fieldName)
+        if ix is None:
+            return
+        if primaryKeys is None:
+            ix.engine.set_filter(None)
+            return
+        mask = np.zeros(len(ix.nid2pk), dtype=bool)
+        for pk in primaryKeys:
+            nid = ix.pk2nid.get(str(pk))
+            if nid is not None:
+                mask[nid] = True
+        ix.engine.set_filter(mask)
+
+    # -- ToStore.vectorSearch (tostore.dart:493-511) --------------------------------------
+    def vectorSearch(self, tableName: str, *, fieldName: str, queryVector: VectorData,
+                     topK: int = 10, efSearch: Optional[int] = None,
+                     distanceThreshold: Optional[float] = None) -> List[VectorSearchResult]:
+        ix = self._find(tableName, fieldName)
+        if ix is None or not ix.nid2pk:                  # :485-504 -> const []
+            return []
+        _ = efSearch                                     # exact scan: no expansion factor
+        values = queryVector.values if isinstance(queryVector, VectorData) else queryVector
+        ids, dist, score = ix.engine.vector_search(values, topK, distanceThreshold)
+        out = []
+        for nid, d, s in zip(ids.tolist(), dist.tolist(), score.tolist()):
+            pk = ix.nid2pk[nid] if 0 <= nid < len(ix.nid2pk) else None
+            if pk is None:                               # :578-579 (deleted / unmapped)
+                continue
+            out.append(VectorSearchResult(primaryKey=pk, distance=d, score=s))
+        return out                                       # already ascending (:587)
+
+    def close(self) -> None:
+        for lst in self._indexes.values():
+            for ix in lst:
+                ix.engine.close()
+        self._indexes.clear()
