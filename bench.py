@@ -204,7 +204,10 @@ def run_b200(args):
     o_ids = torch.empty((nqs, k), dtype=torch.int64, device="cuda")
     o_dist = torch.empty((nqs, k), dtype=torch.float64, device="cuda")
     o_cnt = torch.empty((nqs,), dtype=torch.int32, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: every kernel of the timed region is launched on
+    # it and the CUDA events that time the region are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
     esz = q_dev.element_size() * d
 

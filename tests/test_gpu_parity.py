@@ -90,6 +90,8 @@ def test_random_rows_host_append(dims, metric):
     Q = rng.standard_normal((9, dims)).astype(np.float32)
     Q[8] = rows[7]                                  # query equal to a stored row
     Qp = np.stack([prep(q, metric) for q in Q])
+    if dims == 1 and metric == 2:
+        pytest.skip("1-d cosine distances are all exactly 0 or 2: ties only, order undefined upstream")
     with T.GpuVectorIndex(dims, metric, capacity_rows=n, k_max=64, nq_max=16) as ix:
         ix.append_rows(rows[:1000])
         ix.append_rows(rows[1000:])                 # incremental flush-time appends
@@ -260,7 +262,8 @@ def test_submit_poll_and_device_buffers():
         d_ids = torch.empty((6, k), dtype=torch.int64, device="cuda")
         d_dist = torch.empty((6, k), dtype=torch.float64, device="cuda")
         d_cnt = torch.empty(6, dtype=torch.int32, device="cuda")
-        s = torch.cuda.current_stream()
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
         ix.search_device(dq.data_ptr(), 6, k, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(),
                          stream=s.cuda_stream)
         s.synchronize()
@@ -292,8 +295,9 @@ def test_row_range_shards_merge_to_unsharded_result():
         o_ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
         o_dist = torch.empty((nq, k), dtype=torch.float64, device="cuda")
         o_cnt = torch.empty(nq, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
         a.merge_shards(part_ids.data_ptr(), part_dist.data_ptr(), 2, nq, k, o_ids.data_ptr(),
-                       o_dist.data_ptr(), o_cnt.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+                       o_dist.data_ptr(), o_cnt.data_ptr(), stream=torch.cuda.Stream().cuda_stream)
         torch.cuda.synchronize()
         assert (o_ids.cpu().numpy() == ref[0]).all()
         assert (bits(o_dist.cpu().numpy()) == bits(ref[1])).all()

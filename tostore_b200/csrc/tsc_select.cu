@@ -11,10 +11,10 @@ static int32_t run_select(Index *ix, const SelectParams &p, uint32_t nq, cudaStr
   size_t smem = select_smem_bytes(p.sort_cap, p.qld);
   if (!attr_done[ix->device & 63]) {
     TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kSelectSortMax * sizeof(Pair128) + 64 * 1024)));
+                                  (int)ix->smem_optin - 16 * 1024));
     attr_done[ix->device & 63] = true;
   }
-  if (smem > kSelectSortMax * sizeof(Pair128) + 64 * 1024) {
+  if (smem > ix->smem_optin - 16 * 1024) {
     set_error("select: dims too large for the re-rank staging (%zu B)", smem);
     return TSC_ERR_BAD_DIMS;
   }

@@ -37,9 +37,12 @@ struct SelectParams {
   uint32_t sort_cap;        // pow2 >= m when m <= kSelectSortMax, else pow2 >= kprime
 };
 
-constexpr uint32_t kSelectSortMax = 4096;  // M above this goes through radix select
+constexpr uint32_t kSelectSortMax = 1024;  // M above this goes through radix select
 constexpr uint32_t kMaxRerank = 512;
 constexpr int kSelectThreads = 512;
+constexpr int kSelectWarps = kSelectThreads / 32;
+constexpr int kRadixBins = 2048;   // 11-bit digits
+constexpr int kProdChunk = 64;     // elements whose products one warp stages at a time
 
 struct Pair128 {
   uint64_t hi, lo;
@@ -76,56 +79,164 @@ __device__ __forceinline__ float load_elem(const uint8_t *row, uint32_t i) {
   return __half2float(reinterpret_cast<const __half *>(row)[i]);
 }
 
-// `_exactDistance` (ngh_graph_engine.dart:908-918) for one stored row.
+// `_exactDistance` (core/ngh_graph_engine.dart:908-946) for one stored row, by one
+// warp. Every product is an individually rounded IEEE double multiply, so the
+// lanes may compute them in parallel; the additions are then applied strictly
+// left to right (i = 0..d-1, starting from +0.0) by a single lane per running
+// sum, which is what makes the result bit-identical to the Dart loop. Products
+// are staged through shared memory in chunks of kProdChunk, double buffered so
+// the next chunk's global loads overlap the current chunk's add chain.
+//   pbuf: [2 buffers][2 arrays][kProdChunk] doubles, private to the warp
+//   mag_a: sum of q[i]^2 (cosine only; the same for every candidate of a query)
 template <int DTYPE>
-__device__ double exact_distance(const float *q, const uint8_t *row, uint32_t d, int metric) {
-  if (metric == kL2) {  // :920-927
-    double sum = 0.0;
-    for (uint32_t i = 0; i < d; i++) {
-      double diff = __dsub_rn((double)q[i], (double)load_elem<DTYPE>(row, i));
-      sum = __dadd_rn(sum, __dmul_rn(diff, diff));
+__device__ double warp_exact_distance(const float *q, const uint8_t *row, uint32_t d, int metric,
+                                      double mag_a, double *pbuf, int lane) {
+  constexpr int PER = kProdChunk / 32;
+  double s0 = 0.0, s1 = 0.0;  // lane 0: dot / l2 sum, lane 1: magB
+  const uint32_t nchunk = (d + kProdChunk - 1) / kProdChunk;
+  float bv[PER];
+  auto fetch = [&](uint32_t c) {
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      uint32_t i = c * kProdChunk + j * 32 + lane;
+      bv[j] = i < d ? load_elem<DTYPE>(row, i) : 0.0f;
     }
-    return sqrt(sum);
+  };
+  fetch(0);
+  for (uint32_t c = 0; c < nchunk; c++) {
+    double *p0 = pbuf + (size_t)(c & 1) * 2 * kProdChunk;
+    double *p1 = p0 + kProdChunk;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+      uint32_t e = j * 32 + lane, i = c * kProdChunk + e;
+      double a = i < d ? (double)q[i] : 0.0, b = (double)bv[j];
+      if (metric == kL2) {
+        double diff = __dsub_rn(a, b);
+        p0[e] = __dmul_rn(diff, diff);
+      } else {
+        p0[e] = __dmul_rn(a, b);
+        if (metric == kCos) p1[e] = __dmul_rn(b, b);
+      }
+    }
+    __syncwarp();
+    if (c + 1 < nchunk) fetch(c + 1);
+    const uint32_t n = min((uint32_t)kProdChunk, d - c * kProdChunk);
+    if (lane < 2) {  // lane 0: dot / l2 chain, lane 1: magB chain, in lockstep
+      const double *src = lane == 0 ? p0 : p1;
+      double acc = lane == 0 ? s0 : s1;
+      if (lane == 0 || metric == kCos) {
+#pragma unroll 8
+        for (uint32_t e = 0; e < n; e++) acc = __dadd_rn(acc, src[e]);
+      }
+      if (lane == 0) s0 = acc; else s1 = acc;
+    }
+    // the buffer written next iteration is the other one; the one after that is
+    // this one again, and by then every lane has passed the __syncwarp above
   }
-  if (metric == kIP) {  // :929-935, negated at :914
-    double sum = 0.0;
-    for (uint32_t i = 0; i < d; i++)
-      sum = __dadd_rn(sum, __dmul_rn((double)q[i], (double)load_elem<DTYPE>(row, i)));
-    return -sum;
-  }
-  double dot = 0.0, ma = 0.0, mb = 0.0;  // :937-946
-  for (uint32_t i = 0; i < d; i++) {
-    double a = (double)q[i], b = (double)load_elem<DTYPE>(row, i);
-    dot = __dadd_rn(dot, __dmul_rn(a, b));
-    ma = __dadd_rn(ma, __dmul_rn(a, a));
-    mb = __dadd_rn(mb, __dmul_rn(b, b));
-  }
-  double denom = __dmul_rn(sqrt(ma), sqrt(mb));
-  double sim = denom > 0.0 ? __ddiv_rn(dot, denom) : 0.0;
+  s1 = __shfl_sync(0xFFFFFFFFu, s1, 1);
+  s0 = __shfl_sync(0xFFFFFFFFu, s0, 0);
+  if (metric == kL2) return sqrt(s0);                      // :920-927
+  if (metric == kIP) return -s0;                           // :929-935, negated at :914
+  double denom = __dmul_rn(sqrt(mag_a), sqrt(s1));         // :937-946
+  double sim = denom > 0.0 ? __ddiv_rn(s0, denom) : 0.0;
   return __dsub_rn(1.0, sim);
 }
 
-// dynamic smem: Pair128[sort_cap] | float q[qld] (+ small statics)
+// sum of q[i]^2, sequential (magA of _cosineSimlarity); q padded with zeros
+__device__ double warp_mag_a(const float *q, uint32_t d, double *pbuf, int lane) {
+  double s = 0.0;
+  for (uint32_t c0 = 0; c0 < d; c0 += kProdChunk) {
+    for (int e = lane; e < kProdChunk; e += 32) {
+      double a = (c0 + e) < d ? (double)q[c0 + e] : 0.0;
+      pbuf[e] = __dmul_rn(a, a);
+    }
+    __syncwarp();
+    uint32_t n = min((uint32_t)kProdChunk, d - c0);
+    if (lane == 0)
+      for (uint32_t e = 0; e < n; e++) s = __dadd_rn(s, pbuf[e]);
+    __syncwarp();
+  }
+  return __shfl_sync(0xFFFFFFFFu, s, 0);
+}
+
+// dynamic smem: Pair128[sort_cap] | double pbuf[warps][4*kProdChunk] | float q[qld]
 __host__ __device__ inline size_t select_smem_bytes(uint32_t sort_cap, uint32_t qld) {
-  return (size_t)sort_cap * sizeof(Pair128) + (size_t)qld * 4 + 16;
+  return (size_t)sort_cap * sizeof(Pair128) + (size_t)kSelectWarps * 4 * kProdChunk * 8 +
+         (size_t)qld * 4 + 16;
+}
+
+// One radix-select digit pass over the composites: histogram the `bits`-wide digit
+// at `shift` of every entry matching (prefix, mask); warp 0 finds the bucket where
+// the running count crosses s_remaining and narrows the prefix.
+__device__ __forceinline__ void radix_pass(const uint64_t *cand, uint32_t m, int shift, int bits,
+                                           uint64_t mask, uint32_t *hist, uint64_t *s_prefix,
+                                           uint32_t *s_remaining, uint32_t *s_bucket_count) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nb = 1u << bits;
+  for (uint32_t i = tid; i < nb; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const uint64_t prefix = *s_prefix;
+  for (uint32_t i = tid; i < m; i += blockDim.x) {
+    uint64_t v = cand[i];
+    if ((v & mask) == prefix) atomicAdd(&hist[(uint32_t)(v >> shift) & (nb - 1)], 1u);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t per = nb / 32;  // buckets per lane (nb >= 32)
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per; i++) sum += hist[tid * per + i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if ((int)tid >= o) inc += t;
+    }
+    const uint32_t exc = inc - sum, rem = *s_remaining;
+    if (exc < rem && rem <= inc) {  // exactly one lane: m >= remaining entries match
+      uint32_t cum = exc, b = tid * per;
+      for (uint32_t i = 0; i < per; i++) {
+        uint32_t h = hist[tid * per + i];
+        if (cum + h >= rem) {
+          b = tid * per + i;
+          *s_bucket_count = h;
+          break;
+        }
+        cum += h;
+      }
+      *s_remaining = rem - cum;
+      *s_prefix = prefix | ((uint64_t)b << shift);
+    }
+  }
+  __syncthreads();
 }
 
 template <int DTYPE>
 __global__ void __launch_bounds__(kSelectThreads) select_rerank_kernel(const SelectParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   Pair128 *buf = reinterpret_cast<Pair128 *>(smem);
-  float *qs = reinterpret_cast<float *>(smem + (size_t)p.sort_cap * sizeof(Pair128));
-  __shared__ uint32_t hist[256];
+  double *pbuf_all = reinterpret_cast<double *>(smem + (size_t)p.sort_cap * sizeof(Pair128));
+  float *qs = reinterpret_cast<float *>(pbuf_all + (size_t)kSelectWarps * 4 * kProdChunk);
+  __shared__ uint32_t hist[kRadixBins];
   __shared__ uint64_t s_prefix;
-  __shared__ uint32_t s_remaining, s_count;
+  __shared__ uint32_t s_remaining, s_count, s_bucket;
+  __shared__ double s_mag_a;
 
   const uint32_t q = blockIdx.x;
   const uint64_t *cand = p.cand + (size_t)q * p.m;
   const uint32_t tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  double *pbuf = pbuf_all + (size_t)warp * 4 * kProdChunk;
 
   for (uint32_t i = tid; i < p.qld; i += blockDim.x) qs[i] = p.queries[(size_t)q * p.qld + i];
+  if (tid == 0) {
+    s_prefix = 0;
+    s_remaining = p.kprime;
+    s_count = 0;
+    s_bucket = 0;
+  }
+  __syncthreads();
 
-  // ---- 1. K' best composites -> buf[0 .. ncand) ------------------------------
+  // ---- 1. K' best composites -> buf[0 .. ncand).hi (unordered) ------------------
   uint32_t ncand;
   if (p.m <= kSelectSortMax) {
     for (uint32_t i = tid; i < p.sort_cap; i += blockDim.x) {
@@ -136,56 +247,21 @@ __global__ void __launch_bounds__(kSelectThreads) select_rerank_kernel(const Sel
     bitonic_sort_pairs(buf, p.sort_cap);
     ncand = p.kprime < p.m ? p.kprime : p.m;
   } else {
-    // radix select, 8 bits per pass from the top: the K'-th smallest composite
-    if (tid == 0) {
-      s_prefix = 0;
-      s_remaining = p.kprime;
-      s_count = 0;
+    // radix select of the K'-th smallest composite: three 11/11/10-bit passes over
+    // the key half; the id half is only walked when the pivot key is shared by
+    // more entries than are still needed (ties at the cut).
+    radix_pass(cand, p.m, 53, 11, 0ull, hist, &s_prefix, &s_remaining, &s_bucket);
+    radix_pass(cand, p.m, 42, 11, ~0ull << 53, hist, &s_prefix, &s_remaining, &s_bucket);
+    radix_pass(cand, p.m, 32, 10, ~0ull << 42, hist, &s_prefix, &s_remaining, &s_bucket);
+    uint64_t pivot;
+    if (s_bucket == s_remaining) {
+      pivot = s_prefix | 0xFFFFFFFFull;
+    } else {
+      radix_pass(cand, p.m, 21, 11, ~0ull << 32, hist, &s_prefix, &s_remaining, &s_bucket);
+      radix_pass(cand, p.m, 10, 11, ~0ull << 21, hist, &s_prefix, &s_remaining, &s_bucket);
+      radix_pass(cand, p.m, 0, 10, ~0ull << 10, hist, &s_prefix, &s_remaining, &s_bucket);
+      pivot = s_prefix;
     }
-    for (int pass = 0; pass < 8; pass++) {
-      const int shift = 56 - 8 * pass;
-      for (uint32_t i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-      __syncthreads();
-      const uint64_t prefix = s_prefix;
-      const uint64_t mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-      for (uint32_t i = tid; i < p.m; i += blockDim.x) {
-        uint64_t v = cand[i];
-        if ((v & mask) == prefix) atomicAdd(&hist[(v >> shift) & 0xFF], 1u);
-      }
-      __syncthreads();
-      if (tid < 32) {
-        // warp 0: each lane owns 8 buckets; find the bucket where the running
-        // count crosses the remaining rank (it exists: m >= kprime entries match)
-        uint32_t loc[8], sum = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          loc[i] = hist[tid * 8 + i];
-          sum += loc[i];
-        }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-          if ((int)tid >= o) inc += t;
-        }
-        const uint32_t exc = inc - sum, rem = s_remaining;
-        if (exc < rem && rem <= inc) {
-          uint32_t cum = exc, b = tid * 8;
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            if (cum + loc[i] >= rem) {
-              b = tid * 8 + i;
-              break;
-            }
-            cum += loc[i];
-          }
-          s_remaining = rem - cum;
-          s_prefix = prefix | ((uint64_t)b << shift);
-        }
-      }
-      __syncthreads();
-    }
-    const uint64_t pivot = s_prefix;
     for (uint32_t i = tid; i < p.sort_cap; i += blockDim.x) {
       buf[i].hi = ~0ull;
       buf[i].lo = 0;
@@ -203,31 +279,39 @@ __global__ void __launch_bounds__(kSelectThreads) select_rerank_kernel(const Sel
   }
   __syncthreads();
 
-  // ---- 2. exact fp64 re-rank, one thread per candidate ------------------------
-  // (spread over warps so the sequential fp64 chains run on all four schedulers)
-  {
-    const uint32_t nwarps = blockDim.x >> 5;
-    const uint32_t c = (tid & 31) * nwarps + (tid >> 5);  // candidate index for this thread
-    for (uint32_t i = c; i < p.sort_cap; i += blockDim.x) {
-      uint64_t v = buf[i].hi;
-      uint32_t row = (uint32_t)v;
-      if (i < ncand && row != kInvalidRow) {
-        double d = exact_distance<DTYPE>(qs, p.rows + (size_t)row * p.row_bytes, p.dims, p.metric);
-        bool drop = (p.threshold == p.threshold) && (d > p.threshold);
-        buf[i].hi = drop ? ~0ull : ordered_key64(d);
-        buf[i].lo = drop ? ~0ull : (uint64_t)row;
-      } else {
-        buf[i].hi = ~0ull;
-        buf[i].lo = ~0ull;
+  // ---- 2. exact fp64 re-rank, one warp per candidate ---------------------------------
+  if (p.metric == kCos) {
+    if (warp == 0) {
+      double m = warp_mag_a(qs, p.dims, pbuf, lane);
+      if (lane == 0) s_mag_a = m;
+    }
+    __syncthreads();
+  }
+  const double mag_a = p.metric == kCos ? s_mag_a : 0.0;
+  for (uint32_t i = warp; i < p.sort_cap; i += kSelectWarps) {
+    uint64_t v = buf[i].hi;
+    uint32_t row = (uint32_t)v;
+    uint64_t hi = ~0ull, lo = ~0ull;
+    if (i < ncand && row != kInvalidRow) {
+      double d = warp_exact_distance<DTYPE>(qs, p.rows + (size_t)row * p.row_bytes, p.dims,
+                                            p.metric, mag_a, pbuf, lane);
+      bool drop = (p.threshold == p.threshold) && (d > p.threshold);  // :127
+      if (!drop) {
+        hi = ordered_key64(d);
+        lo = (uint64_t)row;
       }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      buf[i].hi = hi;
+      buf[i].lo = lo;
     }
   }
   __syncthreads();
 
-  // ---- 3. final order + emit ----------------------------------------------------
-  uint32_t n2 = 1;
+  // ---- 3. final order + emit -------------------------------------------------------------
+  uint32_t n2 = 2;
   while (n2 < ncand) n2 <<= 1;
-  if (n2 < 2) n2 = 2;
   if (n2 > p.sort_cap) n2 = p.sort_cap;
   bitonic_sort_pairs(buf, n2);
   if (tid == 0) s_count = 0;
