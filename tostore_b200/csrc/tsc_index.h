@@ -28,7 +28,8 @@ struct ScanConfig {
   int warps = 8;       // warps per CTA
   int rows = 0;        // R rows per stage (0 = auto)
   int stages = 0;      // S (0 = auto)
-  int stage_target = 8192;  // bytes per stage aimed for when R is auto
+  int stage_target = 6144;  // bytes per stage aimed for when R is auto
+  int inflight_target = 96 * 1024;  // bytes of bulk copies in flight per CTA when S is auto
 };
 
 struct Index {

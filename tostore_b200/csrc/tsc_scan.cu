@@ -17,7 +17,8 @@ int32_t scan_configure(Index *ix) {
   ix->scan.warps = env_int("TSC_SCAN_WARPS", 8);
   ix->scan.rows = env_int("TSC_SCAN_ROWS", 0);
   ix->scan.stages = env_int("TSC_SCAN_STAGES", 0);
-  ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 8192);
+  ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 6144);
+  ix->scan.inflight_target = env_int("TSC_SCAN_INFLIGHT_BYTES", 96 * 1024);
   if (ix->scan.warps < 1 || ix->scan.warps > 16 || ix->scan.grid < 1) {
     set_error("bad TSC_SCAN_* override");
     return TSC_ERR_BAD_ARG;
@@ -47,7 +48,15 @@ static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl) {
     size_t per_warp = ((budget - fixed) / w) & ~(size_t)127;
     for (; r >= 1; r >>= 1) {
       uint32_t stage_bytes = (uint32_t)r * ix->row_bytes;
-      int smax = ix->scan.stages > 0 ? ix->scan.stages : 8;
+      // Measured on B200 (profiles/r01_scan_sweep.txt): ~96 KB of bulk copies in
+      // flight per SM is the sweet spot (7.36 TB/s); deeper rings lose 5-10 %.
+      int smax = ix->scan.stages;
+      if (smax <= 0) {
+        smax = (int)((ix->scan.inflight_target + (size_t)w * stage_bytes / 2) /
+                     ((size_t)w * stage_bytes));
+        if (smax < 2) smax = 2;
+        if (smax > 8) smax = 8;
+      }
       int s = smax;
       while (s >= 2 && scan_smem_warp_bytes(qb, kprime, s, stage_bytes) > per_warp) s--;
       if (s >= 2) {
