@@ -199,6 +199,10 @@ int32_t tsc_stats_reset(uint64_t handle);        /* zero the hot_* accumulators 
 int32_t tsc_index_device_rows(uint64_t handle, void **out_ptr, uint64_t *out_rows,
                               uint64_t *out_row_stride_bytes);
 
+/* test hook: fp32 ranking keys the tcgen05 path computes for every (query,row);
+ * out_keys [nq, rows] HOST. Only for 16-bit device dtypes. */
+int32_t tsc_debug_gemm_keys(uint64_t handle, const float *queries, uint32_t nq,
+                            float *out_keys);
 /* self-test hook: the warp-sliced CRC-32 of the page validator, re-enacted on the
  * host (no GPU needed); must equal CRC-32/IEEE (Crc32.of, btree_page.dart:64-89). */
 uint32_t tsc_selftest_crc32(const uint8_t *data, uint32_t len);

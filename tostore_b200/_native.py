@@ -23,6 +23,7 @@ EXPORTS = (
     "tsc_search_device", "tsc_vector_search", "tsc_merge_shards",
     "tsc_comm_unique_id", "tsc_comm_init", "tsc_search_sharded",
     "tsc_stats_get", "tsc_stats_reset", "tsc_index_device_rows", "tsc_selftest_crc32",
+    "tsc_debug_gemm_keys",
 )
 
 TSC_OK = 0
@@ -101,6 +102,7 @@ def lib():
     L.tsc_stats_get.argtypes = [u64, C.POINTER(Stats)]
     L.tsc_stats_reset.argtypes = [u64]
     L.tsc_index_device_rows.argtypes = [u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
+    L.tsc_debug_gemm_keys.argtypes = [u64, vp, u32, vp]
     L.tsc_selftest_crc32.argtypes = [vp, u32]
     L.tsc_selftest_crc32.restype = u32
     for name in EXPORTS:

@@ -70,6 +70,8 @@ static void free_index(Index *ix) {
   cudaFree(ix->d_live);
   cudaFree(ix->d_delta);
   cudaFree(ix->d_queries);
+  cudaFree(ix->d_norm2);
+  cudaFree(ix->d_q16);
   cudaFree(ix->d_cand);
   cudaFree(ix->d_out_ids);
   cudaFree(ix->d_out_dist);
@@ -172,14 +174,18 @@ static int32_t search_padded(Index *ix, const float *d_q, uint32_t nq, uint32_t 
   const uint32_t kprime = kprime_for(k);
   TSC_CUDA(cudaEventRecord(ix->ev0, st));
   uint32_t lists = 0;
-  rc = launch_scan(ix, d_q, nq, kprime, ix->d_cand, &lists, st);
+  const bool use_gemm = nq >= ix->gemm_min_nq && gemm_supported(ix, kprime);
+  if (use_gemm)
+    rc = launch_gemm(ix, d_q, nq, kprime, ix->d_cand, &lists, nullptr, st);
+  else
+    rc = launch_scan(ix, d_q, nq, kprime, ix->d_cand, &lists, st);
   if (rc != TSC_OK) return rc;
   rc = launch_select(ix, d_q, nq, k, kprime, ix->d_cand, lists * kprime, threshold, d_ids, d_dist,
                      d_counts, st);
   if (rc != TSC_OK) return rc;
   TSC_CUDA(cudaEventRecord(ix->ev1, st));
   ix->searches++;
-  ix->last_path = 1;
+  ix->last_path = use_gemm ? 2 : 1;
   ix->last_ms = -1.0;  // resolved lazily from the events
   uint32_t passes = (nq + 7) / 8;
   if (nq <= 4) passes = 1;
@@ -365,6 +371,11 @@ int32_t tsc_index_create(const tsc_index_desc *d, uint64_t *out_handle) {
   ok(dev_alloc(ix, &ix->d_live, ix->mask_words));
   ok(dev_alloc(ix, &ix->d_delta, 4));
   ok(dev_alloc(ix, &ix->d_queries, (size_t)ix->nq_max * ix->qld));
+  if (d->dev_dtype != TSC_DEV_F32) {
+    ok(dev_alloc(ix, &ix->d_norm2, (size_t)ix->capacity));
+    ok(dev_alloc(ix, &ix->d_q16, (size_t)ix->nq_max * ix->qld));
+  }
+  if (const char *ev = getenv("TSC_GEMM_MIN_NQ")) ix->gemm_min_nq = (uint32_t)atoi(ev);
   ok(dev_alloc(ix, &ix->d_cand, (size_t)ix->nq_max * ix->cand_lists * ix->kprime_max));
   ok(dev_alloc(ix, &ix->d_out_ids, (size_t)ix->nq_max * ix->k_max));
   ok(dev_alloc(ix, &ix->d_out_dist, (size_t)ix->nq_max * ix->k_max));
@@ -479,6 +490,8 @@ int32_t tsc_index_append_rows(uint64_t handle, uint64_t first_node_id, const voi
       TSC_CUDA(cudaStreamSynchronize(ix->stream));  // staging buffer is reused
     }
   }
+  rc = gemm_update_norms(ix, row0, n_rows, ix->stream);
+  if (rc != TSC_OK) return rc;
   TSC_CUDA(cudaStreamSynchronize(ix->stream));
   if (row0 + n_rows > ix->rows) ix->rows = row0 + n_rows;
   return TSC_OK;
@@ -499,6 +512,8 @@ int32_t tsc_index_append_synthetic(uint64_t handle, uint64_t seed, uint64_t firs
       ix->ld, ix->desc.dev_dtype);
   TSC_CUDA(cudaGetLastError());
   ix->launches++;
+  rc = gemm_update_norms(ix, row0, n_rows, ix->stream);
+  if (rc != TSC_OK) return rc;
   TSC_CUDA(cudaStreamSynchronize(ix->stream));
   if (row0 + n_rows > ix->rows) ix->rows = row0 + n_rows;
   return TSC_OK;
@@ -584,6 +599,8 @@ int32_t tsc_index_append_pages(uint64_t handle, uint64_t first_logical_page, con
         ix->d_rows + row0 * ix->row_bytes, ix->row_bytes, ix->ld, ix->desc.dev_dtype);
     TSC_CUDA(cudaGetLastError());
     ix->launches++;
+    rc = gemm_update_norms(ix, row0, hi - lo, ix->stream);
+    if (rc != TSC_OK) return rc;
     TSC_CUDA(cudaStreamSynchronize(ix->stream));
     if (row0 + (hi - lo) > ix->rows) ix->rows = row0 + (hi - lo);
   }
@@ -931,6 +948,49 @@ int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
   return launch_merge(ix, (const int64_t *)ix->d_gather_recv,
                       (const double *)(ix->d_gather_recv + nk * 8), nk * 2, (uint32_t)ix->n_ranks,
                       nq, k, d_out_ids, d_out_dist, d_out_counts, st);
+}
+
+// Test hook: raw fp32 ranking keys of the tensor-core path for every (query, row),
+// so tests can pin the UMMA / TMA / TMEM layouts against a plain matmul.
+int32_t tsc_debug_gemm_keys(uint64_t handle, const float *queries, uint32_t nq, float *out_keys) {
+  Index *ix = lookup(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!queries || !out_keys || nq == 0 || nq > ix->nq_max || ix->rows == 0) {
+    set_error("debug_gemm_keys: bad argument");
+    return TSC_ERR_BAD_ARG;
+  }
+  const uint32_t kprime = kprime_for(1);
+  if (!gemm_supported(ix, kprime)) {
+    set_error("debug_gemm_keys: index has no tensor-core path (fp32 storage)");
+    return TSC_ERR_UNSUPPORTED;
+  }
+  TSC_CUDA(cudaSetDevice(ix->device));
+  const uint32_t dims = ix->desc.dims, qld = ix->qld;
+  for (uint32_t q = 0; q < nq; q++) {
+    memcpy(ix->h_queries + (size_t)q * qld, queries + (size_t)q * dims, (size_t)dims * 4);
+    for (uint32_t c = dims; c < qld; c++) ix->h_queries[(size_t)q * qld + c] = 0.0f;
+  }
+  float *d_keys = nullptr;
+  TSC_CUDA(cudaMalloc((void **)&d_keys, (size_t)nq * ix->rows * 4));
+  cudaStream_t st = ix->stream;
+  int32_t rc = refresh_live(ix, st);
+  cudaError_t e = cudaMemcpyAsync(ix->d_queries, ix->h_queries, (size_t)nq * qld * 4,
+                                  cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_keys, 0xFF, (size_t)nq * ix->rows * 4, st);
+  uint32_t lists = 0;
+  if (rc == TSC_OK && e == cudaSuccess)
+    rc = launch_gemm(ix, ix->d_queries, nq, kprime, ix->d_cand, &lists, d_keys, st);
+  if (rc == TSC_OK && e == cudaSuccess)
+    e = cudaMemcpyAsync(out_keys, d_keys, (size_t)nq * ix->rows * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_keys);
+  if (rc != TSC_OK) return rc;
+  if (e != cudaSuccess) {
+    set_error("debug_gemm_keys: %s", cudaGetErrorString(e));
+    return TSC_ERR_CUDA;
+  }
+  return TSC_OK;
 }
 
 // Host re-enactment of page_check_kernel's warp-sliced CRC-32 (same helpers, 32

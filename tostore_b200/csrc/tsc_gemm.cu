@@ -1,0 +1,138 @@
+// tsc_gemm.cu — host launcher for K2 (tsc_gemm.cuh): TMA tensor maps, tile
+// scheduling geometry, row norms (K4).
+#include <stdlib.h>
+
+#include "tsc_gemm.cuh"
+#include "tsc_index.h"
+
+namespace tsc {
+
+// cuTensorMapEncodeTiled comes from the driver; resolve it at run time so the
+// library links against nothing but the (static) runtime.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int32_t load_encode() {
+  if (g_encode) return TSC_OK;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return TSC_ERR_CUDA;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  return TSC_OK;
+}
+
+// 2-D map over a row-major [rows, ld] 16-bit matrix, box = [box_rows, 64], 128B swizzle
+static int32_t make_map(CUtensorMap *m, int dtype, const void *ptr, uint64_t rows, uint32_t ld,
+                        uint32_t row_bytes, uint32_t box_rows) {
+  cuuint64_t dims[2] = {ld, rows};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)kGemmBK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                        2, const_cast<void *>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu ld=%u", (int)r,
+              (unsigned long long)rows, ld);
+    return TSC_ERR_CUDA;
+  }
+  return TSC_OK;
+}
+
+bool gemm_supported(const Index *ix, uint32_t kprime) {
+  return ix->desc.dev_dtype != TSC_DEV_F32 && kprime <= (uint32_t)kGemmMaxKp && ix->d_norm2 &&
+         ix->d_q16;
+}
+
+int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_t st) {
+  if (!ix->d_norm2 || n == 0) return TSC_OK;
+  unsigned blocks = (unsigned)((n + 7) / 8 < (uint64_t)ix->sm_count * 16 ? (n + 7) / 8
+                                                                       : ix->sm_count * 16);
+  if (ix->desc.dev_dtype == TSC_DEV_BF16)
+    row_norms_kernel<kBF16><<<blocks, 256, 0, st>>>(ix->d_rows, first_row, n, ix->ld,
+                                                    ix->row_bytes, ix->d_norm2);
+  else
+    row_norms_kernel<kF16><<<blocks, 256, 0, st>>>(ix->d_rows, first_row, n, ix->ld,
+                                                   ix->row_bytes, ix->d_norm2);
+  TSC_CUDA(cudaGetLastError());
+  ix->launches++;
+  return TSC_OK;
+}
+
+// d_q: fp32 [nq, qld]. d_cand receives [nq][n_slices][kprime]; *out_lists = n_slices.
+int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
+                    uint32_t *out_lists, float *dbg_keys, cudaStream_t st) {
+  int32_t rc = load_encode();
+  if (rc != TSC_OK) return rc;
+  const int dtype = ix->desc.dev_dtype;
+  convert_queries_kernel<<<(nq * ix->qld + 255) / 256, 256, 0, st>>>(d_q, nq * ix->qld, ix->d_q16,
+                                                                     dtype);
+  TSC_CUDA(cudaGetLastError());
+  ix->launches++;
+
+  GemmParams p{};
+  p.n_rows = ix->rows;
+  p.nq = nq;
+  p.k_blocks = (ix->desc.dims + kGemmBK - 1) / kGemmBK;
+  p.q_tiles = (nq + kGemmBM - 1) / kGemmBM;
+  p.n_tiles = (uint32_t)((ix->rows + kGemmBN - 1) / kGemmBN);
+  uint32_t slices = (uint32_t)ix->sm_count / p.q_tiles;
+  if (slices == 0) {
+    set_error("gemm: nq=%u needs more query tiles than SMs", nq);
+    return TSC_ERR_BAD_ARG;
+  }
+  if (slices > p.n_tiles) slices = p.n_tiles;
+  p.n_slices = slices;
+  p.kprime = kprime;
+  p.metric = ix->desc.metric;
+  p.norm2 = ix->d_norm2;
+  p.live_mask = (ix->has_deleted || ix->has_filter) ? ix->d_live : nullptr;
+  p.cand = d_cand;
+  p.dbg_keys = dbg_keys;
+  uint32_t stages = 4;
+  const char *ev = getenv("TSC_GEMM_STAGES");
+  if (ev && atoi(ev) >= 2) stages = (uint32_t)atoi(ev);
+  while (stages > 2 && gemm_smem_bytes(stages, kprime) > ix->smem_optin) stages--;
+  p.stages = stages;
+  const size_t smem = gemm_smem_bytes(stages, kprime);
+  if (smem > ix->smem_optin) {
+    set_error("gemm: shared memory %zu exceeds %zu", smem, ix->smem_optin);
+    return TSC_ERR_UNSUPPORTED;
+  }
+
+  CUtensorMap map_q, map_b;
+  rc = make_map(&map_q, dtype, ix->d_q16, nq, ix->ld, ix->row_bytes, kGemmBM);
+  if (rc != TSC_OK) return rc;
+  rc = make_map(&map_b, dtype, ix->d_rows, ix->rows, ix->ld, ix->row_bytes, kGemmBN);
+  if (rc != TSC_OK) return rc;
+
+  static bool attr_done[64] = {false};
+  if (!attr_done[ix->device & 63]) {
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ix->smem_optin));
+    attr_done[ix->device & 63] = true;
+  }
+  int slot = 0;
+  rc = hot_timer_begin(ix, st, &slot);
+  if (rc != TSC_OK) return rc;
+  gemm_topk_kernel<<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
+      map_q, map_b, p, umma_idesc_f16(dtype, kGemmBM, kGemmBN));
+  TSC_CUDA(cudaGetLastError());
+  ix->launches++;
+  *out_lists = p.n_slices;
+  // algorithmic work: 2 * nq * N * d flops; corpus bytes read once
+  return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
+                       2.0 * nq * (double)ix->rows * ix->desc.dims);
+}
+
+}  // namespace tsc

@@ -60,6 +60,9 @@ struct Index {
   uint32_t k_max = 0, nq_max = 0, kprime_max = 0;
   float *d_queries = nullptr;      // [nq_max, qld]
   float *h_queries = nullptr;      // pinned
+  float *d_norm2 = nullptr;        // [capacity] sum of squares per stored row (16-bit dtypes)
+  uint16_t *d_q16 = nullptr;       // [nq_max, qld] queries in the storage dtype (GEMM path)
+  uint32_t gemm_min_nq = 9;        // batches at least this large take the tensor-core path
   uint64_t *d_cand = nullptr;      // [nq_max][cand_lists][kprime_max]
   uint64_t cand_lists = 0;
   int64_t *d_out_ids = nullptr, *h_out_ids = nullptr;
@@ -103,6 +106,10 @@ int32_t launch_merge(Index *ix, const int64_t *d_part_ids, const double *d_part_
                      uint64_t part_stride, uint32_t n_parts, uint32_t nq, uint32_t k,
                      int64_t *d_ids, double *d_dist, uint32_t *d_counts, cudaStream_t st);
 int32_t scan_configure(Index *ix);
+bool gemm_supported(const Index *ix, uint32_t kprime);
+int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_t st);
+int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
+                    uint32_t *out_lists, float *dbg_keys, cudaStream_t st);
 // bracket one launch of the dominant kernel with events on `st`
 int32_t hot_timer_begin(Index *ix, cudaStream_t st, int *slot);
 int32_t hot_timer_end(Index *ix, cudaStream_t st, int slot, double bytes, double flops);
