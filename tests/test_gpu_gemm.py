@@ -24,7 +24,8 @@ def gemm_keys(ix, q):
 
 
 @pytest.mark.parametrize("dt", [1, 2])
-@pytest.mark.parametrize("dims,n,nq", [(64, 300, 5), (128, 1000, 130), (768, 777, 64), (100, 513, 257)])
+@pytest.mark.parametrize("dims,n,nq", [(64, 300, 5), (128, 1000, 130), (768, 777, 64), (100, 513, 257),
+                                         (1024, 600, 140), (776, 300, 9)])
 def test_gemm_keys_match_matmul(dt, dims, n, nq):
     """UMMA descriptors / TMA swizzle / TMEM epilogue: raw keys vs a float64 matmul
     over the same rounded operands (tolerance: fp32 accumulation order)."""

@@ -72,6 +72,7 @@ static void free_index(Index *ix) {
   cudaFree(ix->d_queries);
   cudaFree(ix->d_norm2);
   cudaFree(ix->d_q16);
+  cudaFree(ix->d_progress);
   cudaFree(ix->d_cand);
   cudaFree(ix->d_out_ids);
   cudaFree(ix->d_out_dist);
@@ -352,7 +353,8 @@ int32_t tsc_index_create(const tsc_index_desc *d, uint64_t *out_handle) {
     delete ix;
     return rc;
   }
-  ix->cand_lists = (uint64_t)ix->scan.grid;
+  // scan: one list per CTA; tensor-core path: two per CTA (<= 2 x SM count)
+  ix->cand_lists = 2ull * (uint64_t)(ix->scan.grid > ix->sm_count ? ix->scan.grid : ix->sm_count);
   ix->mask_words = (ix->capacity + 31) / 32 + 1;
   cudaError_t e = cudaSuccess;
   auto ok = [&](cudaError_t r) {
@@ -374,6 +376,7 @@ int32_t tsc_index_create(const tsc_index_desc *d, uint64_t *out_handle) {
   if (d->dev_dtype != TSC_DEV_F32) {
     ok(dev_alloc(ix, &ix->d_norm2, (size_t)ix->capacity));
     ok(dev_alloc(ix, &ix->d_q16, (size_t)ix->nq_max * ix->qld));
+    ok(dev_alloc(ix, &ix->d_progress, (size_t)4096));
   }
   if (const char *ev = getenv("TSC_GEMM_MIN_NQ")) ix->gemm_min_nq = (uint32_t)atoi(ev);
   ok(dev_alloc(ix, &ix->d_cand, (size_t)ix->nq_max * ix->cand_lists * ix->kprime_max));

@@ -99,6 +99,59 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
   p.live_mask = (ix->has_deleted || ix->has_filter) ? ix->d_live : nullptr;
   p.cand = d_cand;
   p.dbg_keys = dbg_keys;
+  if (const char *xe = getenv("TSC_GEMM_EXP")) p.exp_flags = (uint32_t)atoi(xe);
+  p.l2_prefetch = 0;  // measured: no gain on B200 (the SM ingest port, not HBM latency, binds)
+  if (const char *pe = getenv("TSC_GEMM_L2PF")) p.l2_prefetch = (uint32_t)atoi(pe);
+  p.lockstep_window = 0;
+  if (const char *we = getenv("TSC_GEMM_LOCKSTEP")) p.lockstep_window = (uint32_t)atoi(we);
+  if (p.lockstep_window > 0 && ix->d_progress) {
+    TSC_CUDA(cudaMemsetAsync(ix->d_progress, 0, 4096 * sizeof(int), st));
+    p.progress = ix->d_progress;
+  }
+  // A-in-TMEM variant whenever the query tile fits 384 TMEM columns (dims <= 768)
+  const char *tsenv = getenv("TSC_GEMM_TS");
+  // (measured slower than the SS kernel on B200 - 64-column tiles pay too many
+  // accumulator hand-offs - so it is opt-in: TSC_GEMM_TS=1)
+  const bool use_ts = ix->desc.dims <= (uint32_t)kTsMaxDims && tsenv && atoi(tsenv) == 1;
+  if (use_ts) {
+    p.k_blocks = (ix->desc.dims + kTsBK - 1) / kTsBK;
+    p.n_tiles = (uint32_t)((ix->rows + kTsBN - 1) / kTsBN);
+    if (p.n_slices > p.n_tiles) p.n_slices = p.n_tiles;
+    uint32_t stages = 10;
+    const char *ev = getenv("TSC_GEMM_STAGES");
+    if (ev && atoi(ev) >= 2) stages = (uint32_t)atoi(ev);
+    while (stages > 2 && gemm_ts_smem_bytes(stages, kprime) > ix->smem_optin) stages--;
+    p.stages = stages;
+    const size_t smem = gemm_ts_smem_bytes(stages, kprime);
+    CUtensorMap map_b;
+    rc = make_map(&map_b, dtype, ix->d_rows, ix->rows, ix->ld, ix->row_bytes, kTsBN);
+    if (rc != TSC_OK) return rc;
+    static bool ts_attr_done[64] = {false};
+    if (!ts_attr_done[ix->device & 63]) {
+      TSC_CUDA(cudaFuncSetAttribute(gemm_topk_ts_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ix->smem_optin));
+      TSC_CUDA(cudaFuncSetAttribute(gemm_topk_ts_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ix->smem_optin));
+      ts_attr_done[ix->device & 63] = true;
+    }
+    int slot = 0;
+    rc = hot_timer_begin(ix, st, &slot);
+    if (rc != TSC_OK) return rc;
+    const uint32_t idesc = umma_idesc_f16(dtype, kGemmBM, kTsBN);
+    if (dbg_keys)
+      gemm_topk_ts_kernel<true><<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
+          map_b, p, ix->d_q16, ix->qld, idesc);
+    else
+      gemm_topk_ts_kernel<false><<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
+          map_b, p, ix->d_q16, ix->qld, idesc);
+    TSC_CUDA(cudaGetLastError());
+    ix->launches++;
+    *out_lists = p.n_slices * 2;
+    return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
+                         2.0 * nq * (double)ix->rows * ix->desc.dims);
+  }
   uint32_t stages = 4;
   const char *ev = getenv("TSC_GEMM_STAGES");
   if (ev && atoi(ev) >= 2) stages = (uint32_t)atoi(ev);
@@ -118,18 +171,24 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
 
   static bool attr_done[64] = {false};
   if (!attr_done[ix->device & 63]) {
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
     attr_done[ix->device & 63] = true;
   }
   int slot = 0;
   rc = hot_timer_begin(ix, st, &slot);
   if (rc != TSC_OK) return rc;
-  gemm_topk_kernel<<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
-      map_q, map_b, p, umma_idesc_f16(dtype, kGemmBM, kGemmBN));
+  if (dbg_keys)
+    gemm_topk_kernel<true><<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
+        map_q, map_b, p, umma_idesc_f16(dtype, kGemmBM, kGemmBN));
+  else
+    gemm_topk_kernel<false><<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
+        map_q, map_b, p, umma_idesc_f16(dtype, kGemmBM, kGemmBN));
   TSC_CUDA(cudaGetLastError());
   ix->launches++;
-  *out_lists = p.n_slices;
+  *out_lists = p.n_slices * 2;
   // algorithmic work: 2 * nq * N * d flops; corpus bytes read once
   return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
                        2.0 * nq * (double)ix->rows * ix->desc.dims);

@@ -61,6 +61,7 @@ struct Index {
   float *d_queries = nullptr;      // [nq_max, qld]
   float *h_queries = nullptr;      // pinned
   float *d_norm2 = nullptr;        // [capacity] sum of squares per stored row (16-bit dtypes)
+  int *d_progress = nullptr;       // lockstep counters of the tensor-core path
   uint16_t *d_q16 = nullptr;       // [nq_max, qld] queries in the storage dtype (GEMM path)
   uint32_t gemm_min_nq = 9;        // batches at least this large take the tensor-core path
   uint64_t *d_cand = nullptr;      // [nq_max][cand_lists][kprime_max]
