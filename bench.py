@@ -76,7 +76,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.gpu), "-lms", "100"],
+                 "-i", str(self.gpu), "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -124,8 +124,12 @@ def cpu_arm(rows_total: int, dims: int, k: int, sample_rows: int, steps: int, wa
     import numpy as np
     import oracle
 
-    lib = oracle.c_oracle()
-    threads = lib.tso_max_threads()
+    oracle.c_oracle()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     sample_rows = min(sample_rows, rows_total)
     rows = oracle.synth_rows(SEED, 0, sample_rows, dims)
     queries = oracle.synth_rows(SEED + 1, 0, steps + warmup, dims)

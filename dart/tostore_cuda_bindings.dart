@@ -1,0 +1,266 @@
+// tostore_cuda_bindings.dart — dart:ffi binding of libtostore_cuda.so
+// (include/tostore_cuda.h). Drop into lib/src/handler/ of tocreator/tostore.
+//
+// Style follows the reference's only FFI user, lib/src/handler/system_ffi_helper.dart:
+// a static DynamicLibrary, lookupFunction<Native, Dart>('name'), caller-allocated
+// buffers from `calloc` freed in try/finally, int32 status (0 = success), and no
+// exception crossing the public helper (errors degrade to an empty result, like
+// every missing-precondition case of VectorIndexManager.vectorSearch,
+// lib/src/core/vector_index_manager.dart:485-508).
+//
+// NOT compiled in this repository (no Dart SDK in the build image); it is kept
+// small and one-to-one with the header so it can be reviewed by eye. The Python
+// twin that IS exercised by the test-suite is tostore_b200/_native.py.
+//
+// Keep off the web build with the reference's conditional-import pattern
+// (lib/src/handler/platform_handler.dart:1-2): `if (dart.library.io)`.
+
+import 'dart:ffi';
+import 'dart:typed_data';
+
+import 'package:ffi/ffi.dart';
+
+/// Mirrors `tsc_index_desc`.
+final class TscIndexDesc extends Struct {
+  @Uint32()
+  external int structSize;
+  @Uint32()
+  external int dims;
+  @Uint8()
+  external int metric; // VectorDistanceMetric.index (l2, innerProduct, cosine)
+  @Uint8()
+  external int srcPrecision; // VectorPrecision.index (float64, float32, int8)
+  @Uint8()
+  external int devDtype; // 0 f32, 1 bf16, 2 f16
+  @Uint8()
+  external int reserved0;
+  @Int32()
+  external int deviceId;
+  @Uint64()
+  external int capacityRows;
+  @Uint64()
+  external int firstNodeId;
+  @Uint32()
+  external int kMax;
+  @Uint32()
+  external int nqMax;
+}
+
+typedef _CreateN = Int32 Function(Pointer<TscIndexDesc>, Pointer<Uint64>);
+typedef _CreateD = int Function(Pointer<TscIndexDesc>, Pointer<Uint64>);
+typedef _HandleN = Int32 Function(Uint64);
+typedef _HandleD = int Function(int);
+typedef _AppendRowsN = Int32 Function(Uint64, Uint64, Pointer<Void>, Uint64);
+typedef _AppendRowsD = int Function(int, int, Pointer<Void>, int);
+typedef _AppendPagesN = Int32 Function(
+    Uint64, Uint64, Pointer<Uint8>, Uint64, Uint32, Uint64);
+typedef _AppendPagesD = int Function(
+    int, int, Pointer<Uint8>, int, int, int);
+typedef _SetDeletedN = Int32 Function(Uint64, Pointer<Uint64>, Uint64, Uint8);
+typedef _SetDeletedD = int Function(int, Pointer<Uint64>, int, int);
+typedef _SearchN = Int32 Function(Uint64, Pointer<Float>, Uint32, Uint32, Double,
+    Pointer<Int64>, Pointer<Double>, Pointer<Uint32>);
+typedef _SearchD = int Function(int, Pointer<Float>, int, int, double,
+    Pointer<Int64>, Pointer<Double>, Pointer<Uint32>);
+typedef _SubmitN = Int32 Function(Uint64, Pointer<Float>, Uint32, Uint32, Double,
+    Pointer<Int64>, Pointer<Double>, Pointer<Uint32>, Pointer<Uint64>);
+typedef _SubmitD = int Function(int, Pointer<Float>, int, int, double,
+    Pointer<Int64>, Pointer<Double>, Pointer<Uint32>, Pointer<Uint64>);
+typedef _PollN = Int32 Function(Uint64, Pointer<Int32>);
+typedef _PollD = int Function(int, Pointer<Int32>);
+typedef _LastErrorN = Pointer<Utf8> Function();
+typedef _LastErrorD = Pointer<Utf8> Function();
+
+/// One (nodeId, distance) pair — same shape as `NghSearchResult`
+/// (lib/src/core/ngh_graph_engine.dart:26-40).
+class TscHit {
+  final int nodeId;
+  final double distance;
+  const TscHit(this.nodeId, this.distance);
+}
+
+class TostoreCuda {
+  static DynamicLibrary? _lib;
+  static bool _failed = false;
+
+  static DynamicLibrary? _open() {
+    if (_lib != null || _failed) return _lib;
+    try {
+      _lib = DynamicLibrary.open('libtostore_cuda.so');
+    } catch (_) {
+      _failed = true; // no GPU library: callers keep using NghGraphEngine.search
+    }
+    return _lib;
+  }
+
+  static bool get isAvailable {
+    final lib = _open();
+    if (lib == null) return false;
+    try {
+      final count =
+          lib.lookupFunction<Int32 Function(), int Function()>('tsc_device_count');
+      return count() > 0;
+    } catch (_) {
+      return false;
+    }
+  }
+
+  static String lastError() {
+    final lib = _open();
+    if (lib == null) return 'libtostore_cuda.so not found';
+    return lib
+        .lookupFunction<_LastErrorN, _LastErrorD>('tsc_last_error')()
+        .toDartString();
+  }
+
+  /// tsc_index_create. Returns 0 on failure.
+  static int createIndex({
+    required int dims,
+    required int metricIndex,
+    required int precisionIndex,
+    required int capacityRows,
+    int devDtype = 0,
+    int deviceId = 0,
+    int firstNodeId = 0,
+    int kMax = 128,
+    int nqMax = 64,
+  }) {
+    final lib = _open();
+    if (lib == null) return 0;
+    final create = lib.lookupFunction<_CreateN, _CreateD>('tsc_index_create');
+    final desc = calloc<TscIndexDesc>();
+    final out = calloc<Uint64>();
+    try {
+      desc.ref
+        ..structSize = sizeOf<TscIndexDesc>()
+        ..dims = dims
+        ..metric = metricIndex
+        ..srcPrecision = precisionIndex
+        ..devDtype = devDtype
+        ..deviceId = deviceId
+        ..capacityRows = capacityRows
+        ..firstNodeId = firstNodeId
+        ..kMax = kMax
+        ..nqMax = nqMax;
+      return create(desc, out) == 0 ? out.value : 0;
+    } finally {
+      calloc.free(desc);
+      calloc.free(out);
+    }
+  }
+
+  static void destroyIndex(int handle) {
+    _open()?.lookupFunction<_HandleN, _HandleD>('tsc_index_destroy')(handle);
+  }
+
+  /// Flush-time hook: the Float32List rows VectorIndexManager.writeChanges just
+  /// handed to NghGraphEngine.insertBatch (vector_index_manager.dart:378-387).
+  static bool appendRows(int handle, int firstNodeId, Float32List rows, int nRows) {
+    final lib = _open();
+    if (lib == null || nRows == 0) return lib != null;
+    final fn = lib.lookupFunction<_AppendRowsN, _AppendRowsD>('tsc_index_append_rows');
+    final buf = calloc<Float>(rows.length);
+    try {
+      buf.asTypedList(rows.length).setAll(0, rows);
+      return fn(handle, firstNodeId, buf.cast<Void>(), nRows) == 0;
+    } finally {
+      calloc.free(buf);
+    }
+  }
+
+  /// Cold start: raw bytes of consecutive rawvec pages exactly as
+  /// StorageInterface.readAsBytesAt returned them (ngh_partition_manager.dart:262-264).
+  static bool appendPages(int handle, int firstLogicalPage, Uint8List pages,
+      int pageSize, int liveRows) {
+    final lib = _open();
+    if (lib == null) return false;
+    final fn = lib.lookupFunction<_AppendPagesN, _AppendPagesD>('tsc_index_append_pages');
+    final buf = calloc<Uint8>(pages.length);
+    try {
+      buf.asTypedList(pages.length).setAll(0, pages);
+      return fn(handle, firstLogicalPage, buf, pages.length ~/ pageSize, pageSize,
+              liveRows) ==
+          0;
+    } finally {
+      calloc.free(buf);
+    }
+  }
+
+  /// deleteBatch hook (vector_index_manager.dart:429-434).
+  static bool setDeleted(int handle, List<int> nodeIds, {bool deleted = true}) {
+    final lib = _open();
+    if (lib == null || nodeIds.isEmpty) return lib != null;
+    final fn = lib.lookupFunction<_SetDeletedN, _SetDeletedD>('tsc_index_set_deleted');
+    final buf = calloc<Uint64>(nodeIds.length);
+    try {
+      for (var i = 0; i < nodeIds.length; i++) {
+        buf[i] = nodeIds[i];
+      }
+      return fn(handle, buf, nodeIds.length, deleted ? 1 : 0) == 0;
+    } finally {
+      calloc.free(buf);
+    }
+  }
+
+  /// Blocking search: replaces the body of the `_graphEngine.search` call at
+  /// vector_index_manager.dart:538-548. `query` is the already padded (and, for
+  /// cosine, normalised) Float32List. Returns [] on any error.
+  static List<TscHit> search(int handle, Float32List query, int topK,
+      {double? distanceThreshold}) {
+    final lib = _open();
+    if (lib == null || topK <= 0) return const [];
+    final fn = lib.lookupFunction<_SearchN, _SearchD>('tsc_search');
+    final q = calloc<Float>(query.length);
+    final ids = calloc<Int64>(topK);
+    final dist = calloc<Double>(topK);
+    final count = calloc<Uint32>();
+    try {
+      q.asTypedList(query.length).setAll(0, query);
+      final rc = fn(handle, q, 1, topK, distanceThreshold ?? double.nan, ids, dist, count);
+      if (rc != 0) return const [];
+      return [for (var i = 0; i < count.value; i++) TscHit(ids[i], dist[i])];
+    } finally {
+      calloc.free(q);
+      calloc.free(ids);
+      calloc.free(dist);
+      calloc.free(count);
+    }
+  }
+
+  /// Non-blocking variant: submit, then `await Future.delayed(Duration.zero)`
+  /// between polls, the way YieldController keeps the isolate responsive.
+  static Future<List<TscHit>> searchAsync(int handle, Float32List query, int topK,
+      {double? distanceThreshold}) async {
+    final lib = _open();
+    if (lib == null || topK <= 0) return const [];
+    final submit = lib.lookupFunction<_SubmitN, _SubmitD>('tsc_search_submit');
+    final poll = lib.lookupFunction<_PollN, _PollD>('tsc_search_poll');
+    final q = calloc<Float>(query.length);
+    final ids = calloc<Int64>(topK);
+    final dist = calloc<Double>(topK);
+    final count = calloc<Uint32>();
+    final ticket = calloc<Uint64>();
+    final done = calloc<Int32>();
+    try {
+      q.asTypedList(query.length).setAll(0, query);
+      if (submit(handle, q, 1, topK, distanceThreshold ?? double.nan, ids, dist, count,
+              ticket) !=
+          0) {
+        return const [];
+      }
+      while (true) {
+        if (poll(ticket.value, done) != 0) return const [];
+        if (done.value != 0) break;
+        await Future<void>.delayed(Duration.zero);
+      }
+      return [for (var i = 0; i < count.value; i++) TscHit(ids[i], dist[i])];
+    } finally {
+      calloc.free(q);
+      calloc.free(ids);
+      calloc.free(dist);
+      calloc.free(count);
+      calloc.free(ticket);
+      calloc.free(done);
+    }
+  }
+}
