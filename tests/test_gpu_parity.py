@@ -341,3 +341,31 @@ def test_full_size_c2_properties():
             assert set(better.tolist()) <= set(ids[0].tolist()) | set(planted.tolist())
         st = ix.stats()
         assert st.last_path == 1 and st.last_search_ms > 0
+
+
+@pytest.mark.parametrize("dt,dims", [(0, 384), (1, 256), (0, 100)])
+def test_sparse_where_filter_uses_per_row_scan(dt, dims):
+    """Low-selectivity WHERE bitmap -> per-live-row bulk copies (K6); same results as the oracle."""
+    T = t()
+    n, k = 60000, 10
+    rows = onp.round_dev(oracle.synth_rows(71, 0, n, dims), dt)
+    Q = oracle.synth_rows(72, 0, 5, dims)
+    rng = np.random.default_rng(3)
+    for metric in (0, 2):
+        Qp = np.stack([prep(q, metric) for q in Q])
+        with T.GpuVectorIndex(dims, metric, capacity_rows=n, dev_dtype=dt, k_max=16, nq_max=8) as ix:
+            ix.append_synthetic(71, n)
+            for frac in (0.10, 0.001, 0.0):
+                mask = rng.random(n) < frac
+                if frac == 0.001:
+                    mask[n - 1] = mask[0] = True          # edges of the bitmap
+                ix.set_filter(mask)
+                ix.set_deleted(np.nonzero(mask)[0][:3])    # tombstones on top of the filter
+                dead = np.zeros(n, dtype=bool)
+                dead[np.nonzero(mask)[0][:3]] = True
+                for nq in (1, 5):
+                    ids, dist, cnt = ix.search(Qp[:nq], k)
+                    for q in range(nq):
+                        oi, od = oracle.search(rows, Qp[q], metric, k, deleted=dead, filter=mask)
+                        assert_same(ids, dist, cnt, q, oi, od, k, f"dt{dt} d{dims} m{metric} f{frac}")
+                ix.set_deleted(np.nonzero(dead)[0], deleted=False)

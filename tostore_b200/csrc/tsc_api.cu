@@ -69,6 +69,7 @@ static void free_index(Index *ix) {
   cudaFree(ix->d_filter);
   cudaFree(ix->d_live);
   cudaFree(ix->d_delta);
+  cudaFree(ix->d_live_count);
   cudaFree(ix->d_queries);
   cudaFree(ix->d_norm2);
   cudaFree(ix->d_q16);
@@ -148,13 +149,19 @@ static int32_t ensure_stage(Index *ix, size_t bytes) {
 }
 
 static int32_t refresh_live(Index *ix, cudaStream_t st) {
-  if (!ix->live_dirty) return TSC_OK;
+  if (!ix->live_dirty && ix->live_rows_for == ix->rows) return TSC_OK;
   if (ix->has_deleted || ix->has_filter) {
+    TSC_CUDA(cudaMemsetAsync(ix->d_live_count, 0, 8, st));
     combine_live_kernel<<<ix->sm_count * 4, 256, 0, st>>>(
         ix->has_deleted ? ix->d_deleted : nullptr, ix->has_filter ? ix->d_filter : nullptr,
-        ix->d_live, ix->mask_words);
+        ix->d_live, ix->mask_words, ix->rows, ix->d_live_count);
     TSC_CUDA(cudaGetLastError());
     ix->launches++;
+    unsigned long long cnt = 0;
+    TSC_CUDA(cudaMemcpyAsync(&cnt, ix->d_live_count, 8, cudaMemcpyDeviceToHost, st));
+    TSC_CUDA(cudaStreamSynchronize(st));
+    ix->live_rows = cnt;
+    ix->live_rows_for = ix->rows;
   }
   ix->live_dirty = false;
   return TSC_OK;
@@ -372,6 +379,8 @@ int32_t tsc_index_create(const tsc_index_desc *d, uint64_t *out_handle) {
   ok(dev_alloc(ix, &ix->d_filter, ix->mask_words));
   ok(dev_alloc(ix, &ix->d_live, ix->mask_words));
   ok(dev_alloc(ix, &ix->d_delta, 4));
+  ok(dev_alloc(ix, &ix->d_live_count, 1));
+  if (const char *ev = getenv("TSC_SCAN_SPARSE_FRAC")) ix->sparse_frac = atof(ev);
   ok(dev_alloc(ix, &ix->d_queries, (size_t)ix->nq_max * ix->qld));
   if (d->dev_dtype != TSC_DEV_F32) {
     ok(dev_alloc(ix, &ix->d_norm2, (size_t)ix->capacity));
@@ -497,6 +506,7 @@ int32_t tsc_index_append_rows(uint64_t handle, uint64_t first_node_id, const voi
   if (rc != TSC_OK) return rc;
   TSC_CUDA(cudaStreamSynchronize(ix->stream));
   if (row0 + n_rows > ix->rows) ix->rows = row0 + n_rows;
+  ix->live_dirty = true;
   return TSC_OK;
 }
 

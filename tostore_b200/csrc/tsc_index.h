@@ -54,6 +54,10 @@ struct Index {
   uint32_t *d_deleted = nullptr, *d_filter = nullptr, *d_live = nullptr;
   bool has_deleted = false, has_filter = false, live_dirty = false;
   uint64_t deleted_rows = 0;
+  uint64_t live_rows = 0;            // popcount of `live` over [0, rows) (valid when a mask is active)
+  uint64_t live_rows_for = 0;        // value of `rows` the count was taken at
+  unsigned long long *d_live_count = nullptr;
+  double sparse_frac = 0.35;         // live fraction below which the per-live-row scan is used
   int *d_delta = nullptr;
 
   // search scratch

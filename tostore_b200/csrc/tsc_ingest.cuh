@@ -242,13 +242,21 @@ __global__ void set_bits_kernel(const uint64_t *node_ids, uint64_t n, uint64_t s
 
 // live = ~deleted & filter (filter may be NULL)
 __global__ void combine_live_kernel(const uint32_t *deleted, const uint32_t *filter,
-                                    uint32_t *live, uint64_t words) {
+                                    uint32_t *live, uint64_t words, uint64_t n_rows,
+                                    unsigned long long *live_count) {
+  unsigned long long cnt = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
        i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t d = deleted ? deleted[i] : 0u;
     uint32_t f = filter ? filter[i] : 0xFFFFFFFFu;
-    live[i] = ~d & f;
+    uint32_t l = ~d & f;
+    live[i] = l;
+    uint64_t base = i * 32;
+    if (base + 32 > n_rows) l = base < n_rows ? (l & (uint32_t)((1ull << (n_rows - base)) - 1ull)) : 0u;
+    cnt += __popc(l);
   }
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(live_count, cnt);
 }
 
 // [nq, dims] -> [nq, qld] zero padded

@@ -32,10 +32,11 @@ struct ScanPlan {
   size_t smem;
 };
 
-static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl) {
+static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl,
+                      bool sparse = false) {
   const size_t budget = ix->smem_optin - 1024;
   for (int w = ix->scan.warps; w >= 1; w >>= 1) {
-    int r = ix->scan.rows;
+    int r = sparse ? 1 : ix->scan.rows;  // sparse: one live row per stage
     if (r <= 0) {
       r = 8;
       while (r > 1 && (size_t)r * ix->row_bytes > (size_t)ix->scan.stage_target) r >>= 1;
@@ -55,7 +56,7 @@ static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl) {
         smax = (int)((ix->scan.inflight_target + (size_t)w * stage_bytes / 2) /
                      ((size_t)w * stage_bytes));
         if (smax < 2) smax = 2;
-        if (smax > 8) smax = 8;
+        if (smax > (sparse ? 16 : 8)) smax = sparse ? 16 : 8;
       }
       int s = smax;
       while (s >= 2 && scan_smem_warp_bytes(qb, kprime, s, stage_bytes) > per_warp) s--;
@@ -93,6 +94,44 @@ static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cuda
   return hot_timer_end(ix, st, slot, (double)p.n_rows * ix->desc.dims * ix->elem_bytes, 0.0);
 }
 
+template <int METRIC, int DTYPE, int QB>
+static int32_t run_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
+  static bool attr_done[64] = {false};
+  auto kern = scan_topk_sparse_kernel<METRIC, DTYPE, QB>;
+  if (!attr_done[ix->device & 63]) {
+    TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ix->smem_optin));
+    attr_done[ix->device & 63] = true;
+  }
+  int slot = 0;
+  int32_t rc = hot_timer_begin(ix, st, &slot);
+  if (rc != TSC_OK) return rc;
+  kern<<<ix->scan.grid, pl.warps * 32, pl.smem, st>>>(p);
+  TSC_CUDA(cudaGetLastError());
+  ix->launches++;
+  // algorithmic bytes: only live rows are read (+ the bitmap)
+  return hot_timer_end(ix, st, slot,
+                       (double)ix->live_rows * ix->desc.dims * ix->elem_bytes + p.n_rows / 8.0, 0.0);
+}
+
+template <int METRIC, int DTYPE>
+static int32_t dispatch_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl,
+                               cudaStream_t st) {
+  if (pl.qb == 1) return run_sparse<METRIC, DTYPE, 1>(ix, p, pl, st);
+  if (pl.qb == 4) return run_sparse<METRIC, DTYPE, 4>(ix, p, pl, st);
+  return run_sparse<METRIC, DTYPE, 8>(ix, p, pl, st);
+}
+
+template <int METRIC>
+static int32_t dispatch_sparse_dtype(Index *ix, const ScanParams &p, const ScanPlan &pl,
+                                     cudaStream_t st) {
+  switch (ix->desc.dev_dtype) {
+    case TSC_DEV_F32: return dispatch_sparse<METRIC, kF32>(ix, p, pl, st);
+    case TSC_DEV_BF16: return dispatch_sparse<METRIC, kBF16>(ix, p, pl, st);
+    default: return dispatch_sparse<METRIC, kF16>(ix, p, pl, st);
+  }
+}
+
 template <int METRIC, int DTYPE>
 static int32_t dispatch_qr(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
 #define TSC_CASE(QB, R) \
@@ -124,7 +163,11 @@ int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
     uint32_t left = nq - q0;
     int qb = left >= 5 ? 8 : (left >= 2 ? 4 : 1);
     ScanPlan pl;
-    if (!plan_scan(ix, qb, kprime, &pl)) {
+    // sparse liveness (WHERE prefilter): move only the live rows, one bulk copy each
+    const bool masked = ix->has_deleted || ix->has_filter;
+    const bool sparse = masked && ix->row_bytes >= 256 &&
+                        (double)ix->live_rows < ix->sparse_frac * (double)ix->rows;
+    if (!plan_scan(ix, qb, kprime, &pl, sparse)) {
       set_error("scan: dims=%u (row %u B) with k'=%u does not fit shared memory", ix->desc.dims,
                 ix->row_bytes, kprime);
       return TSC_ERR_BAD_DIMS;
@@ -145,6 +188,16 @@ int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
     p.cand = d_cand + (size_t)q0 * ix->scan.grid * kprime;
     p.sort_cap = pl.sort_cap;
     int32_t rc;
+    if (sparse) {
+      switch (ix->desc.metric) {
+        case TSC_METRIC_L2: rc = dispatch_sparse_dtype<kL2>(ix, p, pl, st); break;
+        case TSC_METRIC_INNER_PRODUCT: rc = dispatch_sparse_dtype<kIP>(ix, p, pl, st); break;
+        default: rc = dispatch_sparse_dtype<kCos>(ix, p, pl, st); break;
+      }
+      if (rc != TSC_OK) return rc;
+      q0 += n;
+      continue;
+    }
     switch (ix->desc.metric) {
       case TSC_METRIC_L2: rc = dispatch_dtype<kL2>(ix, p, pl, st); break;
       case TSC_METRIC_INNER_PRODUCT: rc = dispatch_dtype<kIP>(ix, p, pl, st); break;

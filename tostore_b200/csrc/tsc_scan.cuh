@@ -120,6 +120,41 @@ __host__ __device__ inline size_t scan_smem_warp_bytes(int qb, uint32_t kprime, 
   return (lists + bars + ring + 127) & ~(size_t)127;
 }
 
+// ---- block-level merge: W sorted lists -> one list of kp per query -------------
+// (bitonic sort of the composites in shared memory; every bulk copy this CTA
+// issued has been waited on, so no async write is outstanding)
+__device__ __forceinline__ void scan_block_merge(const ScanParams &p, uint64_t *sortbuf,
+                                                 const uint32_t *lkeys, const uint32_t *lids,
+                                                 uint32_t kp, int warp, int warps, int lane) {
+  for (uint32_t q = 0; q < p.nq; q++) {
+    __syncthreads();
+    for (uint32_t i = lane; i < kp; i += 32)
+      sortbuf[(size_t)warp * kp + i] =
+          ((uint64_t)lkeys[(size_t)q * kp + i] << 32) | lids[(size_t)q * kp + i];
+    for (uint32_t i = (uint32_t)warps * kp + threadIdx.x; i < p.sort_cap; i += blockDim.x)
+      sortbuf[i] = ~0ull;
+    __syncthreads();
+    for (uint32_t k = 2; k <= p.sort_cap; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = threadIdx.x; i < p.sort_cap; i += blockDim.x) {
+          uint32_t x = i ^ j;
+          if (x > i) {
+            uint64_t a = sortbuf[i], b = sortbuf[x];
+            bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              sortbuf[i] = b;
+              sortbuf[x] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    uint64_t *out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * kp;
+    for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) out[i] = sortbuf[i];
+  }
+}
+
 template <int METRIC, int DTYPE, int QB, int R>
 __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -289,36 +324,167 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     }
   }
 
-  // ---- block-level merge: W sorted lists -> one list of kp per query ---------
-  // (bitonic sort of the composites in shared memory; every bulk copy this CTA
-  // issued has been waited on, so no async write is outstanding)
-  for (uint32_t q = 0; q < p.nq; q++) {
-    __syncthreads();
-    for (uint32_t i = lane; i < kp; i += 32)
-      sortbuf[(size_t)warp * kp + i] =
-          ((uint64_t)lkeys[(size_t)q * kp + i] << 32) | lids[(size_t)q * kp + i];
-    for (uint32_t i = (uint32_t)warps * kp + threadIdx.x; i < p.sort_cap; i += blockDim.x)
-      sortbuf[i] = ~0ull;
-    __syncthreads();
-    for (uint32_t k = 2; k <= p.sort_cap; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < p.sort_cap; i += blockDim.x) {
-          uint32_t x = i ^ j;
-          if (x > i) {
-            uint64_t a = sortbuf[i], b = sortbuf[x];
-            bool up = (i & k) == 0;
-            if ((a > b) == up) {
-              sortbuf[i] = b;
-              sortbuf[x] = a;
+  scan_block_merge(p, sortbuf, lkeys, lids, kp, warp, warps, lane);
+}
+
+// K6: scan of a sparsely live column (WHERE prefilter / heavy tombstoning).
+// Same arithmetic and candidate lists as scan_topk_kernel, but the unit of data
+// movement is ONE LIVE ROW: a warp walks its share of the liveness bitmap (one
+// 32-bit word = 32 consecutive rows at a time) and issues a bulk copy only for rows
+// whose bit is set, so dead rows cost no HBM bytes (rows are whole 16-byte-aligned
+// byte ranges; at d=384 fp32 a row is exactly twelve 128-byte lines). The ring is a
+// queue of S one-row stages; rows are consumed in issue (= increasing id) order.
+template <int METRIC, int DTYPE, int QB>
+__global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int E = Chunk<DTYPE>::kElems;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps = blockDim.x >> 5;
+  const uint32_t kp = p.kprime;
+  const uint32_t S = p.stages;
+
+  float *qs = reinterpret_cast<float *>(smem);
+  uint64_t *sortbuf = reinterpret_cast<uint64_t *>(smem + scan_smem_query_bytes(QB, p.qld));
+  uint8_t *wbase = smem + scan_smem_query_bytes(QB, p.qld) + scan_smem_sort_bytes(p.sort_cap) +
+                   (size_t)warp * scan_smem_warp_bytes(QB, kp, S, p.stage_bytes);
+  uint32_t *lkeys = reinterpret_cast<uint32_t *>(wbase);
+  uint32_t *lids = lkeys + (size_t)QB * kp;
+  size_t off = ((size_t)QB * kp * 8 + 15) & ~(size_t)15;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + off);
+  off += ((size_t)S * 8 + 15) & ~(size_t)15;
+  off = (off + 127) & ~(size_t)127;
+  uint8_t *ring = wbase + off;
+
+  for (uint32_t i = threadIdx.x; i < (uint32_t)QB * p.qld; i += blockDim.x) {
+    uint32_t q = i / p.qld;
+    qs[i] = (q < p.nq) ? p.queries[i] : 0.0f;
+  }
+  for (uint32_t i = lane; i < (uint32_t)QB * kp; i += 32) {
+    lkeys[i] = kEmptyKey;
+    lids[i] = kInvalidRow;
+  }
+  if (lane == 0) {
+    for (uint32_t s = 0; s < S; s++) mbar_init(smem_u32(&bars[s]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const uint64_t policy = policy_evict_first();
+  const uint64_t n_words = (p.n_rows + 31) / 32;
+  const uint64_t gw = (uint64_t)blockIdx.x * warps + warp;
+  const uint64_t GW = (uint64_t)gridDim.x * warps;
+  const uint32_t cpr = p.chunks_per_row;
+
+  uint32_t thr[QB];
+#pragma unroll
+  for (int q = 0; q < QB; q++) thr[q] = kEmptyKey;
+
+  // issue side: (word, remaining bits) cursor over this warp's bitmap words
+  uint64_t word = gw;
+  uint32_t bits = 0;
+  auto load_word = [&]() {
+    bits = 0;
+    while (word < n_words) {
+      bits = p.live_mask[word];
+      uint64_t base_row = word * 32;
+      if (base_row + 32 > p.n_rows) bits &= (uint32_t)((1ull << (p.n_rows - base_row)) - 1ull);
+      if (bits) break;
+      word += GW;
+    }
+  };
+  load_word();
+  uint32_t head = 0, tail = 0, inflight = 0, hpar = 0;
+  // row ids of the stages in flight (uniform per warp): kept in registers of lane s
+  uint32_t my_row = kInvalidRow;
+
+  for (;;) {
+    while (inflight < S && bits) {
+      const uint32_t b = __ffs(bits) - 1;
+      bits &= bits - 1;
+      const uint32_t row = (uint32_t)(word * 32 + b);
+      if (lane == (int)tail) my_row = row;
+      if (lane == 0) {
+        const uint32_t bar = smem_u32(&bars[tail]);
+        mbar_expect_tx(bar, p.row_bytes);
+        bulk_g2s(smem_u32(ring + (size_t)tail * p.stage_bytes), p.rows + (size_t)row * p.row_bytes,
+                 p.row_bytes, bar, policy);
+      }
+      if (++tail == S) tail = 0;
+      inflight++;
+      if (!bits) {
+        word += GW;
+        load_word();
+      }
+    }
+    if (inflight == 0) break;
+
+    mbar_wait(smem_u32(&bars[head]), hpar);
+    const uint32_t row = __shfl_sync(0xFFFFFFFFu, my_row, head);
+    float acc[QB];
+    float bb = 0.0f;
+#pragma unroll
+    for (int q = 0; q < QB; q++) acc[q] = 0.0f;
+    const uint4 *stage = reinterpret_cast<const uint4 *>(ring + (size_t)head * p.stage_bytes);
+#pragma unroll 2
+    for (uint32_t c = lane; c < cpr; c += 32) {
+      float b[E];
+      uint4 v = stage[c];
+      Chunk<DTYPE>::unpack(v, b);
+      if (METRIC == kCos) {
+#pragma unroll
+        for (int e = 0; e < E; e++) bb = fmaf(b[e], b[e], bb);
+      }
+#pragma unroll
+      for (int q = 0; q < QB; q++) {
+        const float4 *qp = reinterpret_cast<const float4 *>(qs + (size_t)q * p.qld + (size_t)c * E);
+#pragma unroll
+        for (int h = 0; h < E / 4; h++) {
+          float4 t = qp[h];
+          const float a[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            if (METRIC == kL2) {
+              float d = a[e] - b[4 * h + e];
+              acc[q] = fmaf(d, d, acc[q]);
+            } else {
+              acc[q] = fmaf(a[e], b[4 * h + e], acc[q]);
             }
           }
         }
-        __syncthreads();
       }
     }
-    uint64_t *out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * kp;
-    for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) out[i] = sortbuf[i];
+    __syncwarp();  // stage `head` is free again
+    if (++head == S) {
+      head = 0;
+      hpar ^= 1u;
+    }
+    inflight--;
+
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      if (METRIC == kCos) bb += __shfl_xor_sync(0xFFFFFFFFu, bb, o);
+#pragma unroll
+      for (int q = 0; q < QB; q++) acc[q] += __shfl_xor_sync(0xFFFFFFFFu, acc[q], o);
+    }
+#pragma unroll
+    for (int q = 0; q < QB; q++) {
+      float key;
+      if (METRIC == kL2) {
+        key = acc[q];
+      } else if (METRIC == kIP) {
+        key = -acc[q];
+      } else {
+        key = (bb > 0.0f) ? -acc[q] * rsqrtf(bb) : 0.0f;
+      }
+      key += 0.0f;
+      uint32_t uk = ordered_key(key);
+      if (uk < thr[q] && (uint32_t)q < p.nq)
+        thr[q] = list_insert(lkeys + (size_t)q * kp, lids + (size_t)q * kp, (int)kp, uk, row, lane);
+    }
   }
+  __syncwarp();
+  scan_block_merge(p, sortbuf, lkeys, lids, kp, warp, warps, lane);
 }
 
 }  // namespace tsc
