@@ -282,3 +282,61 @@ def node_location(node_id: int, per_page: int, pages_per_partition: int):
     logical = node_id // per_page
     return (logical // pages_per_partition, 1 + logical % pages_per_partition,
             node_id % per_page)
+
+
+# --------------------------------------------------------------------------
+# synthetic on-disk NGH index (test fixture writer): the files a flushed ToStore
+# database holds for one vector index — meta.json, rawvec/ and graph/ partition
+# files with a per-file meta page at page 0 (core/ngh_page.dart:29-98).
+# --------------------------------------------------------------------------
+PT_NGH_META = 5
+
+
+def _partition_meta_page(partition: int, category: int, total: int, file_size: int,
+                         page_size: int) -> bytes:
+    payload = struct.pack("<IHHiiqqii", 0x3148474E, 1, category, partition, 0, total, file_size,
+                          -1, 0)
+    payload += b"\0" * (128 - len(payload))
+    return build_page(PT_NGH_META, payload, page_size)
+
+
+def write_ngh_index(index_dir: str, rows: np.ndarray, metric: str, precision: int,
+                    deleted=None, page_size: int = 16384, max_partition_file_size: int = 16 * 1024 * 1024,
+                    max_degree: int = 64, max_entries_per_dir: int = 500):
+    import json
+    import os
+    rows = np.asarray(rows, dtype=np.float32)
+    n, dims = rows.shape
+    bpe = bytes_per_element(precision)
+    rpp = vectors_per_raw_page(page_size, dims, bpe)
+    npg = nodes_per_graph_page(page_size, max_degree)
+    ppp = max_partition_file_size // page_size
+    flags = np.zeros(n, dtype=np.uint8)
+    if deleted is not None:
+        flags[np.asarray(deleted, dtype=bool)] = 1
+
+    def write_category(cat_name, cat_code, per_page, make_page):
+        n_logical = -(-n // per_page) if n else 0
+        for part in range(-(-n_logical // ppp) if n_logical else 0):
+            d = os.path.join(index_dir, "ngh", cat_name, f"dir_{part // max_entries_per_dir}")
+            os.makedirs(d, exist_ok=True)
+            pages = []
+            for lp in range(part * ppp, min((part + 1) * ppp, n_logical)):
+                pages.append(make_page(lp * per_page, min(n, (lp + 1) * per_page)))
+            size = (1 + len(pages)) * page_size
+            with open(os.path.join(d, f"p{part}.ngh"), "wb") as f:
+                f.write(_partition_meta_page(part, cat_code, sum(1 for _ in pages), size, page_size))
+                f.write(b"".join(pages))
+
+    os.makedirs(os.path.join(index_dir, "ngh"), exist_ok=True)
+    write_category("rawvec", 2, rpp, lambda a, b: build_rawvec_page(rows[a:b], dims, precision, page_size))
+    write_category("graph", 0, npg, lambda a, b: build_graph_page(flags[a:b].tolist(), max_degree, page_size))
+    meta = {"version": 1, "name": "idx_embedding", "tableName": "t", "fieldName": "embedding",
+            "dimensions": dims, "distanceMetric": metric,
+            "precision": {F64: "float64", F32: "float32", I8: "int8"}[precision],
+            "maxDegree": max_degree, "totalVectors": n, "deletedCount": int(flags.sum()),
+            "nextNodeId": n, "nghPageSize": page_size, "rawVectorPartitionCount": 1,
+            "graphPartitionCount": 1, "maxPartitionFileSize": max_partition_file_size}
+    with open(os.path.join(index_dir, "ngh", "meta.json"), "w") as f:
+        json.dump(meta, f)
+    return meta

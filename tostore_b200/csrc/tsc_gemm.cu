@@ -69,6 +69,70 @@ int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_
   return TSC_OK;
 }
 
+// SS kernel for one CTA (CG = 1) or a CTA pair (CG = 2) per tile
+template <int CG>
+static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, float *dbg_keys,
+                         uint32_t *out_lists, cudaStream_t st) {
+  const int dtype = ix->desc.dev_dtype;
+  const uint32_t q_units = (p.q_tiles + CG - 1) / CG;
+  uint32_t slices = (uint32_t)(ix->sm_count / CG) / q_units;
+  if (slices == 0) {
+    set_error("gemm: nq=%u needs more query tiles than SMs", nq);
+    return TSC_ERR_BAD_ARG;
+  }
+  if (slices > p.n_tiles) slices = p.n_tiles;
+  p.n_slices = slices;
+  uint32_t stages = CG == 2 ? 5 : 4;
+  const char *ev = getenv("TSC_GEMM_STAGES");
+  if (ev && atoi(ev) >= 2) stages = (uint32_t)atoi(ev);
+  while (stages > 2 && gemm_smem_bytes<CG>(stages, kprime) > ix->smem_optin) stages--;
+  p.stages = stages;
+  const size_t smem = gemm_smem_bytes<CG>(stages, kprime);
+  if (smem > ix->smem_optin) {
+    set_error("gemm: shared memory %zu exceeds %zu", smem, ix->smem_optin);
+    return TSC_ERR_UNSUPPORTED;
+  }
+  CUtensorMap map_q, map_b;
+  int32_t rc = make_map(&map_q, dtype, ix->d_q16, nq, ix->ld, ix->row_bytes, kGemmBM);
+  if (rc != TSC_OK) return rc;
+  rc = make_map(&map_b, dtype, ix->d_rows, ix->rows, ix->ld, ix->row_bytes, GemmGeom<CG>::kBRows);
+  if (rc != TSC_OK) return rc;
+
+  static bool attr_done[64] = {false};
+  if (!attr_done[ix->device & 63]) {
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true, CG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+    attr_done[ix->device & 63] = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(q_units * CG * p.n_slices);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const uint32_t idesc = umma_idesc_f16(dtype, kGemmBM * CG, kGemmBN);
+  int slot = 0;
+  rc = hot_timer_begin(ix, st, &slot);
+  if (rc != TSC_OK) return rc;
+  if (dbg_keys)
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, CG>, map_q, map_b, p, idesc));
+  else
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG>, map_q, map_b, p, idesc));
+  ix->launches++;
+  *out_lists = p.n_slices * 2;
+  // algorithmic work: 2 * nq * N * d flops; corpus bytes read once (SURVEY.md §8d)
+  return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
+                       2.0 * nq * (double)ix->rows * ix->desc.dims);
+}
+
 // d_q: fp32 [nq, qld]. d_cand receives [nq][n_slices][kprime]; *out_lists = n_slices.
 int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
                     uint32_t *out_lists, float *dbg_keys, cudaStream_t st) {
@@ -100,14 +164,6 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
   p.cand = d_cand;
   p.dbg_keys = dbg_keys;
   if (const char *xe = getenv("TSC_GEMM_EXP")) p.exp_flags = (uint32_t)atoi(xe);
-  p.l2_prefetch = 0;  // measured: no gain on B200 (the SM ingest port, not HBM latency, binds)
-  if (const char *pe = getenv("TSC_GEMM_L2PF")) p.l2_prefetch = (uint32_t)atoi(pe);
-  p.lockstep_window = 0;
-  if (const char *we = getenv("TSC_GEMM_LOCKSTEP")) p.lockstep_window = (uint32_t)atoi(we);
-  if (p.lockstep_window > 0 && ix->d_progress) {
-    TSC_CUDA(cudaMemsetAsync(ix->d_progress, 0, 4096 * sizeof(int), st));
-    p.progress = ix->d_progress;
-  }
   // A-in-TMEM variant whenever the query tile fits 384 TMEM columns (dims <= 768)
   const char *tsenv = getenv("TSC_GEMM_TS");
   // (measured slower than the SS kernel on B200 - 64-column tiles pay too many
@@ -152,46 +208,11 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
     return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
                          2.0 * nq * (double)ix->rows * ix->desc.dims);
   }
-  uint32_t stages = 4;
-  const char *ev = getenv("TSC_GEMM_STAGES");
-  if (ev && atoi(ev) >= 2) stages = (uint32_t)atoi(ev);
-  while (stages > 2 && gemm_smem_bytes(stages, kprime) > ix->smem_optin) stages--;
-  p.stages = stages;
-  const size_t smem = gemm_smem_bytes(stages, kprime);
-  if (smem > ix->smem_optin) {
-    set_error("gemm: shared memory %zu exceeds %zu", smem, ix->smem_optin);
-    return TSC_ERR_UNSUPPORTED;
-  }
-
-  CUtensorMap map_q, map_b;
-  rc = make_map(&map_q, dtype, ix->d_q16, nq, ix->ld, ix->row_bytes, kGemmBM);
-  if (rc != TSC_OK) return rc;
-  rc = make_map(&map_b, dtype, ix->d_rows, ix->rows, ix->ld, ix->row_bytes, kGemmBN);
-  if (rc != TSC_OK) return rc;
-
-  static bool attr_done[64] = {false};
-  if (!attr_done[ix->device & 63]) {
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-    attr_done[ix->device & 63] = true;
-  }
-  int slot = 0;
-  rc = hot_timer_begin(ix, st, &slot);
-  if (rc != TSC_OK) return rc;
-  if (dbg_keys)
-    gemm_topk_kernel<true><<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
-        map_q, map_b, p, umma_idesc_f16(dtype, kGemmBM, kGemmBN));
-  else
-    gemm_topk_kernel<false><<<p.q_tiles * p.n_slices, kGemmThreads, smem, st>>>(
-        map_q, map_b, p, umma_idesc_f16(dtype, kGemmBM, kGemmBN));
-  TSC_CUDA(cudaGetLastError());
-  ix->launches++;
-  *out_lists = p.n_slices * 2;
-  // algorithmic work: 2 * nq * N * d flops; corpus bytes read once (SURVEY.md §8d)
-  return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
-                       2.0 * nq * (double)ix->rows * ix->desc.dims);
+  // CTA pairs (cta_group::2) whenever the query tiles pair up evenly; TSC_GEMM_2CTA=0/1 overrides
+  bool pair = (p.q_tiles % 2) == 0;
+  if (const char *ce = getenv("TSC_GEMM_2CTA")) pair = atoi(ce) != 0;
+  return pair ? launch_ss<2>(ix, p, nq, kprime, dbg_keys, out_lists, st)
+              : launch_ss<1>(ix, p, nq, kprime, dbg_keys, out_lists, st);
 }
 
 }  // namespace tsc

@@ -53,9 +53,6 @@ struct GemmParams {
   const uint32_t *live_mask; // optional
   uint64_t *cand;            // [nq][n_slices * 2][kprime] (two column halves per CTA)
   float *dbg_keys;           // optional [nq][n_rows] (tests only)
-  int *progress;             // [n_slices][q_tiles] tiles issued by each CTA's producer (lockstep)
-  uint32_t lockstep_window;  // a CTA may run at most this many tiles ahead of its slice mates
-  uint32_t l2_prefetch;      // corpus tiles (of this slice) prefetched into L2 ahead of use
   uint32_t exp_flags;        // perf experiments (results invalid when non-zero): 1 = producer
                              // re-loads one corpus tile, 2 = epilogue skips the TMEM read,
                              // 4 = no TMA at all (MMA issue rate only), 8 = skip A loads
@@ -163,13 +160,6 @@ __host__ __device__ inline uint32_t umma_idesc_f16(int dtype, int m, int n) {
          ((uint32_t)(m >> 4) << 24);
 }
 
-// smem: [stages x (A 16 KB | B 32 KB)] [scale 2x256 f32][bias 2x256 f32]
-//       [lists: keys kp x 128 f32 | rows kp x 128 u32] [barriers] [tmem ptr]
-__host__ __device__ inline size_t gemm_smem_bytes(uint32_t stages, uint32_t kprime) {
-  return 1024 /* alignment slack */ + (size_t)stages * (16384 + 32768) + 2 * 2 * 256 * 4 +
-         (size_t)kprime * kGemmEpiThreads * 8 + (2 * stages + 4) * 8 + 16;
-}
-
 // Insert into one thread's sorted (ascending) list, column-major in smem
 // ([kp][128 threads]); returns the new threshold. Equal keys keep arrival (row) order.
 __device__ __noinline__ float gemm_list_insert(float *l_keys, uint32_t *l_rows, uint32_t kp,
@@ -185,7 +175,92 @@ __device__ __noinline__ float gemm_list_insert(float *l_keys, uint32_t *l_rows, 
   return l_keys[(kp - 1) * kGemmEpiThreads + qlane];
 }
 
-template <bool DBG>
+// ---- CTA-pair (cta_group::2) helpers ------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+               : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier of the pair's leader
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map,
+                                                uint32_t cluster_bar, int32_t c0, int32_t c1,
+                                                uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss2(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the MMAs issued so far have completed) on the barrier at this smem
+// offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit2(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+// ====================================================================================
+// The SS kernel, for one CTA (CG = 1) or a CTA pair (CG = 2, cta_group::2).
+//
+// CG = 2: two SMs of a cluster cooperate on a 256 (queries) x 256 (corpus rows)
+// tile. Each CTA stages its own 128 queries and only HALF of the corpus tile; one
+// tcgen05.mma.cta_group::2 issued by the leader drives both tensor cores (M = 256:
+// rows 0-127 from the leader's A, 128-255 from the peer's; N = 256: columns 0-127
+// from the leader's B half, 128-255 from the peer's). The bytes an SM has to ingest
+// per MMA cycle drop from 96 to 64 - the limit measured for the 1-CTA shape.
+//
+// Epilogue warps never synchronise with each other: each warp prepares the per-column
+// coefficients of its own 128 columns, so a warp that is busy inserting candidates
+// (frequent while the lists are still filling) does not hold the others back.
+// ====================================================================================
+template <int CG>
+struct GemmGeom {
+  static constexpr uint32_t kBRows = 256 / CG;                  // corpus rows this CTA stages
+  static constexpr uint32_t kStageBytes = 16384 + kBRows * 128; // A 16 KB + B
+};
+// smem: [stages x (A | B)] [coeffs: 8 warps x 2 bufs x {scale,bias} x 128] [lists] [barriers]
+template <int CG>
+__host__ __device__ inline size_t gemm_smem_bytes(uint32_t stages, uint32_t kprime) {
+  return 1024 + (size_t)stages * GemmGeom<CG>::kStageBytes + 8 * 2 * 128 * 2 * 4 +
+         (size_t)kprime * kGemmEpiThreads * 8 + (2 * stages + 4) * 8 + 16;
+}
+
+template <bool DBG, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p, const uint32_t idesc) {
@@ -193,18 +268,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SW128 needs 1024 B alignment
   uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t S = p.stages;
-  constexpr uint32_t kStageBytes = 16384 + 32768;
-  float *s_scale = reinterpret_cast<float *>(sm + (size_t)S * kStageBytes);  // [2][256]
-  float *s_bias = s_scale + 2 * 256;                                         // [2][256]
-  float *l_keys = s_bias + 2 * 256;                                          // [kp][128]
+  constexpr uint32_t kStageBytes = GemmGeom<CG>::kStageBytes;
+  float *s_coef = reinterpret_cast<float *>(sm + (size_t)S * kStageBytes);  // [8][2][2][128]
+  float *l_keys = s_coef + 8 * 2 * 2 * 128;                                  // [kp][256]
   uint32_t *l_rows = reinterpret_cast<uint32_t *>(l_keys + (size_t)p.kprime * kGemmEpiThreads);
   uint64_t *bars = reinterpret_cast<uint64_t *>(l_rows + (size_t)p.kprime * kGemmEpiThreads);
   uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t qt = blockIdx.x % p.q_tiles;
-  const uint32_t slice = blockIdx.x / p.q_tiles;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const uint32_t unit = blockIdx.x / CG;                      // CTA (pair) index
+  const uint32_t q_units = (p.q_tiles + CG - 1) / CG;
+  const uint32_t qt = (unit % q_units) * CG + crank;          // this CTA's query tile
+  const uint32_t slice = unit / q_units;
 
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -215,55 +292,43 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(smem_u32(&tfull[a]), 1);
-      mbar_init(smem_u32(&tempty[a]), kGemmEpiThreads);
+      mbar_init(smem_u32(&tempty[a]), CG * 8);   // one arrival per epilogue warp (of both CTAs)
     }
     mbar_fence_init();
   }
-  if (warp == kWarpMma) tmem_alloc(smem_u32(s_tmem), 512);
+  if (warp == kWarpMma) {
+    if (CG == 2) tmem_alloc2(smem_u32(s_tmem), 512);
+    else tmem_alloc(smem_u32(s_tmem), 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
   if (warp == kWarpTma) {
     // ===== TMA producer (whole warp walks the loop, one elected lane issues) =====
     const uint64_t pol_q = policy_evict_normal();  // queries are re-read by every tile
-    const uint64_t pol_b = policy_evict_normal();  // corpus tile is shared by q_tiles CTAs
+    const uint64_t pol_b = policy_evict_normal();  // corpus tile is shared by the slice's CTAs
     uint32_t s = 0, ph = 0;
-    uint32_t t_idx = 0;  // tiles this CTA has started loading
-    for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices, t_idx++) {
-      // The q_tiles CTAs of a slice read the same corpus tiles; only the first read
-      // of a tile should come from HBM. Keep them within `lockstep_window` tiles of
-      // each other so the tile is still in L2 when the others arrive.
-      if (p.progress && p.q_tiles > 1) {
-        volatile int *pr = p.progress + (size_t)slice * p.q_tiles;
-        if (lane == 0) pr[qt] = (int)t_idx;
-        if (lane < p.q_tiles && t_idx > p.lockstep_window) {
-          const int need = (int)(t_idx - p.lockstep_window);
-          while (pr[lane] < need) {
-          }
-        }
-        __syncwarp();
-      }
+    for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
       for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
-        if (p.exp_flags & 4u) continue;
         mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
         if (elect_one()) {
-          const uint32_t bar = smem_u32(&full[s]);
-          const bool skip_a = (p.exp_flags & 8u) != 0;
-          mbar_expect_tx(bar, skip_a ? 32768u : kStageBytes);
           const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + 16384;
-          const uint32_t ctl = (p.exp_flags & 1u) ? slice : ct;
-          if (!skip_a)
+          if (CG == 2) {
+            // bytes of BOTH CTAs are counted on the leader's barrier: its MMA eats both halves
+            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+            if (crank == 0) mbar_expect_tx(smem_u32(&full[s]), 2 * kStageBytes);
+            tma_load_2d_2sm(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK), (int32_t)(qt * kGemmBM),
+                            pol_q);
+            tma_load_2d_2sm(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK),
+                            (int32_t)(ct * kGemmBN + crank * GemmGeom<CG>::kBRows), pol_b);
+          } else {
+            const uint32_t bar = smem_u32(&full[s]);
+            mbar_expect_tx(bar, kStageBytes);
             tma_load_2d(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK), (int32_t)(qt * kGemmBM), pol_q);
-          tma_load_2d(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK), (int32_t)(ctl * kGemmBN), pol_b);
-          // Every CTA of a slice reads this corpus tile at about the same time, so all
-          // of them would sit behind the same HBM miss. One of them (round robin over
-          // the K blocks) pulls the slice's tile `l2_prefetch` steps ahead into L2.
-          if (p.l2_prefetch && kb % p.q_tiles == qt) {
-            const uint32_t ctp = ct + p.l2_prefetch * p.n_slices;
-            if (ctp < p.n_tiles)
-              tma_prefetch_l2_2d(&map_b, (int32_t)(kb * kGemmBK), (int32_t)(ctp * kGemmBN));
+            tma_load_2d(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK), (int32_t)(ct * kGemmBN), pol_b);
           }
         }
         __syncwarp();
@@ -271,46 +336,62 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
       }
     }
   } else if (warp == kWarpMma) {
-    // ===== MMA issuer (whole warp walks the loop, one elected lane issues) =====
-    uint32_t s = 0, ph = 0, as = 0, aph = 0;
-    const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
-    for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
-      mbar_wait(smem_u32(&tempty[as]), aph ^ 1u);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * kGemmBN;
-      for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
-        if (!(p.exp_flags & 4u)) mbar_wait(smem_u32(&full[s]), ph);
+    // ===== MMA issuer (whole warp walks the loop, one elected lane issues; with a CTA
+    // pair only the leader issues and its commits are multicast to both CTAs) =====
+    if (crank == 0) {
+      uint32_t s = 0, ph = 0, as = 0, aph = 0;
+      const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+      for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
+        mbar_wait(smem_u32(&tempty[as]), aph ^ 1u);  // epilogues have drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = base + s * kStageBytes, b_addr = a_addr + 16384;
-          const uint32_t a_lo = (uint32_t)umma_desc_sw128(a_addr);
-          const uint32_t b_lo = (uint32_t)umma_desc_sw128(b_addr);
+        const uint32_t d_tmem = tmem_base + as * kGemmBN;
+        for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
+          mbar_wait(smem_u32(&full[s]), ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_addr = base + s * kStageBytes, b_addr = a_addr + 16384;
+            const uint32_t a_lo = (uint32_t)umma_desc_sw128(a_addr);
+            const uint32_t b_lo = (uint32_t)umma_desc_sw128(b_addr);
 #pragma unroll
-          for (int k = 0; k < kGemmBK / kGemmUK; k++) {
-            // +32 bytes per K step inside the 128-byte swizzle row (units of 16 B)
-            umma_ss(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
-                    (kb | k) != 0);
+            for (int k = 0; k < kGemmBK / kGemmUK; k++) {
+              // +32 bytes per K step inside the 128-byte swizzle row (units of 16 B)
+              if (CG == 2)
+                umma_ss2(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                         (kb | k) != 0);
+              else
+                umma_ss(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                        (kb | k) != 0);
+            }
+            if (CG == 2) {
+              umma_commit2(smem_u32(&empty[s]));  // frees the stage in both CTAs
+              if (kb + 1 == p.k_blocks) umma_commit2(smem_u32(&tfull[as]));
+            } else {
+              umma_commit(smem_u32(&empty[s]));
+              if (kb + 1 == p.k_blocks) umma_commit(smem_u32(&tfull[as]));
+            }
           }
-          umma_commit(smem_u32(&empty[s]));  // frees the smem stage when these MMAs retire
-          if (kb + 1 == p.k_blocks) umma_commit(smem_u32(&tfull[as]));  // accumulator complete
+          __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
+        if (++as == 2) { as = 0; aph ^= 1u; }
       }
-      if (++as == 2) { as = 0; aph ^= 1u; }
     }
   } else {
     // ===== epilogue: 8 warps; thread <-> (query, half of the tile's columns) =====
-    // TMEM lane quadrant = warp % 4 (hardware rule); warps 2-5 take columns
-    // [0,128) of every tile, warps 6-9 columns [128,256). Each thread keeps its own
-    // threshold (register) and sorted list (smem), so a query has two lists per CTA.
-    const int et = threadIdx.x;                      // 0..255
+    // TMEM lane quadrant = warp % 4 (hardware rule); warps 0-3 take columns [0,128) of
+    // every tile, warps 4-7 columns [128,256). Each thread keeps its own threshold
+    // (register) and sorted list (smem), so a query has two lists per CTA.
     const int quad = warp & 3;
-    const int half = warp >> 2;                      // 0 / 1
+    const int half = warp >> 2;
     const int qlane = quad * 32 + lane;              // query row inside the tile
     const int lidx = half * 128 + qlane;             // list slot, 0..255
     const uint32_t q = qt * kGemmBM + qlane;
     const uint32_t kp = p.kprime;
+    const uint32_t col_base = (uint32_t)half * 128;
+    float *w_coef = s_coef + (size_t)warp * (2 * 2 * 128);   // [buf][scale|bias][128]
+    const uint32_t tempty_bar[2] = {
+        CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]),
+        CG == 2 ? mapa_u32(smem_u32(&tempty[1]), 0) : smem_u32(&tempty[1])};
     for (uint32_t j = 0; j < kp; j++) {
       l_keys[j * kGemmEpiThreads + lidx] = __int_as_float(0x7F800000);
       l_rows[j * kGemmEpiThreads + lidx] = kInvalidRow;
@@ -318,34 +399,38 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     float thr = __int_as_float(0x7F800000);
     uint32_t as = 0, aph = 0;
 
-    // per-column scale / bias (dead or out-of-range rows -> NaN key); thread `et`
-    // owns column `et` of every tile and prefetches the next tile's value one tile
-    // ahead so the global-load latency is off the critical path
-    auto column_coeffs = [&](uint32_t ct, float &sc, float &bi) {
-      const uint64_t n = (uint64_t)ct * kGemmBN + et;
-      sc = __int_as_float(0x7FC00000);
-      bi = 0.0f;
-      bool live = ct < p.n_tiles && n < p.n_rows;
-      if (live && p.live_mask) live = (p.live_mask[n >> 5] >> (n & 31)) & 1u;
-      if (live) {
-        if (p.metric == kIP || (p.exp_flags & 64u)) {
-          sc = -1.0f;
-        } else {
-          const float n2 = __ldg(p.norm2 + n);
-          if (p.metric == kL2) { sc = -2.0f; bi = n2; }
-          else { sc = n2 > 0.0f ? -rsqrtf(n2) : 0.0f; }
+    // per-column scale / bias (dead or out-of-range rows -> NaN key). Lane l prepares
+    // columns l, l+32, l+64, l+96 of the warp's half and prefetches the next tile's
+    // values one tile ahead so the global-load latency is off the critical path.
+    float sc_n[4], bi_n[4];
+    auto column_coeffs = [&](uint32_t ct) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint64_t n = (uint64_t)ct * kGemmBN + col_base + j * 32 + lane;
+        float sc = __int_as_float(0x7FC00000), bi = 0.0f;
+        bool live = ct < p.n_tiles && n < p.n_rows;
+        if (live && p.live_mask) live = (p.live_mask[n >> 5] >> (n & 31)) & 1u;
+        if (live) {
+          if (p.metric == kIP) {
+            sc = -1.0f;
+          } else {
+            const float n2 = __ldg(p.norm2 + n);
+            if (p.metric == kL2) { sc = -2.0f; bi = n2; }
+            else { sc = n2 > 0.0f ? -rsqrtf(n2) : 0.0f; }
+          }
         }
+        sc_n[j] = sc;
+        bi_n[j] = bi;
       }
     };
-    float sc_next, bi_next;
-    column_coeffs(slice, sc_next, bi_next);
+    column_coeffs(slice);
 
-    auto process = [&](const uint32_t (&v)[32], uint32_t col0, uint64_t row0) {
-      // straight-line common path: 32 keys + their minimum; the (rare) insertion
-      // walk only runs when some key beats this thread's current threshold
+    auto process = [&](const uint32_t (&v)[32], uint32_t c0, uint64_t row0) {
+      // straight-line common path: 32 keys + their minimum; the (rarer) insertion walk
+      // only runs when some key beats this thread's current threshold
       float key[32];
-      const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + as * 256 + col0);
-      const float4 *bi4 = reinterpret_cast<const float4 *>(s_bias + as * 256 + col0);
+      const float4 *sc4 = reinterpret_cast<const float4 *>(w_coef + as * 256 + c0);
+      const float4 *bi4 = reinterpret_cast<const float4 *>(w_coef + as * 256 + 128 + c0);
       float lo = __int_as_float(0x7F800000);
 #pragma unroll
       for (int j4 = 0; j4 < 8; j4++) {
@@ -358,81 +443,56 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         lo = fminf(lo, fminf(fminf(key[4 * j4 + 0], key[4 * j4 + 1]),
                              fminf(key[4 * j4 + 2], key[4 * j4 + 3])));
       }
+      const uint64_t r0 = row0 + col_base + c0;
       if (DBG) {
         if (q < p.nq)
 #pragma unroll
           for (int j = 0; j < 32; j++)
-            if (row0 + col0 + j < p.n_rows)
-              p.dbg_keys[(size_t)q * p.n_rows + row0 + col0 + j] = key[j] + 0.0f;
+            if (r0 + j < p.n_rows) p.dbg_keys[(size_t)q * p.n_rows + r0 + j] = key[j] + 0.0f;
       }
       if (lo < thr) {
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           if (key[j] < thr)
-            thr = gemm_list_insert(l_keys, l_rows, kp, lidx, key[j] + 0.0f,
-                                   (uint32_t)(row0 + col0 + j));
+            thr = gemm_list_insert(l_keys, l_rows, kp, lidx, key[j] + 0.0f, (uint32_t)(r0 + j));
         }
       }
     };
 
     for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
       const uint64_t row0 = (uint64_t)ct * kGemmBN;
-      s_scale[as * 256 + et] = sc_next;
-      s_bias[as * 256 + et] = bi_next;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
-      column_coeffs(ct + p.n_slices, sc_next, bi_next);  // prefetch for the next tile
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        w_coef[as * 256 + j * 32 + lane] = sc_n[j];
+        w_coef[as * 256 + 128 + j * 32 + lane] = bi_n[j];
+      }
+      __syncwarp();
+      column_coeffs(ct + p.n_slices);  // prefetch for the next tile
       mbar_wait(smem_u32(&tfull[as]), aph);
       tc_fence_after();
-      const uint32_t col_base = (uint32_t)half * 128;
       const uint32_t t_addr =
           tmem_base + ((uint32_t)(quad * 32) << 16) + as * kGemmBN + col_base;
-      if (p.exp_flags & 2u) {
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tempty[as]));
-        if (++as == 2) { as = 0; aph ^= 1u; }
-        continue;
-      }
-      // 4 chunks of 32 columns, TMEM loads software-pipelined over two register sets
-      uint32_t va[32], vb[32];
-      if (p.exp_flags & 32u) {  // experiment: compute on whatever the registers hold
-#pragma unroll
-        for (int j = 0; j < 32; j++) { va[j] = j * 0x3f800000u + ct; vb[j] = va[j] ^ 0x12345u; }
-        process(va, col_base, row0);
-        process(vb, col_base + 32, row0);
-        process(va, col_base + 64, row0);
-        process(vb, col_base + 96, row0);
-      } else if (p.exp_flags & 16u) {  // experiment: TMEM reads only
-        tmem_ld32_nowait(t_addr, va);
-        tmem_ld32_nowait(t_addr + 32, vb);
-        tmem_ld_wait();
-        uint32_t acc = va[0] ^ vb[31];
-        tmem_ld32_nowait(t_addr + 64, va);
-        tmem_ld32_nowait(t_addr + 96, vb);
-        tmem_ld_wait();
-        if ((acc ^ va[5] ^ vb[7]) == 0x7fc12345u) thr = 0.0f;
-      } else {
-        // All four TMEM loads of this thread's 128 columns are issued back to back:
-        // measured, a tcgen05.ld that has to wait behind the tensor core's accumulator
-        // traffic takes ~1 us, so serialising them (load, compute, load, ...) made the
-        // epilogue slower than the MMA of the next tile. Once the registers hold the
-        // tile the TMEM buffer is handed back before any arithmetic.
-        uint32_t vc[32], vd[32];
-        tmem_ld32_nowait(t_addr, va);
-        tmem_ld32_nowait(t_addr + 32, vb);
-        tmem_ld32_nowait(t_addr + 64, vc);
-        tmem_ld32_nowait(t_addr + 96, vd);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tempty[as]));
-        process(va, col_base, row0);
-        process(vb, col_base + 32, row0);
-        process(vc, col_base + 64, row0);
-        process(vd, col_base + 96, row0);
-        if (++as == 2) { as = 0; aph ^= 1u; }
-        continue;
-      }
+      // All four TMEM loads of this thread's 128 columns are issued back to back:
+      // measured, a tcgen05.ld that has to wait behind the tensor core's accumulator
+      // traffic is slow, and serialising them (load, compute, load, ...) made the
+      // epilogue as slow as the next tile's MMA. Once the registers hold the tile the
+      // TMEM buffer is handed back before any arithmetic.
+      uint32_t va[32], vb[32], vc[32], vd[32];
+      tmem_ld32_nowait(t_addr, va);
+      tmem_ld32_nowait(t_addr + 32, vb);
+      tmem_ld32_nowait(t_addr + 64, vc);
+      tmem_ld32_nowait(t_addr + 96, vd);
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(smem_u32(&tempty[as]));
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_bar[as]);
+        else mbar_arrive(tempty_bar[as]);
+      }
+      process(va, 0, row0);
+      process(vb, 32, row0);
+      process(vc, 64, row0);
+      process(vd, 96, row0);
       if (++as == 2) { as = 0; aph ^= 1u; }
     }
     if (q < p.nq) {
@@ -447,8 +507,12 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
+  if (CG == 2) cluster_sync_all();  // peer arrivals on the leader's barriers must land first
+  else __syncthreads();
+  if (warp == kWarpMma) {
+    if (CG == 2) tmem_dealloc2(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 // ====================================================================================
