@@ -1,5 +1,6 @@
 // tsc_gemm.cu — host launcher for K2 (tsc_gemm.cuh): TMA tensor maps, tile
 // scheduling geometry, row norms (K4).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "tsc_gemm.cuh"
@@ -70,7 +71,7 @@ int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_
 }
 
 // SS kernel for one CTA (CG = 1) or a CTA pair (CG = 2) per tile
-template <int CG>
+template <int CG, int KPR>
 static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, float *dbg_keys,
                          uint32_t *out_lists, cudaStream_t st) {
   const int dtype = ix->desc.dev_dtype;
@@ -98,13 +99,24 @@ static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, 
   rc = make_map(&map_b, dtype, ix->d_rows, ix->rows, ix->ld, ix->row_bytes, GemmGeom<CG>::kBRows);
   if (rc != TSC_OK) return rc;
 
-  static bool attr_done[64] = {false};
+  static bool attr_done[64] = {false};   // per (CG, KPR) instantiation
   if (!attr_done[ix->device & 63]) {
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG>,
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG, false, KPR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true, CG>,
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true, CG, false, KPR>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG, true, KPR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
     attr_done[ix->device & 63] = true;
+  }
+  // diagnostics (never set in production): TSC_GEMM_EXP = experiment bit mask,
+  // TSC_GEMM_PROF=1 prints the per-role wait / work cycle averages of this launch
+  const char *prof_env = getenv("TSC_GEMM_PROF");
+  const bool prof = prof_env && atoi(prof_env) != 0 && ix->d_progress && !dbg_keys;
+  const bool exp_kernel = (p.exp_flags != 0 || prof) && !dbg_keys;
+  if (prof) {
+    TSC_CUDA(cudaMemsetAsync(ix->d_progress, 0, kProfSlots * 8, st));
+    p.prof = reinterpret_cast<unsigned long long *>(ix->d_progress);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(q_units * CG * p.n_slices);
@@ -123,14 +135,34 @@ static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, 
   rc = hot_timer_begin(ix, st, &slot);
   if (rc != TSC_OK) return rc;
   if (dbg_keys)
-    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, CG>, map_q, map_b, p, idesc));
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, CG, false, KPR>, map_q, map_b, p, idesc));
+  else if (exp_kernel)
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG, true, KPR>, map_q, map_b, p, idesc));
   else
-    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG>, map_q, map_b, p, idesc));
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG, false, KPR>, map_q, map_b, p, idesc));
   ix->launches++;
   *out_lists = p.n_slices * 2;
   // algorithmic work: 2 * nq * N * d flops; corpus bytes read once
-  return hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
-                       2.0 * nq * (double)ix->rows * ix->desc.dims);
+  rc = hot_timer_end(ix, st, slot, (double)ix->rows * ix->desc.dims * ix->elem_bytes,
+                     2.0 * nq * (double)ix->rows * ix->desc.dims);
+  if (rc == TSC_OK && prof) {
+    unsigned long long h[kProfSlots];
+    TSC_CUDA(cudaMemcpyAsync(h, ix->d_progress, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TSC_CUDA(cudaStreamSynchronize(st));
+    auto avg = [&](int slot_, int n_) { return h[n_] ? (double)h[slot_] / (double)h[n_] : 0.0; };
+    fprintf(stderr,
+            "gemm_prof cg=%d stages=%u exp=%u | prod: wait_empty %.0f of %.0f | mma: "
+            "wait_full %.0f wait_tempty %.0f of %.0f | epi/warp: wait_tfull %.0f "
+            "ldtm %.0f math %.0f of %.0f (cycles, mean per role instance; %u tiles x %u k-blocks "
+            "per CTA)\n",
+            CG, p.stages, p.exp_flags, avg(kProfProdWaitEmpty, kProfProdN),
+            avg(kProfProdTotal, kProfProdN), avg(kProfMmaWaitFull, kProfMmaN),
+            avg(kProfMmaWaitTempty, kProfMmaN),
+            avg(kProfMmaTotal, kProfMmaN), avg(kProfEpiWaitTfull, kProfEpiN),
+            avg(kProfEpiLdtm, kProfEpiN), avg(kProfEpiMath, kProfEpiN),
+            avg(kProfEpiTotal, kProfEpiN), (p.n_tiles + p.n_slices - 1) / p.n_slices, p.k_blocks);
+  }
+  return rc;
 }
 
 // d_q: fp32 [nq, qld]. d_cand receives [nq][n_slices][kprime]; *out_lists = n_slices.
@@ -211,8 +243,11 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
   // CTA pairs (cta_group::2) whenever the query tiles pair up evenly; TSC_GEMM_2CTA=0/1 overrides
   bool pair = (p.q_tiles % 2) == 0;
   if (const char *ce = getenv("TSC_GEMM_2CTA")) pair = atoi(ce) != 0;
-  return pair ? launch_ss<2>(ix, p, nq, kprime, dbg_keys, out_lists, st)
-              : launch_ss<1>(ix, p, nq, kprime, dbg_keys, out_lists, st);
+  if (kprime <= 20)
+    return pair ? launch_ss<2, 20>(ix, p, nq, kprime, dbg_keys, out_lists, st)
+                : launch_ss<1, 20>(ix, p, nq, kprime, dbg_keys, out_lists, st);
+  return pair ? launch_ss<2, 32>(ix, p, nq, kprime, dbg_keys, out_lists, st)
+              : launch_ss<1, 32>(ix, p, nq, kprime, dbg_keys, out_lists, st);
 }
 
 }  // namespace tsc

@@ -53,10 +53,16 @@ struct GemmParams {
   const uint32_t *live_mask; // optional
   uint64_t *cand;            // [nq][n_slices * 2][kprime] (two column halves per CTA)
   float *dbg_keys;           // optional [nq][n_rows] (tests only)
-  uint32_t exp_flags;        // perf experiments (results invalid when non-zero): 1 = producer
-                             // re-loads one corpus tile, 2 = epilogue skips the TMEM read,
-                             // 4 = no TMA at all (MMA issue rate only), 8 = skip A loads
+  uint32_t exp_flags;        // perf experiments (EXP kernels only; results invalid when non-zero):
+                             // 1 = producer re-loads one corpus tile, 2 = epilogue skips the TMEM
+                             // read and the arithmetic, 4 = no TMA at all (MMA issue rate only),
+                             // 8 = skip A loads, 16 = epilogue TMEM reads only, 32 = arithmetic only
+  unsigned long long *prof;  // EXP kernels: per-role wait / work cycle sums (kProf* slots)
 };
+// slots of GemmParams::prof (sums over all CTAs, atomicAdd by one lane per role)
+enum : int { kProfProdWaitEmpty = 0, kProfProdTotal, kProfMmaWaitFull, kProfMmaWaitTempty,
+             kProfMmaTotal, kProfEpiWaitTfull, kProfEpiLdtm, kProfEpiMath,
+             kProfEpiTotal, kProfProdN, kProfMmaN, kProfEpiN, kProfSlots };
 
 // ---- PTX wrappers -----------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
@@ -253,14 +259,37 @@ struct GemmGeom {
   static constexpr uint32_t kBRows = 256 / CG;                  // corpus rows this CTA stages
   static constexpr uint32_t kStageBytes = 16384 + kBRows * 128; // A 16 KB + B
 };
-// smem: [stages x (A | B)] [coeffs: 8 warps x 2 bufs x {scale,bias} x 128] [lists] [barriers]
+// smem: [stages x (A | B)] [coeffs: 8 warps x 2 bufs x {scale,bias} x 128]
+//       [candidate row ids: kprime x 256] [barriers]   (candidate keys live in registers)
 template <int CG>
 __host__ __device__ inline size_t gemm_smem_bytes(uint32_t stages, uint32_t kprime) {
   return 1024 + (size_t)stages * GemmGeom<CG>::kStageBytes + 8 * 2 * 128 * 2 * 4 +
-         (size_t)kprime * kGemmEpiThreads * 8 + (2 * stages + 4) * 8 + 16;
+         (size_t)kprime * kGemmEpiThreads * 4 + (2 * stages + 4) * 8 + 16;
 }
 
-template <bool DBG, int CG>
+// dynamic pick of one of 32 registers: 31 selects, no local memory
+__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) b[i] = (j & 8) ? a[i + 8] : a[i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) c[i] = (j & 4) ? b[i + 4] : b[i];
+#pragma unroll
+  for (int i = 0; i < 2; i++) d[i] = (j & 2) ? c[i + 2] : c[i];
+  return __uint_as_float((j & 1) ? d[1] : d[0]);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// KPR = capacity of the per-thread candidate list (registers): 20 or 32 >= kprime
+// (10 warps put 3 on one scheduler: 16,384 / 96 caps a thread at 168 registers, which is
+// why the epilogue reads its 128 columns in two batches of 64 instead of all at once.)
+template <bool DBG, int CG, bool EXP, int KPR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p, const uint32_t idesc) {
@@ -270,8 +299,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t S = p.stages;
   constexpr uint32_t kStageBytes = GemmGeom<CG>::kStageBytes;
   float *s_coef = reinterpret_cast<float *>(sm + (size_t)S * kStageBytes);  // [8][2][2][128]
-  float *l_keys = s_coef + 8 * 2 * 2 * 128;                                  // [kp][256]
-  uint32_t *l_rows = reinterpret_cast<uint32_t *>(l_keys + (size_t)p.kprime * kGemmEpiThreads);
+  uint32_t *l_rows = reinterpret_cast<uint32_t *>(s_coef + 8 * 2 * 2 * 128);  // [kp][256]
   uint64_t *bars = reinterpret_cast<uint64_t *>(l_rows + (size_t)p.kprime * kGemmEpiThreads);
   uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
   uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * S + 4);
@@ -282,6 +310,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t q_units = (p.q_tiles + CG - 1) / CG;
   const uint32_t qt = (unit % q_units) * CG + crank;          // this CTA's query tile
   const uint32_t slice = unit / q_units;
+  const uint32_t xf = EXP ? p.exp_flags : 0u;
+  long long t_w0 = 0, t_w1 = 0, t_w2 = 0;   // EXP: cycle sums of this warp's role
+  auto tick = [&]() -> long long { return EXP ? clock64() : 0ll; };
 
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&map_q);
@@ -311,29 +342,45 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const uint64_t pol_q = policy_evict_normal();  // queries are re-read by every tile
     const uint64_t pol_b = policy_evict_normal();  // corpus tile is shared by the slice's CTAs
     uint32_t s = 0, ph = 0;
+    const long long t_beg = tick();
     for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
+      if (xf & 4u) break;
       for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
+        const long long t0 = tick();
         mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+        t_w0 += tick() - t0;
         if (elect_one()) {
           const uint32_t a_dst = base + s * kStageBytes, b_dst = a_dst + 16384;
+          const uint32_t ctl = (xf & 1u) ? slice : ct;
+          const bool skip_a = (xf & 8u) != 0;
+          const uint32_t bytes = skip_a ? kStageBytes - 16384 : kStageBytes;
           if (CG == 2) {
             // bytes of BOTH CTAs are counted on the leader's barrier: its MMA eats both halves
             const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
-            if (crank == 0) mbar_expect_tx(smem_u32(&full[s]), 2 * kStageBytes);
-            tma_load_2d_2sm(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK), (int32_t)(qt * kGemmBM),
-                            pol_q);
+            if (crank == 0) mbar_expect_tx(smem_u32(&full[s]), 2 * bytes);
+            if (!skip_a)
+              tma_load_2d_2sm(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK),
+                              (int32_t)(qt * kGemmBM), pol_q);
             tma_load_2d_2sm(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK),
-                            (int32_t)(ct * kGemmBN + crank * GemmGeom<CG>::kBRows), pol_b);
+                            (int32_t)(ctl * kGemmBN + crank * GemmGeom<CG>::kBRows), pol_b);
           } else {
             const uint32_t bar = smem_u32(&full[s]);
-            mbar_expect_tx(bar, kStageBytes);
-            tma_load_2d(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK), (int32_t)(qt * kGemmBM), pol_q);
-            tma_load_2d(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK), (int32_t)(ct * kGemmBN), pol_b);
+            mbar_expect_tx(bar, bytes);
+            if (!skip_a)
+              tma_load_2d(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK), (int32_t)(qt * kGemmBM),
+                          pol_q);
+            tma_load_2d(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK), (int32_t)(ctl * kGemmBN),
+                        pol_b);
           }
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1u; }
       }
+    }
+    if (EXP && lane == 0 && p.prof) {
+      atomicAdd(p.prof + kProfProdWaitEmpty, (unsigned long long)t_w0);
+      atomicAdd(p.prof + kProfProdTotal, (unsigned long long)(tick() - t_beg));
+      atomicAdd(p.prof + kProfProdN, 1ull);
     }
   } else if (warp == kWarpMma) {
     // ===== MMA issuer (whole warp walks the loop, one elected lane issues; with a CTA
@@ -341,12 +388,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (crank == 0) {
       uint32_t s = 0, ph = 0, as = 0, aph = 0;
       const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
+      const long long t_beg = tick();
       for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
+        long long t0 = tick();
         mbar_wait(smem_u32(&tempty[as]), aph ^ 1u);  // epilogues have drained this accumulator
+        t_w1 += tick() - t0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kGemmBN;
         for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
-          mbar_wait(smem_u32(&full[s]), ph);
+          t0 = tick();
+          if (!(xf & 4u)) mbar_wait(smem_u32(&full[s]), ph);
+          t_w0 += tick() - t0;
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a_addr = base + s * kStageBytes, b_addr = a_addr + 16384;
@@ -375,12 +427,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
+      if (EXP && lane == 0 && p.prof) {
+        atomicAdd(p.prof + kProfMmaWaitFull, (unsigned long long)t_w0);
+        atomicAdd(p.prof + kProfMmaWaitTempty, (unsigned long long)t_w1);
+        atomicAdd(p.prof + kProfMmaTotal, (unsigned long long)(tick() - t_beg));
+        atomicAdd(p.prof + kProfMmaN, 1ull);
+      }
     }
   } else {
     // ===== epilogue: 8 warps; thread <-> (query, half of the tile's columns) =====
     // TMEM lane quadrant = warp % 4 (hardware rule); warps 0-3 take columns [0,128) of
-    // every tile, warps 4-7 columns [128,256). Each thread keeps its own threshold
-    // (register) and sorted list (smem), so a query has two lists per CTA.
+    // every tile, warps 4-7 columns [128,256). Each thread keeps the K' best keys it has
+    // seen in REGISTERS (unordered; `thr` = their maximum) and the matching row ids in
+    // shared memory, so a query has two candidate lists per CTA. An insertion replaces
+    // the current maximum: ~80 register-only instructions and one fire-and-forget STS.
+    // (A sorted list in shared memory cost ~2,000 cycles per insertion - a chain of
+    // dependent LDS behind the tensor core's operand traffic - and with ~6,700
+    // insertions per warp the epilogue, not the MMA, paced the kernel.)
     const int quad = warp & 3;
     const int half = warp >> 2;
     const int qlane = quad * 32 + lane;              // query row inside the tile
@@ -392,16 +455,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const uint32_t tempty_bar[2] = {
         CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]),
         CG == 2 ? mapa_u32(smem_u32(&tempty[1]), 0) : smem_u32(&tempty[1])};
-    for (uint32_t j = 0; j < kp; j++) {
-      l_keys[j * kGemmEpiThreads + lidx] = __int_as_float(0x7F800000);
-      l_rows[j * kGemmEpiThreads + lidx] = kInvalidRow;
-    }
+    float lk[KPR];   // slots >= kp hold -inf: never the maximum, never replaced, never emitted
+#pragma unroll
+    for (int j = 0; j < KPR; j++)
+      lk[j] = __int_as_float((uint32_t)j < kp ? 0x7F800000u : 0xFF800000u);
+    for (uint32_t j = 0; j < kp; j++) l_rows[j * kGemmEpiThreads + lidx] = kInvalidRow;
     float thr = __int_as_float(0x7F800000);
     uint32_t as = 0, aph = 0;
 
-    // per-column scale / bias (dead or out-of-range rows -> NaN key). Lane l prepares
-    // columns l, l+32, l+64, l+96 of the warp's half and prefetches the next tile's
-    // values one tile ahead so the global-load latency is off the critical path.
+    // per-column scale / bias: key = fma(acc, scale, bias), scale <= 0 (-1, -2, -1/|b|),
+    // bias >= 0 (0 or |b|^2); dead or out-of-range rows get a NaN scale -> NaN key. Lane l
+    // prepares columns l, l+32, l+64, l+96 of the warp's half and prefetches the next
+    // tile's values one tile ahead so the global-load latency is off the critical path.
     float sc_n[4], bi_n[4];
     auto column_coeffs = [&](uint32_t ct) {
 #pragma unroll
@@ -425,40 +490,82 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     };
     column_coeffs(slice);
 
-    auto process = [&](const uint32_t (&v)[32], uint32_t c0, uint64_t row0) {
-      // straight-line common path: 32 keys + their minimum; the (rarer) insertion walk
-      // only runs when some key beats this thread's current threshold
-      float key[32];
-      const float4 *sc4 = reinterpret_cast<const float4 *>(w_coef + as * 256 + c0);
-      const float4 *bi4 = reinterpret_cast<const float4 *>(w_coef + as * 256 + 128 + c0);
-      float lo = __int_as_float(0x7F800000);
+    // ---- the hot loop never touches shared memory ---------------------------------
+    // Measured (profiles/r01b_gemm_roles.txt): with per-column coefficients read from
+    // shared memory for every accumulator, the epilogue's LDS traffic competes with the
+    // tensor core's operand reads and TMA's writes for the same port and the arithmetic
+    // of one tile took 5,400 cycles - longer than the tile's MMAs. Instead each thread
+    // tests the RAW accumulators against a bound R that is necessary for any column of
+    // this warp's 128 to beat the thread's threshold:
+    //     key = acc*sc + bi < thr, sc in [sc_min, 0], bi >= bi_min, thr < bi_min
+    //       =>  acc > (bi_min - thr) / |sc_min|  =: R
+    // (thr >= bi_min, e.g. while the list is still filling: R = -inf, everything is
+    // examined). R is shrunk by 2^-18 so that fp32 rounding of R itself can never hide
+    // a pass; fma(acc, sc, bi) is a single exactly rounded operation, so acc <= R
+    // implies key >= thr. The common path is 16 three-input maxima per 32 columns;
+    // only chunks with an accumulator above R read their coefficients.
+    float bi_min = __int_as_float(0x7F800000), rcp_sc = 0.0f;   // per tile (warp-uniform)
+    float R = __int_as_float(0xFF800000);
+    auto bound_for = [&](float t) -> float {
+      return t < bi_min ? (bi_min - t) * rcp_sc * (1.0f - 3.8146973e-06f)
+                        : __int_as_float(0xFF800000);
+    };
+    auto list_insert = [&](float key, uint32_t row) {
+      int slot = 0;
 #pragma unroll
-      for (int j4 = 0; j4 < 8; j4++) {
-        const float4 sc = sc4[j4], bi = bi4[j4];
-        key[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, bi.x);
-        key[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, bi.y);
-        key[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, bi.z);
-        key[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, bi.w);
-        // fminf ignores NaN keys (dead / out-of-range rows)
-        lo = fminf(lo, fminf(fminf(key[4 * j4 + 0], key[4 * j4 + 1]),
-                             fminf(key[4 * j4 + 2], key[4 * j4 + 3])));
-      }
+      for (int j = KPR - 1; j >= 0; j--)
+        if (lk[j] == thr) slot = j;
+#pragma unroll
+      for (int j = 0; j < KPR; j++) lk[j] = (j == slot) ? key : lk[j];
+      l_rows[slot * kGemmEpiThreads + lidx] = row;
+      float m = fmaxf(lk[0], lk[1]);
+#pragma unroll
+      for (int j = 2; j + 1 < KPR; j += 2) m = fmax3(m, lk[j], lk[j + 1]);
+      thr = m;
+    };
+
+    auto process = [&](const uint32_t (&v)[32], uint32_t c0, uint64_t row0) {
+      const float *sc_s = w_coef + as * 256 + c0;
+      const float *bi_s = sc_s + 128;
       const uint64_t r0 = row0 + col_base + c0;
       if (DBG) {
         if (q < p.nq)
 #pragma unroll
           for (int j = 0; j < 32; j++)
-            if (r0 + j < p.n_rows) p.dbg_keys[(size_t)q * p.n_rows + r0 + j] = key[j] + 0.0f;
+            if (r0 + j < p.n_rows)
+              p.dbg_keys[(size_t)q * p.n_rows + r0 + j] =
+                  fmaf(__uint_as_float(v[j]), sc_s[j], bi_s[j]) + 0.0f;
       }
-      if (lo < thr) {
+      const float *f = reinterpret_cast<const float *>(&v[0]);
+      float g[4];
 #pragma unroll
-        for (int j = 0; j < 32; j++) {
-          if (key[j] < thr)
-            thr = gemm_list_insert(l_keys, l_rows, kp, lidx, key[j] + 0.0f, (uint32_t)(r0 + j));
+      for (int i = 0; i < 4; i++)
+        g[i] = fmax3(fmax3(f[8 * i], f[8 * i + 1], f[8 * i + 2]),
+                     fmax3(f[8 * i + 3], f[8 * i + 4], f[8 * i + 5]),
+                     fmaxf(f[8 * i + 6], f[8 * i + 7]));
+      if (fmaxf(fmax3(g[0], g[1], g[2]), g[3]) > R) {
+        // rare path: which accumulators exceed the bound, then one exact test each
+        uint32_t pass = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (g[i] > R) {
+#pragma unroll
+            for (int j = 8 * i; j < 8 * i + 8; j++)
+              if (f[j] > R) pass |= 1u << j;
+          }
+        while (pass) {
+          const int j = __ffs(pass) - 1;
+          pass &= pass - 1;
+          const float key = fmaf(pick32(v, j), sc_s[j], bi_s[j]);
+          if (key < thr) {
+            list_insert(key + 0.0f, (uint32_t)(r0 + j));
+            R = bound_for(thr);
+          }
         }
       }
     };
 
+    const long long t_beg = tick();
     for (uint32_t ct = slice; ct < p.n_tiles; ct += p.n_slices) {
       const uint64_t row0 = (uint64_t)ct * kGemmBN;
 #pragma unroll
@@ -466,42 +573,103 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         w_coef[as * 256 + j * 32 + lane] = sc_n[j];
         w_coef[as * 256 + 128 + j * 32 + lane] = bi_n[j];
       }
+      {
+        // warp-wide bounds of this tile's live columns (NaN scale = dead column)
+        float lo_sc = 0.0f, lo_bi = __int_as_float(0x7F800000);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          lo_sc = fminf(lo_sc, sc_n[j]);
+          if (sc_n[j] == sc_n[j]) lo_bi = fminf(lo_bi, bi_n[j]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo_sc = fminf(lo_sc, __shfl_xor_sync(0xFFFFFFFFu, lo_sc, o));
+          lo_bi = fminf(lo_bi, __shfl_xor_sync(0xFFFFFFFFu, lo_bi, o));
+        }
+        bi_min = lo_bi;
+        rcp_sc = 1.0f / (-lo_sc);          // +inf when no live column has a non-zero scale
+        R = bound_for(thr);
+      }
       __syncwarp();
       column_coeffs(ct + p.n_slices);  // prefetch for the next tile
+      long long t0 = tick();
       mbar_wait(smem_u32(&tfull[as]), aph);
+      t_w0 += tick() - t0;
       tc_fence_after();
       const uint32_t t_addr =
           tmem_base + ((uint32_t)(quad * 32) << 16) + as * kGemmBN + col_base;
-      // All four TMEM loads of this thread's 128 columns are issued back to back:
-      // measured, a tcgen05.ld that has to wait behind the tensor core's accumulator
-      // traffic is slow, and serialising them (load, compute, load, ...) made the
-      // epilogue as slow as the next tile's MMA. Once the registers hold the tile the
-      // TMEM buffer is handed back before any arithmetic.
-      uint32_t va[32], vb[32], vc[32], vd[32];
+      if (EXP && (xf & (2u | 32u))) {   // experiments: no TMEM read (2), arithmetic on junk (32)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_bar[as]);
+          else mbar_arrive(tempty_bar[as]);
+        }
+        if (xf & 32u) {
+          uint32_t va[32], vb[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) { va[j] = 0x3F800000u + j * 4099u + ct; vb[j] = va[j] ^ 0x12345u; }
+          process(va, 0, row0);
+          process(vb, 32, row0);
+          process(va, 64, row0);
+          process(vb, 96, row0);
+        }
+        if (++as == 2) { as = 0; aph ^= 1u; }
+        continue;
+      }
+      t0 = tick();
+      // Two batches of 64 columns (a TMEM read costs ~35 cycles, measured); the buffer
+      // goes back to the MMA issuer as soon as the second batch is in registers.
+      uint32_t va[32], vb[32];
       tmem_ld32_nowait(t_addr, va);
       tmem_ld32_nowait(t_addr + 32, vb);
-      tmem_ld32_nowait(t_addr + 64, vc);
-      tmem_ld32_nowait(t_addr + 96, vd);
       tmem_ld_wait();
+      t_w1 += tick() - t0;
+      t0 = tick();
+      const bool ld_only = EXP && (xf & 16u);   // experiment: TMEM reads only
+      if (ld_only) {
+        if ((va[0] ^ vb[31]) == 0x7FC12345u) thr = 0.0f;
+      } else {
+        process(va, 0, row0);
+        process(vb, 32, row0);
+      }
+      t_w2 += tick() - t0;
+      t0 = tick();
+      tmem_ld32_nowait(t_addr + 64, va);
+      tmem_ld32_nowait(t_addr + 96, vb);
+      tmem_ld_wait();
+      t_w1 += tick() - t0;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (CG == 2) mbar_arrive_cluster(tempty_bar[as]);
         else mbar_arrive(tempty_bar[as]);
       }
-      process(va, 0, row0);
-      process(vb, 32, row0);
-      process(vc, 64, row0);
-      process(vd, 96, row0);
+      t0 = tick();
+      if (ld_only) {
+        if ((va[5] ^ vb[7]) == 0x7FC12345u) thr = 0.0f;
+      } else {
+        process(va, 64, row0);
+        process(vb, 96, row0);
+      }
+      t_w2 += tick() - t0;
       if (++as == 2) { as = 0; aph ^= 1u; }
+    }
+    if (EXP && lane == 0 && p.prof) {
+      atomicAdd(p.prof + kProfEpiWaitTfull, (unsigned long long)t_w0);
+      atomicAdd(p.prof + kProfEpiLdtm, (unsigned long long)t_w1);
+      atomicAdd(p.prof + kProfEpiMath, (unsigned long long)t_w2);
+      atomicAdd(p.prof + kProfEpiTotal, (unsigned long long)(tick() - t_beg));
+      atomicAdd(p.prof + kProfEpiN, 1ull);
     }
     if (q < p.nq) {
       uint64_t *out = p.cand + ((size_t)q * p.n_slices * 2 + slice * 2 + half) * kp;
-      for (uint32_t j = 0; j < kp; j++) {
-        uint32_t r = l_rows[j * kGemmEpiThreads + lidx];
-        out[j] = r == kInvalidRow
-                     ? ~0ull
-                     : (((uint64_t)ordered_key(l_keys[j * kGemmEpiThreads + lidx]) << 32) | r);
+#pragma unroll
+      for (int j = 0; j < KPR; j++) {
+        if ((uint32_t)j < kp) {
+          const uint32_t r = l_rows[j * kGemmEpiThreads + lidx];
+          out[j] = r == kInvalidRow ? ~0ull : (((uint64_t)ordered_key(lk[j]) << 32) | r);
+        }
       }
     }
   }
