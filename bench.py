@@ -50,6 +50,19 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_traffic(n, d, world):
+    """dram__bytes_read+write of the dominant kernel from the committed `ncu --set full`
+    capture (profiles/), valid only for the exact workload it was taken on."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01c_scan_traffic.json")) as f:
+            t = json.load(f)
+        if world == 1 and n == 10_000_000 and d == 768:
+            return float(t["traffic"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -303,6 +316,7 @@ def run_b200(args):
     if rank == 0:
         peak, which = peaks()
         achieved = hot_bytes / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
+        traffic, traffic_src = ncu_traffic(n, d, world)
         line = {
             "metric": METRIC_NAME, "value": steps / (total_ms * 1e-3), "unit": "queries/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
@@ -316,7 +330,8 @@ def run_b200(args):
                                    f"{(hi - lo) * d * 4 / 1e9:.2f} GB per GPU vs 126 MB L2)",
                        "queries": "distinct synthetic query per step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)" if which == "measured"
                          else "fallback 6650 GB/s (B200_PROFILING.md)",
                          "kernel": "scan_topk_kernel<L2,f32,QB=1>",
