@@ -21,6 +21,9 @@
  *     deleteBatch core/ngh_graph_engine.dart:411-445            -> tsc_index_set_deleted,
  *                                                                  tsc_index_apply_graph_pages
  *   - nodeId -> (partition,page,slot) model/ngh_index_meta.dart:451-490
+ *   - ConditionRecordMatcher (condition tree + operators over numeric fields)
+ *     handler/value_matcher.dart:337-625, query/query_condition.dart:486-520
+ *                                                              -> tsc_index_filter_where
  *
  * Conventions (mirroring lib/src/handler/system_ffi_helper.dart): every buffer
  * is caller-allocated and caller-freed; int32 status, 0 = success, negative =
@@ -141,6 +144,46 @@ int32_t tsc_index_apply_graph_pages(uint64_t handle, uint64_t first_logical_page
  * 1 = row may be returned. NULL clears the filter. */
 int32_t tsc_index_set_filter(uint64_t handle, const uint64_t *bitmap_words,
                              uint64_t n_words);
+
+/* ---- structured WHERE prefilter on the GPU (BASELINE config 5; additive: the
+ * reference has no WHERE for vectors). Numeric table fields are kept column-wise in
+ * HBM, aligned by node id; a condition tree in postfix order is evaluated in one pass
+ * into the filter bitmap. Operator semantics restate ConditionRecordMatcher
+ * (handler/value_matcher.dart:570-612; numeric order = Dart num.compareTo :150-174:
+ * -0.0 < 0.0, NaN above +inf and equal to itself; NULL != x is true, NULL NOT IN is
+ * true, every ordering operator / IN / BETWEEN is false on NULL; a childless AND or OR
+ * is true :476-493). ---- */
+enum { TSC_COL_I64 = 0, TSC_COL_F64 = 1 };
+enum { TSC_W_LEAF = 0, TSC_W_AND = 1, TSC_W_OR = 2 };
+enum {
+  TSC_OP_EQ = 0, TSC_OP_NE = 1, TSC_OP_GT = 2, TSC_OP_GE = 3, TSC_OP_LT = 4, TSC_OP_LE = 5,
+  TSC_OP_BETWEEN = 6, TSC_OP_IN = 7, TSC_OP_NOT_IN = 8, TSC_OP_IS_NULL = 9,
+  TSC_OP_IS_NOT_NULL = 10, TSC_OP_TRUE = 11, TSC_OP_FALSE = 12
+};
+typedef struct tsc_where_op {
+  uint8_t kind;          /* TSC_W_*                                               */
+  uint8_t op;            /* TSC_OP_* (leaves)                                     */
+  uint16_t n;            /* AND / OR: children popped; IN / NOT IN: list length   */
+  uint32_t column_id;    /* leaves: the column the operator reads                 */
+  int64_t i_lo, i_hi;    /* operand(s) when the column is TSC_COL_I64             */
+  double f_lo, f_hi;     /* operand(s) when the column is TSC_COL_F64             */
+  uint32_t args_offset;  /* IN / NOT IN: first element in `in_args`               */
+  uint32_t reserved;
+} tsc_where_op;
+int32_t tsc_index_column_create(uint64_t handle, uint32_t column_id, uint8_t col_type);
+/* values: n x 8 bytes (int64 or double per the column type), HOST. is_null: n bytes
+ * (non-zero = NULL) or NULL pointer for "no NULLs". Rows are node ids
+ * [first_node_id, first_node_id + n), appended densely like the embedding rows;
+ * overwriting already-appended rows is allowed (updates). */
+int32_t tsc_index_column_append(uint64_t handle, uint32_t column_id, uint64_t first_node_id,
+                                const void *values, const uint8_t *is_null, uint64_t n);
+/* Evaluate the postfix program (<= 64 steps, <= 4096 IN-list values, in_args are 8-byte
+ * values typed like the column of the leaf that uses them) over rows [0, rows) of every
+ * column it names and install the result as the index's filter (as tsc_index_set_filter
+ * does). An empty program matches every row. out_matched (optional): rows that passed.
+ * Columns shorter than the embedding column read as NULL beyond their end. */
+int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_t n_ops,
+                               const void *in_args, uint32_t n_in_args, uint64_t *out_matched);
 
 /* ---- search ---- */
 /* queries: [nq, dims] fp32, already padded/truncated to dims and, for cosine,

@@ -58,7 +58,7 @@ def test_sharded_search_nccl_all_gather():
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     from oracle import oracle_np as onp
-    world, port = 2, _free_port()
+    world, port = min(torch.cuda.device_count(), 8), _free_port()   # 2, 4 or 8 shards
     with mp.Manager() as mgr:
         ret = mgr.dict()
         mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)

@@ -1,0 +1,240 @@
+"""Structured WHERE prefilter (BASELINE config 5): the reference's condition semantics
+(handler/value_matcher.dart:476-612, query/query_condition.dart:743-815) restated by
+oracle/where_oracle.py, and tsc_index_filter_where (GPU) against it.
+
+CPU part: hand-written known answers pin the oracle, and the postfix compiler is checked
+by interpreting its programs with a pure-Python stack machine that follows
+tsc_where.cuh's rules. GPU part: same conditions through the C ABI, bit for bit."""
+import math
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import where_oracle as wo
+from tostore_b200 import where as W
+
+I64, F64 = W.COL_I64, W.COL_F64
+COLS = {"age": (1, I64), "score": (2, F64), "year": (7, I64)}
+TYPES = {"age": "i64", "score": "f64", "year": "i64"}
+
+
+def _columns(n=257, seed=3):
+    rng = np.random.default_rng(seed)
+    age = [None if rng.random() < 0.1 else int(rng.integers(-5, 60)) for _ in range(n)]
+    special = [0.0, -0.0, math.nan, math.inf, -math.inf, 1.5, -1.5, 2.0]
+    score = [None if rng.random() < 0.1 else
+             (special[int(rng.integers(0, len(special)))] if rng.random() < 0.3
+              else float(np.round(rng.normal() * 3, 1))) for _ in range(n)]
+    year = [int(rng.integers(1990, 2030)) for _ in range(n - 40)]     # shorter column: NULL tail
+    return {"age": age, "score": score, "year": year}
+
+
+CONDITIONS = [
+    {},
+    {"age": {">": 30}},
+    {"age": {">=": 30, "<": 0}},                      # operator map = OR of its operators
+    {"age": 17},
+    {"age": None},
+    {"age": {"!=": 17}},                              # NULL != 17 is true
+    {"age": {"IN": [1, 2, 3, 40]}},
+    {"age": {"NOT IN": [1, 2, 3, 40]}},               # NULL NOT IN is true
+    {"age": {"BETWEEN": {"start": 10, "end": 20}}},
+    {"age": {">": 29.5}},                             # integer field: operand -> round() = 30
+    {"age": {"=": 2.5}},                              # -> 3 (half away from zero)
+    {"age": {"=": -2.5}},                             # -> -3
+    {"score": {"=": 0.0}},                            # compareTo: -0.0 != 0.0
+    {"score": {"=": -0.0}},
+    {"score": {"<": 0.0}},                            # -0.0 < 0.0
+    {"score": {"=": math.nan}},                       # NaN equals itself
+    {"score": {">": math.inf}},                       # only NaN is above +inf
+    {"score": {"<=": math.nan}},                      # everything non-null
+    {"score": {"BETWEEN": {"start": -1.5, "end": 1}}},
+    {"score": {"IN": [1.5, math.nan, 2]}},
+    {"score": {"IS": None}},
+    {"score": {"IS NOT": None}},
+    {"year": {">=": 2000}},                           # short column: NULL beyond its end
+    {"year": {"!=": 2000}},
+    {"age": {">": 10}, "score": {"<": 2.0}},          # two fields in one leaf = AND
+    {"AND": [{"age": {">": 10}}, {"OR": [{"score": {"<": -1.0}}, {"year": {"IN": [1999, 2001, 2024]}}]}]},
+    {"OR": [{"age": {"<": 0}}, {"AND": [{"score": {">=": 1.5}}, {"age": {"IS NOT": None}}]}, {"year": 2010}]},
+    {"AND": []},
+    {"OR": []},                                       # childless OR is true (value_matcher.dart:491)
+    {"age": {}},                                      # empty operator map matches nothing
+    {"age": {">": None}},                             # value > NULL for every non-null value
+    {"age": {"<": None}},
+]
+
+
+# ---- oracle known answers (hand-computed from the reference's rules) ---------------------
+def test_oracle_known_answers():
+    cols = {"age": [5, None, 30, 31, -1], "score": [0.0, -0.0, math.nan, None, 2.5]}
+    t = {"age": "i64", "score": "f64"}
+    ev = lambda c: wo.evaluate_columns(c, cols, t)
+    assert ev({"age": {">": 29.5}}) == [False, False, False, True, False]      # round(29.5) = 30
+    assert ev({"age": {"!=": 5}}) == [False, True, True, True, True]
+    assert ev({"age": {"NOT IN": [5, 30]}}) == [False, True, False, True, True]
+    assert ev({"age": {"IN": [5, 30]}}) == [True, False, True, False, False]
+    assert ev({"age": {"BETWEEN": {"start": 5, "end": 30}}}) == [True, False, True, False, False]
+    assert ev({"score": {"=": 0.0}}) == [True, False, False, False, False]
+    assert ev({"score": {"<": 0.0}}) == [False, True, False, False, False]
+    assert ev({"score": {"=": math.nan}}) == [False, False, True, False, False]
+    assert ev({"score": {">": 1e308}}) == [False, False, True, False, False]
+    assert ev({"score": None}) == [False, False, False, True, False]
+    assert ev({"age": {">=": 30, "<": 0}}) == [False, False, True, True, True]
+    assert ev({"OR": []}) == [True] * 5 and ev({"AND": []}) == [True] * 5 and ev({}) == [True] * 5
+    assert ev({"age": {}}) == [False] * 5
+    assert wo.dart_round(2.5) == 3 and wo.dart_round(-2.5) == -3 and wo.dart_round(0.49999999999999994) == 0
+    assert wo.dart_compare(-0.0, 0.0) == -1 and wo.dart_compare(math.nan, math.inf) == 1
+    assert wo.dart_compare(math.nan, math.nan) == 0 and wo.dart_compare(0, -0.0) == 1
+
+
+# ---- the compiler, interpreted on the CPU with the kernel's rules --------------------------
+def _key(t, v):
+    if t == I64:
+        return (int(v) + (1 << 63)) & ((1 << 64) - 1)
+    b = struct.unpack("<Q", struct.pack("<d", float(v)))[0]
+    if (b & 0x7FFFFFFFFFFFFFFF) > 0x7FF0000000000000:
+        return (1 << 64) - 1
+    return (~b) & ((1 << 64) - 1) if b >> 63 else b | (1 << 63)
+
+
+def _interpret(prog: W.WhereProgram, columns, n_rows):
+    by_id = {cid: (name, t) for name, (cid, t) in COLS.items()}
+    out = []
+    for r in range(n_rows):
+        stack = []
+        for o in prog.ops:
+            if o.kind == W.W_LEAF:
+                if o.op in (W.OP_TRUE, W.OP_FALSE):
+                    stack.append(o.op == W.OP_TRUE)
+                    continue
+                name, t = by_id[o.column_id]
+                vals = columns[name]
+                v = vals[r] if r < len(vals) else None
+                null = v is None
+                key = None if null else _key(t, v)
+                lo = _key(t, o.i_lo if t == I64 else o.f_lo)
+                hi = _key(t, o.i_hi if t == I64 else o.f_hi)
+                args = [_key(t, a) for (_, a) in prog.args[o.args_offset:o.args_offset + o.n]]
+                res = {W.OP_EQ: lambda: not null and key == lo, W.OP_NE: lambda: null or key != lo,
+                       W.OP_GT: lambda: not null and key > lo, W.OP_GE: lambda: not null and key >= lo,
+                       W.OP_LT: lambda: not null and key < lo, W.OP_LE: lambda: not null and key <= lo,
+                       W.OP_BETWEEN: lambda: not null and lo <= key <= hi,
+                       W.OP_IN: lambda: not null and key in args,
+                       W.OP_NOT_IN: lambda: null or key not in args,
+                       W.OP_IS_NULL: lambda: null, W.OP_IS_NOT_NULL: lambda: not null}[o.op]()
+                stack.append(bool(res))
+            else:
+                kids = [stack.pop() for _ in range(o.n)]
+                stack.append(True if o.n == 0 else (all(kids) if o.kind == W.W_AND else any(kids)))
+        assert len(stack) == (1 if prog.ops else 0)
+        out.append(stack[0] if stack else True)
+    return out
+
+
+@pytest.mark.parametrize("ci", range(len(CONDITIONS)))
+def test_compiled_program_equals_oracle(ci):
+    cols = _columns()
+    n = len(cols["age"])
+    cond = CONDITIONS[ci]
+    want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
+    got = _interpret(W.compile_condition(cond, COLS), cols, n)
+    assert got == want
+
+
+def test_builder_map_form():
+    qc = W.QueryCondition().where("age", ">", 30).where("score", "<=", 1.5).orWhere("year", "IN", [1, 2])
+    assert qc.build() == {"OR": [{"AND": [{"age": {">": 30}}, {"score": {"<=": 1.5}}]},
+                                 {"year": {"IN": [1, 2]}}]}
+    assert W.QueryCondition().isEmpty and W.QueryCondition().build() == {}
+    assert W.QueryCondition().whereBetween("age", 1, 2).build() == {"age": {"BETWEEN": {"start": 1, "end": 2}}}
+    assert W.QueryCondition().where("age", 5).build() == {"age": 5}
+    with pytest.raises(NotImplementedError):
+        W.compile_condition({"age": {"LIKE": "a%"}}, COLS)
+    with pytest.raises(KeyError):
+        W.compile_condition({"nope": 1}, COLS)
+
+
+# ---- GPU: tsc_index_filter_where against the oracle ------------------------------------------
+def _gpu_index(cols, n, d=32):
+    import oracle
+    from tostore_b200 import GpuVectorIndex
+    ix = GpuVectorIndex(d, 0, capacity_rows=n + 64, k_max=16, nq_max=8)
+    rows = oracle.synth_rows(41, 0, n, d)
+    ix.append_rows(rows)
+    for name, (cid, t) in COLS.items():
+        ix.column_create(cid, t)
+        ix.column_append(cid, cols[name])
+    return ix, rows
+
+
+@pytest.mark.gpu
+def test_gpu_filter_where_equals_oracle():
+    import oracle
+    cols = _columns(n=1000, seed=11)
+    n = len(cols["age"])
+    ix, rows = _gpu_index(cols, n)
+    q = oracle.synth_rows(42, 0, 1, 32)[0]
+    with ix:
+        for cond in CONDITIONS:
+            want = np.array(wo.evaluate_columns(cond, cols, TYPES, n_rows=n), dtype=bool)
+            matched = ix.filter_where(W.compile_condition(cond, COLS))
+            assert matched == int(want.sum()), (cond, matched, int(want.sum()))
+            ids, dist, cnt = ix.search(q, 10)
+            oi, od = oracle.search(rows, q, 0, 10, filter=want)
+            assert cnt[0] == len(oi) and (ids[0, : len(oi)] == oi).all(), cond
+            assert (dist[0, : len(od)].view(np.int64) == od.view(np.int64)).all(), cond
+        with pytest.raises(Exception):
+            ix.filter_where(W.compile_condition({"age": 1}, {"age": (99, I64)}))   # unknown column
+
+
+@pytest.mark.gpu
+def test_gpu_filter_where_column_updates_and_bad_programs():
+    from tostore_b200 import TscError
+    cols = {"age": [1, 2, None, 4] * 50, "score": [0.5] * 200, "year": [2000] * 200}
+    ix, _ = _gpu_index(cols, 200)
+    with ix:
+        assert ix.filter_where(W.compile_condition({"age": {">=": 2}}, COLS)) == 100
+        ix.column_append(1, [7] * 10, first_node_id=0)                  # overwrite rows 0..9 (update)
+        want = wo.evaluate_columns({"age": {">=": 2}}, {"age": [7] * 10 + cols["age"][10:]}, {"age": "i64"})
+        assert ix.filter_where(W.compile_condition({"age": {">=": 2}}, COLS)) == sum(want)
+        bad = W.WhereProgram()
+        bad._node(W.W_AND, 2)                                           # pops from an empty stack
+        with pytest.raises(TscError):
+            ix.filter_where(bad)
+        two = W.WhereProgram()
+        two._leaf(W.OP_TRUE)
+        two._leaf(W.OP_TRUE)                                            # leaves two values
+        with pytest.raises(TscError):
+            ix.filter_where(two)
+        with pytest.raises(TscError):
+            ix.column_create(1, I64)                                    # duplicate id
+        with pytest.raises(TscError):
+            ix.column_append(2, [1.0], first_node_id=5000)              # not contiguous
+
+
+@pytest.mark.gpu
+def test_gpu_filter_where_large_selectivity_and_sparse_scan():
+    """C5-shaped: 2M x 64 rows, a range predicate with ~10 % selectivity -> the per-live-row
+    sparse scan; ids and distances against the oracle."""
+    import oracle
+    from tostore_b200 import GpuVectorIndex
+    n, d = 2_000_000, 64
+    rng = np.random.default_rng(5)
+    price = rng.integers(0, 1000, n)
+    rating = rng.random(n) * 5
+    cols = {"price": (3, I64), "rating": (4, F64)}
+    cond = {"AND": [{"price": {"<": 200}}, {"rating": {">=": 2.5}}]}
+    with GpuVectorIndex(d, 0, capacity_rows=n, k_max=16, nq_max=8) as ix:
+        ix.append_synthetic(77, n)
+        ix.column_create(3, I64)
+        ix.column_create(4, F64)
+        ix.column_append(3, price)
+        ix.column_append(4, rating)
+        want = (price < 200) & (rating >= 2.5)
+        assert ix.filter_where(W.compile_condition(cond, cols)) == int(want.sum())
+        q = oracle.synth_rows(78, 0, 1, d)[0]
+        ids, dist, cnt = ix.search(q, 10)
+        oi, od = oracle.search_synth(77, n, d, 0, q, 0, 10, filter=want)
+        assert (ids[0] == oi).all() and (dist[0].view(np.int64) == od.view(np.int64)).all()

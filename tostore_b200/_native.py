@@ -24,6 +24,7 @@ EXPORTS = (
     "tsc_comm_unique_id", "tsc_comm_init", "tsc_search_sharded",
     "tsc_stats_get", "tsc_stats_reset", "tsc_index_device_rows", "tsc_selftest_crc32",
     "tsc_debug_gemm_keys",
+    "tsc_index_column_create", "tsc_index_column_append", "tsc_index_filter_where",
 )
 
 TSC_OK = 0
@@ -103,6 +104,9 @@ def lib():
     L.tsc_stats_reset.argtypes = [u64]
     L.tsc_index_device_rows.argtypes = [u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u64)]
     L.tsc_debug_gemm_keys.argtypes = [u64, vp, u32, vp]
+    L.tsc_index_column_create.argtypes = [u64, u32, C.c_uint8]
+    L.tsc_index_column_append.argtypes = [u64, u32, u64, vp, vp, u64]
+    L.tsc_index_filter_where.argtypes = [u64, vp, u32, vp, u32, C.POINTER(u64)]
     L.tsc_selftest_crc32.argtypes = [vp, u32]
     L.tsc_selftest_crc32.restype = u32
     for name in EXPORTS:

@@ -42,6 +42,8 @@ static Index *lookup(uint64_t h) {
   return it->second;
 }
 
+Index *lookup_index(uint64_t h) { return lookup(h); }
+
 struct Ticket {
   Index *ix;
   uint64_t handle;
@@ -82,6 +84,11 @@ static void free_index(Index *ix) {
   cudaFree(ix->d_page_status);
   cudaFree(ix->d_gather_send);
   cudaFree(ix->d_gather_recv);
+  cudaFree(ix->d_where_args);
+  for (auto &c : ix->columns) {
+    cudaFree(c.d_values);
+    cudaFree(c.d_null);
+  }
   cudaFreeHost(ix->h_queries);
   cudaFreeHost(ix->h_out_ids);
   cudaFreeHost(ix->h_out_dist);
@@ -147,6 +154,8 @@ static int32_t ensure_stage(Index *ix, size_t bytes) {
   ix->device_bytes += bytes;
   return TSC_OK;
 }
+
+int32_t ensure_stage_bytes(Index *ix, size_t bytes) { return ensure_stage(ix, bytes); }
 
 static int32_t refresh_live(Index *ix, cudaStream_t st) {
   if (!ix->live_dirty && ix->live_rows_for == ix->rows) return TSC_OK;
@@ -440,10 +449,13 @@ int32_t tsc_index_clear(uint64_t handle) {
   TSC_CUDA(cudaSetDevice(ix->device));
   TSC_CUDA(cudaMemsetAsync(ix->d_deleted, 0, ix->mask_words * 4, ix->stream));
   TSC_CUDA(cudaMemsetAsync(ix->d_filter, 0xFF, ix->mask_words * 4, ix->stream));
+  for (auto &c : ix->columns)
+    TSC_CUDA(cudaMemsetAsync(c.d_null, 0xFF, ix->mask_words * 4, ix->stream));
   TSC_CUDA(cudaStreamSynchronize(ix->stream));
   ix->rows = 0;
   ix->deleted_rows = 0;
   ix->has_deleted = ix->has_filter = ix->live_dirty = false;
+  for (auto &c : ix->columns) c.rows = 0;
   return TSC_OK;
 }
 

@@ -6,6 +6,7 @@
 
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/tostore_cuda.h"
 
@@ -30,6 +31,15 @@ struct ScanConfig {
   int stages = 0;      // S (0 = auto)
   int stage_target = 6144;  // bytes per stage aimed for when R is auto
   int inflight_target = 96 * 1024;  // bytes of bulk copies in flight per CTA when S is auto
+};
+
+// numeric table field kept column-wise next to the embedding column (tsc_where.cuh)
+struct AttrColumn {
+  uint32_t id = 0;
+  uint8_t type = 0;              // TSC_COL_I64 / TSC_COL_F64
+  uint64_t *d_values = nullptr;  // [capacity] raw 8-byte values
+  uint32_t *d_null = nullptr;    // [mask_words] bit r = row r is NULL (allocated on first NULL)
+  uint64_t rows = 0;             // rows appended so far
 };
 
 struct Index {
@@ -81,6 +91,11 @@ struct Index {
 
   ScanConfig scan;
 
+  // attribute columns for the WHERE prefilter
+  std::vector<AttrColumn> columns;
+  uint64_t *d_where_args = nullptr;   // IN-list keys
+  size_t where_args_cap = 0;
+
   // sharding
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
@@ -100,6 +115,9 @@ struct Index {
   uint32_t last_path = 0;
   uint64_t device_bytes = 0;
 };
+
+Index *lookup_index(uint64_t handle);   // NULL + error string when unknown
+int32_t ensure_stage_bytes(Index *ix, size_t bytes);
 
 // launchers implemented per translation unit
 int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,

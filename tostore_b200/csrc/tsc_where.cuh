@@ -1,0 +1,148 @@
+// tsc_where.cuh — K8: structured WHERE prefilter evaluated on the GPU.
+//
+// SURVEY.md §8f row 3 / BASELINE config 5 ("structured WHERE prefilter + kNN"). The
+// reference evaluates a condition tree per record on the CPU
+// (ConditionRecordMatcher, handler/value_matcher.dart:337-625) and has no WHERE for
+// vectors at all; here the numeric table fields a predicate needs are kept
+// column-wise in HBM, aligned by node id, and ONE pass turns a condition tree into the
+// liveness bitmap the scan kernels already honour — no PK list, no host round trip.
+//
+// Semantics restated from the reference (value_matcher.dart):
+//   * tree: AND = every child, OR = any child, a childless AND / OR is true (:476-493)
+//   * operators (:570-612): '=' cmp==0; '!=' cmp!=0 (so NULL != x is TRUE);
+//     '>' '>=' '<' '<=' need a non-null value; IN false / NOT IN true on NULL;
+//     BETWEEN = start <= v <= end, false on NULL; IS NULL / IS NOT NULL
+//   * numeric order = Dart num.compareTo (:150-174): a total order in which
+//     -0.0 < 0.0, NaN is above +inf and equal to itself
+// Both column types are mapped to uint64 keys whose unsigned order is that order, so
+// one kernel serves int and double fields; operands are converted on the host.
+#pragma once
+
+#include "tsc_common.cuh"
+
+namespace tsc {
+
+enum : uint8_t { kWLeaf = 0, kWAnd = 1, kWOr = 2 };
+enum : uint8_t {
+  kOpEq = 0, kOpNe, kOpGt, kOpGe, kOpLt, kOpLe, kOpBetween, kOpIn, kOpNotIn, kOpIsNull,
+  kOpIsNotNull, kOpTrue, kOpFalse, kOpCount
+};
+constexpr int kWhereMaxOps = 64;     // program length / bit-stack depth
+constexpr int kWhereMaxCols = 16;
+
+struct WhereDevOp {        // 32 bytes, operands already in key space
+  uint8_t kind, op;
+  uint16_t n;              // children of AND / OR, or length of the IN list
+  uint32_t col;            // slot in WhereCols
+  uint64_t lo, hi;         // operand keys (BETWEEN: start, end)
+  uint32_t args_off;       // IN list: first key in `args`
+  uint32_t pad;
+};
+
+struct WhereCols {
+  const uint64_t *values[kWhereMaxCols];  // raw 8-byte values (int64 or double bits)
+  const uint32_t *nulls[kWhereMaxCols];   // optional: bit r = row r is NULL
+  uint8_t is_f64[kWhereMaxCols];
+};
+
+struct WhereProgram {
+  WhereDevOp ops[kWhereMaxOps];
+  uint32_t n_ops;
+};
+
+__host__ __device__ __forceinline__ uint64_t where_key_i64(int64_t v) {
+  return (uint64_t)v ^ 0x8000000000000000ull;
+}
+// Dart double.compareTo order; every NaN is the same (largest) key
+__host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
+  if ((b & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return 0xFFFFFFFFFFFFFFFFull;
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// One thread per row, one warp per 32-row bitmap word (ballot), grid-stride over words.
+// HBM traffic: 8 bytes per row per leaf (coalesced 256-byte warp loads) + 4 bytes per 32
+// rows written; a leaf on the column the previous leaf used re-uses the loaded value.
+__global__ void __launch_bounds__(256)
+where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_constant__ WhereCols cols,
+                  const uint64_t *__restrict__ args, uint64_t n_rows, uint32_t *__restrict__ out_bits,
+                  unsigned long long *__restrict__ matched) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t n_words = (n_rows + 31) / 32;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  unsigned long long local = 0;
+  for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+    const uint64_t row = w * 32 + lane;
+    const bool valid = row < n_rows;
+    uint64_t stack = 0;
+    uint32_t last_col = 0xFFFFFFFFu;
+    uint64_t key = 0;
+    bool isnull = true;
+    for (uint32_t i = 0; i < prog.n_ops; i++) {
+      const WhereDevOp &op = prog.ops[i];
+      bool r;
+      if (op.kind == kWLeaf) {
+        if (op.op < kOpTrue && op.col != last_col) {
+          last_col = op.col;
+          isnull = true;
+          if (valid) {
+            const uint64_t raw = __ldg(cols.values[op.col] + row);
+            key = cols.is_f64[op.col] ? where_key_f64_bits(raw) : (raw ^ 0x8000000000000000ull);
+            const uint32_t *nb = cols.nulls[op.col];
+            isnull = nb ? ((__ldg(nb + (row >> 5)) >> (row & 31)) & 1u) : false;
+          }
+        }
+        switch (op.op) {
+          case kOpEq: r = !isnull && key == op.lo; break;
+          case kOpNe: r = isnull || key != op.lo; break;
+          case kOpGt: r = !isnull && key > op.lo; break;
+          case kOpGe: r = !isnull && key >= op.lo; break;
+          case kOpLt: r = !isnull && key < op.lo; break;
+          case kOpLe: r = !isnull && key <= op.lo; break;
+          case kOpBetween: r = !isnull && key >= op.lo && key <= op.hi; break;
+          case kOpIn:
+          case kOpNotIn: {
+            bool any = false;
+            for (uint32_t j = 0; j < op.n; j++) any |= (key == __ldg(args + op.args_off + j));
+            r = op.op == kOpIn ? (!isnull && any) : (isnull || !any);
+            break;
+          }
+          case kOpIsNull: r = isnull; break;
+          case kOpIsNotNull: r = !isnull; break;
+          case kOpTrue: r = true; break;
+          default: r = false; break;
+        }
+        stack = (stack << 1) | (r ? 1ull : 0ull);
+      } else {
+        const uint32_t n = op.n;
+        const uint64_t m = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
+        const uint64_t top = stack & m;
+        r = (n == 0) ? true : (op.kind == kWAnd ? top == m : top != 0);
+        stack = (n >= 64) ? 0ull : (stack >> n);
+        stack = (stack << 1) | (r ? 1ull : 0ull);
+      }
+    }
+    const bool res = valid && (prog.n_ops == 0 || (stack & 1ull));
+    const unsigned bits = __ballot_sync(0xFFFFFFFFu, res);
+    if (lane == 0) {
+      out_bits[w] = bits;
+      local += __popc(bits);
+    }
+  }
+  if (lane == 0 && local) atomicAdd(matched, local);
+}
+
+// fixed-width columns arrive densely from the host; nulls as one byte per row
+__global__ void pack_null_bits_kernel(const uint8_t *__restrict__ is_null, uint64_t n,
+                                      uint64_t first_row, uint32_t *__restrict__ null_bits) {
+  // rows [first_row, first_row + n): read-modify-write whole words with atomics because the
+  // first and last word may be shared with rows appended earlier / later
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = first_row + i;
+    const uint32_t bit = 1u << (row & 31);
+    if (is_null[i]) atomicOr(null_bits + (row >> 5), bit);
+    else atomicAnd(null_bits + (row >> 5), ~bit);
+  }
+}
+
+}  // namespace tsc

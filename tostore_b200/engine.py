@@ -114,6 +114,49 @@ class GpuVectorIndex:
         N.check(self._lib.tsc_index_set_filter(self.handle, words.ctypes.data, words.size),
                 "tsc_index_set_filter")
 
+    # -- structured WHERE prefilter (attribute columns, evaluated on the GPU) --------
+    def column_create(self, column_id: int, col_type: int) -> None:
+        """col_type: where.COL_I64 / where.COL_F64."""
+        N.check(self._lib.tsc_index_column_create(self.handle, int(column_id), int(col_type)),
+                "tsc_index_column_create")
+        self._col_types = getattr(self, "_col_types", {})
+        self._col_types[int(column_id)] = int(col_type)
+
+    def column_append(self, column_id: int, values, is_null=None,
+                      first_node_id: Optional[int] = None) -> None:
+        """values: int64 / float64 array per the column type; is_null: bool array or None.
+        A list may hold None for NULL."""
+        t = getattr(self, "_col_types", {}).get(int(column_id))
+        if t is None:
+            raise KeyError(f"column {column_id} was not created on this index")
+        if is_null is None and isinstance(values, (list, tuple)) and any(v is None for v in values):
+            is_null = np.array([v is None for v in values], dtype=bool)
+            values = [0 if v is None else v for v in values]
+        vals = np.ascontiguousarray(values, dtype=np.int64 if t == 0 else np.float64)
+        nulls = None if is_null is None else np.ascontiguousarray(is_null, dtype=np.uint8)
+        if nulls is not None and nulls.size != vals.size:
+            raise ValueError("is_null must have one entry per value")
+        if first_node_id is None:
+            self._col_rows = getattr(self, "_col_rows", {})
+            first_node_id = self.first_node_id + self._col_rows.get(int(column_id), 0)
+        N.check(self._lib.tsc_index_column_append(self.handle, int(column_id), int(first_node_id),
+                                                  vals.ctypes.data,
+                                                  None if nulls is None else nulls.ctypes.data,
+                                                  vals.size), "tsc_index_column_append")
+        self._col_rows = getattr(self, "_col_rows", {})
+        end = int(first_node_id) - self.first_node_id + vals.size
+        self._col_rows[int(column_id)] = max(self._col_rows.get(int(column_id), 0), end)
+
+    def filter_where(self, program) -> int:
+        """Install the rows matching a compiled `where.WhereProgram` as the filter;
+        returns how many rows passed."""
+        ops, n_ops, raw, n_args = program.buffers()
+        matched = C.c_uint64(0)
+        N.check(self._lib.tsc_index_filter_where(self.handle, C.cast(ops, C.c_void_p), n_ops,
+                                                 raw.ctypes.data, n_args, C.byref(matched)),
+                "tsc_index_filter_where")
+        return matched.value
+
     # -- search --------------------------------------------------------------------
     def search(self, queries, k: int, threshold: Optional[float] = None):
         """queries: fp32 [nq, dims] (prepared as the reference prepares them).

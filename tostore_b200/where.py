@@ -1,0 +1,231 @@
+"""Structured WHERE prefilter: condition tree -> postfix program for
+`tsc_index_filter_where` (the GPU evaluates it over attribute columns, tsc_where.cuh).
+
+Host mirror of the reference's condition handling for numeric fields (paths relative
+to /root/reference/lib/src):
+  * `QueryCondition` map form (`{'AND': [...]}`, `{'OR': [...]}`, leaf
+    `{field: {op: value}}` / `{field: value}`)      query/query_condition.dart:24-55, :486-520
+  * operand normalisation to the field's type       query/query_condition.dart:743-815,
+                                                    model/table_schema.dart:1356-1421
+  * operator meaning                                handler/value_matcher.dart:570-612
+An operator map with several entries is an OR of them (value_matcher.dart:552-563);
+several fields in one leaf are an AND (:499-510).
+
+The reference has no WHERE for `vectorSearch`; this is the additive prefilter of
+BASELINE config 5. Text operators (LIKE ...) have no columnar form here and raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+COL_I64, COL_F64 = 0, 1
+W_LEAF, W_AND, W_OR = 0, 1, 2
+(OP_EQ, OP_NE, OP_GT, OP_GE, OP_LT, OP_LE, OP_BETWEEN, OP_IN, OP_NOT_IN, OP_IS_NULL,
+ OP_IS_NOT_NULL, OP_TRUE, OP_FALSE) = range(13)
+MAX_OPS, MAX_IN_ARGS = 64, 4096
+_INT64_MIN, _INT64_MAX = -(1 << 63), (1 << 63) - 1
+_SIMPLE = {"=": OP_EQ, "!=": OP_NE, "<>": OP_NE, ">": OP_GT, ">=": OP_GE, "<": OP_LT, "<=": OP_LE}
+
+
+class WhereOp(C.Structure):            # include/tostore_cuda.h: tsc_where_op
+    _fields_ = [("kind", C.c_uint8), ("op", C.c_uint8), ("n", C.c_uint16),
+                ("column_id", C.c_uint32), ("i_lo", C.c_int64), ("i_hi", C.c_int64),
+                ("f_lo", C.c_double), ("f_hi", C.c_double), ("args_offset", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+def _dart_round(x: float) -> int:
+    if x != x or math.isinf(x):
+        raise ValueError("cannot convert NaN / infinity to an integer field operand")
+    a = abs(x)
+    r = a if a >= 2.0 ** 52 else (math.floor(a) + (1 if a - math.floor(a) >= 0.5 else 0))
+    v = int(r) if x >= 0 else -int(r)
+    return max(_INT64_MIN, min(_INT64_MAX, v))
+
+
+def _convert(v, col_type: int):
+    """`FieldSchema.convertValue` for integer / double fields (table_schema.dart:1371-1421)."""
+    if isinstance(v, (bool, np.bool_)):
+        v = 1 if v else 0
+    if isinstance(v, np.integer):
+        v = int(v)
+    if isinstance(v, np.floating):
+        v = float(v)
+    if col_type == COL_I64:
+        if isinstance(v, int):
+            if not _INT64_MIN <= v <= _INT64_MAX:
+                raise ValueError(f"operand {v} does not fit an int64 field")
+            return v
+        if isinstance(v, float):
+            return _dart_round(v)
+    else:
+        if isinstance(v, float):
+            return v
+        if isinstance(v, int):
+            return float(v)
+    raise TypeError(f"operand {v!r} is not numeric")
+
+
+class WhereProgram:
+    """Postfix program + IN-list values, ready for the C ABI."""
+
+    def __init__(self):
+        self.ops: List[WhereOp] = []
+        self.args: List[Tuple[int, object]] = []     # (col_type, value)
+
+    def _leaf(self, op: int, col: int = 0, col_type: int = COL_I64, lo=0, hi=0, n: int = 0,
+              args_offset: int = 0) -> None:
+        o = WhereOp(kind=W_LEAF, op=op, n=n, column_id=col, args_offset=args_offset)
+        if col_type == COL_I64:
+            o.i_lo, o.i_hi = int(lo), int(hi)
+        else:
+            o.f_lo, o.f_hi = float(lo), float(hi)
+        self.ops.append(o)
+
+    def _node(self, kind: int, n: int) -> None:
+        self.ops.append(WhereOp(kind=kind, n=n))
+
+    def buffers(self):
+        if len(self.ops) > MAX_OPS:
+            raise ValueError(f"condition compiles to {len(self.ops)} steps (limit {MAX_OPS})")
+        if len(self.args) > MAX_IN_ARGS:
+            raise ValueError(f"IN lists hold {len(self.args)} values (limit {MAX_IN_ARGS})")
+        ops = (WhereOp * max(len(self.ops), 1))(*self.ops)
+        raw = np.zeros(max(len(self.args), 1), dtype=np.uint64)
+        for i, (t, v) in enumerate(self.args):
+            raw[i] = (np.array([v], dtype=np.int64) if t == COL_I64
+                      else np.array([v], dtype=np.float64)).view(np.uint64)[0]
+        return ops, len(self.ops), raw, len(self.args)
+
+
+def compile_condition(cond: Dict[str, object], columns: Dict[str, Tuple[int, int]]) -> WhereProgram:
+    """cond: map form of a `QueryCondition`; columns: field name -> (column_id, COL_*).
+    An empty condition compiles to the empty program (matches every row)."""
+    prog = WhereProgram()
+    if cond:
+        _emit(cond, columns, prog)
+    return prog
+
+
+def _emit(cond, columns, prog: WhereProgram) -> None:
+    if not isinstance(cond, dict):
+        raise TypeError("condition must be a map")
+    if "AND" in cond or "OR" in cond:
+        key = "AND" if "AND" in cond else "OR"
+        kids = list(cond[key])
+        if len(kids) > 63:
+            raise ValueError("more than 63 children under one AND / OR")
+        for c in kids:
+            _emit(c, columns, prog)
+        prog._node(W_AND if key == "AND" else W_OR, len(kids))
+        return
+    n_fields = 0
+    for field, c in cond.items():                      # fields of one leaf: AND
+        name = field.split(".")[-1] if field not in columns else field
+        if name not in columns:
+            raise KeyError(f"WHERE names field {field!r} which has no attribute column")
+        col, t = columns[name]
+        if isinstance(c, dict):
+            n_ops = 0
+            for op, ov in c.items():                   # operators of one field: OR
+                _emit_operator(op, ov, col, t, prog)
+                n_ops += 1
+            if n_ops != 1:
+                prog._node(W_OR, n_ops) if n_ops else prog._leaf(OP_FALSE)
+        elif c is None:
+            prog._leaf(OP_IS_NULL, col, t)             # `condition == null -> value == null`
+        else:
+            prog._leaf(OP_EQ, col, t, _convert(c, t))
+        n_fields += 1
+    if n_fields != 1:
+        prog._node(W_AND, n_fields)
+
+
+def _emit_operator(op: str, ov, col: int, t: int, prog: WhereProgram) -> None:
+    up = op.upper()
+    if up in _SIMPLE:
+        if ov is None:
+            # matcher(value, null): 0 iff value is null, else +1 (value_matcher.dart:160-163)
+            code = {OP_EQ: OP_IS_NULL, OP_NE: OP_IS_NOT_NULL, OP_GT: OP_IS_NOT_NULL,
+                    OP_GE: OP_IS_NOT_NULL, OP_LT: OP_FALSE, OP_LE: OP_FALSE}[_SIMPLE[up]]
+            prog._leaf(code, col, t)
+        else:
+            prog._leaf(_SIMPLE[up], col, t, _convert(ov, t))
+    elif up == "BETWEEN":
+        if not isinstance(ov, dict) or "start" not in ov or "end" not in ov:
+            prog._leaf(OP_FALSE)
+        else:
+            prog._leaf(OP_BETWEEN, col, t, _convert(ov["start"], t), _convert(ov["end"], t))
+    elif up in ("IN", "NOT IN"):
+        if not isinstance(ov, (list, tuple)):
+            prog._leaf(OP_FALSE if up == "IN" else OP_TRUE)
+        else:
+            vals = [_convert(x, t) for x in ov if x is not None]
+            off = len(prog.args)
+            prog.args.extend((t, v) for v in vals)
+            prog._leaf(OP_IN if up == "IN" else OP_NOT_IN, col, t, n=len(vals), args_offset=off)
+    elif up == "IS":
+        prog._leaf(OP_IS_NULL if ov is None else OP_FALSE, col, t)
+    elif up == "IS NOT":
+        prog._leaf(OP_IS_NOT_NULL if ov is None else OP_FALSE, col, t)
+    else:
+        raise NotImplementedError(f"operator {op!r} has no columnar GPU form (numeric fields only)")
+
+
+class QueryCondition:
+    """Small builder for the map form (`QueryCondition.where / or / build`,
+    query/query_condition.dart:117-260): `where` ANDs onto the current group, `orWhere`
+    starts an alternative."""
+
+    def __init__(self):
+        self._groups: List[List[dict]] = [[]]
+
+    def where(self, field: str, operator, value=None) -> "QueryCondition":
+        self._groups[-1].append(_build(field, operator, value))
+        return self
+
+    def orWhere(self, field: str, operator, value=None) -> "QueryCondition":
+        self._groups.append([_build(field, operator, value)])
+        return self
+
+    def whereIn(self, field, values):
+        return self.where(field, "IN", list(values))
+
+    def whereNotIn(self, field, values):
+        return self.where(field, "NOT IN", list(values))
+
+    def whereBetween(self, field, start, end):
+        return self.where(field, "BETWEEN", [start, end])
+
+    def whereNull(self, field):
+        return self.where(field, "IS", None)
+
+    def whereNotNull(self, field):
+        return self.where(field, "IS NOT", None)
+
+    @property
+    def isEmpty(self) -> bool:
+        return not any(self._groups)
+
+    def build(self) -> dict:
+        groups = [g for g in self._groups if g]
+        if not groups:
+            return {}
+        ands = [g[0] if len(g) == 1 else {"AND": g} for g in groups]
+        return ands[0] if len(ands) == 1 else {"OR": ands}
+
+
+def _build(field, operator, value):
+    """`_buildCondition` (query_condition.dart:478-520)."""
+    if value is None:
+        if operator in ("IS", "IS NOT"):
+            return {field: {operator: None}}
+        return {field: operator}
+    op = str(operator).upper()
+    if op == "BETWEEN":
+        return {field: {"BETWEEN": {"start": value[0], "end": value[1]}}}
+    return {field: {op: value}}
