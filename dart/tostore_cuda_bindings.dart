@@ -18,6 +18,8 @@
 import 'dart:ffi';
 import 'dart:typed_data';
 
+import 'dart:convert';
+
 import 'package:ffi/ffi.dart';
 
 /// Mirrors `tsc_index_desc`.
@@ -46,6 +48,32 @@ final class TscIndexDesc extends Struct {
   external int nqMax;
 }
 
+/// Mirrors `tsc_where_op`: one step of the postfix condition program
+/// (leaf operators restate ConditionRecordMatcher._evaluateOperator,
+/// lib/src/handler/value_matcher.dart:570-612).
+final class TscWhereOp extends Struct {
+  @Uint8()
+  external int kind; // 0 leaf, 1 AND, 2 OR
+  @Uint8()
+  external int op; // 0 = 1 != 2 > 3 >= 4 < 5 <= 6 BETWEEN 7 IN 8 NOT IN 9 IS NULL 10 IS NOT NULL
+  @Uint16()
+  external int n;
+  @Uint32()
+  external int columnId;
+  @Int64()
+  external int iLo;
+  @Int64()
+  external int iHi;
+  @Double()
+  external double fLo;
+  @Double()
+  external double fHi;
+  @Uint32()
+  external int argsOffset;
+  @Uint32()
+  external int reserved;
+}
+
 typedef _CreateN = Int32 Function(Pointer<TscIndexDesc>, Pointer<Uint64>);
 typedef _CreateD = int Function(Pointer<TscIndexDesc>, Pointer<Uint64>);
 typedef _HandleN = Int32 Function(Uint64);
@@ -68,6 +96,23 @@ typedef _SubmitD = int Function(int, Pointer<Float>, int, int, double,
     Pointer<Int64>, Pointer<Double>, Pointer<Uint32>, Pointer<Uint64>);
 typedef _PollN = Int32 Function(Uint64, Pointer<Int32>);
 typedef _PollD = int Function(int, Pointer<Int32>);
+typedef _ColCreateN = Int32 Function(Uint64, Uint32, Uint8);
+typedef _ColCreateD = int Function(int, int, int);
+typedef _ColAppendN = Int32 Function(
+    Uint64, Uint32, Uint64, Pointer<Void>, Pointer<Uint8>, Uint64);
+typedef _ColAppendD = int Function(int, int, int, Pointer<Void>, Pointer<Uint8>, int);
+typedef _FilterWhereN = Int32 Function(
+    Uint64, Pointer<TscWhereOp>, Uint32, Pointer<Void>, Uint32, Pointer<Uint64>);
+typedef _FilterWhereD = int Function(
+    int, Pointer<TscWhereOp>, int, Pointer<Void>, int, Pointer<Uint64>);
+typedef _SetPksN = Int32 Function(Uint64, Uint64, Pointer<Uint8>, Pointer<Uint64>, Uint64);
+typedef _SetPksD = int Function(int, int, Pointer<Uint8>, Pointer<Uint64>, int);
+typedef _SearchPkN = Int32 Function(
+    Uint64, Pointer<Double>, Uint64, Uint32, Double, Pointer<Int64>, Pointer<Double>,
+    Pointer<Double>, Pointer<Uint8>, Uint64, Pointer<Uint64>, Pointer<Uint32>);
+typedef _SearchPkD = int Function(
+    int, Pointer<Double>, int, int, double, Pointer<Int64>, Pointer<Double>,
+    Pointer<Double>, Pointer<Uint8>, int, Pointer<Uint64>, Pointer<Uint32>);
 typedef _LastErrorN = Pointer<Utf8> Function();
 typedef _LastErrorD = Pointer<Utf8> Function();
 
@@ -261,6 +306,133 @@ class TostoreCuda {
       calloc.free(count);
       calloc.free(ticket);
       calloc.free(done);
+    }
+  }
+  /// Attribute column for the GPU WHERE prefilter: `colType` 0 = integer, 1 = double
+  /// (DataType.integer / DataType.double fields of the table).
+  static bool columnCreate(int handle, int columnId, int colType) {
+    final lib = _open();
+    if (lib == null) return false;
+    return lib.lookupFunction<_ColCreateN, _ColCreateD>('tsc_index_column_create')(
+            handle, columnId, colType) ==
+        0;
+  }
+
+  /// Flush-time hook next to appendRows: the field's values for node ids
+  /// [firstNodeId, firstNodeId + values.length); `null` entries become NULL.
+  static bool columnAppendInt(int handle, int columnId, int firstNodeId, List<int?> values) {
+    final lib = _open();
+    if (lib == null || values.isEmpty) return lib != null;
+    final fn = lib.lookupFunction<_ColAppendN, _ColAppendD>('tsc_index_column_append');
+    final v = calloc<Int64>(values.length);
+    final nulls = calloc<Uint8>(values.length);
+    try {
+      for (var i = 0; i < values.length; i++) {
+        v[i] = values[i] ?? 0;
+        nulls[i] = values[i] == null ? 1 : 0;
+      }
+      return fn(handle, columnId, firstNodeId, v.cast(), nulls, values.length) == 0;
+    } finally {
+      calloc.free(v);
+      calloc.free(nulls);
+    }
+  }
+
+  static bool columnAppendDouble(int handle, int columnId, int firstNodeId, List<double?> values) {
+    final lib = _open();
+    if (lib == null || values.isEmpty) return lib != null;
+    final fn = lib.lookupFunction<_ColAppendN, _ColAppendD>('tsc_index_column_append');
+    final v = calloc<Double>(values.length);
+    final nulls = calloc<Uint8>(values.length);
+    try {
+      for (var i = 0; i < values.length; i++) {
+        v[i] = values[i] ?? 0.0;
+        nulls[i] = values[i] == null ? 1 : 0;
+      }
+      return fn(handle, columnId, firstNodeId, v.cast(), nulls, values.length) == 0;
+    } finally {
+      calloc.free(v);
+      calloc.free(nulls);
+    }
+  }
+
+  /// Evaluate a compiled condition (postfix `ops`, filled by the caller from
+  /// `QueryCondition.build()` after `normalize`) on the GPU and install it as the
+  /// prefilter of the following searches. Returns the number of matching rows, -1 on error.
+  static int filterWhere(int handle, Pointer<TscWhereOp> ops, int nOps, Pointer<Void> inArgs,
+      int nInArgs) {
+    final lib = _open();
+    if (lib == null) return -1;
+    final fn = lib.lookupFunction<_FilterWhereN, _FilterWhereD>('tsc_index_filter_where');
+    final matched = calloc<Uint64>();
+    try {
+      return fn(handle, ops, nOps, inArgs, nInArgs, matched) == 0 ? matched.value : -1;
+    } finally {
+      calloc.free(matched);
+    }
+  }
+
+  /// `__nid2pk` deltas of `_writeNodeMappings` (vector_index_manager.dart:1276-1293):
+  /// keys for node ids [firstNodeId, ...); an empty string is the tombstone mapping.
+  static bool setPrimaryKeys(int handle, int firstNodeId, List<String> pks) {
+    final lib = _open();
+    if (lib == null || pks.isEmpty) return lib != null;
+    final fn = lib.lookupFunction<_SetPksN, _SetPksD>('tsc_index_set_primary_keys');
+    final enc = [for (final p in pks) utf8.encode(p)];
+    final total = enc.fold<int>(0, (a, b) => a + b.length);
+    final bytes = calloc<Uint8>(total == 0 ? 1 : total);
+    final offs = calloc<Uint64>(pks.length + 1);
+    try {
+      var o = 0;
+      for (var i = 0; i < enc.length; i++) {
+        offs[i] = o;
+        bytes.asTypedList(total == 0 ? 1 : total).setRange(o, o + enc[i].length, enc[i]);
+        o += enc[i].length;
+      }
+      offs[pks.length] = o;
+      return fn(handle, firstNodeId, bytes, offs, pks.length) == 0;
+    } finally {
+      calloc.free(bytes);
+      calloc.free(offs);
+    }
+  }
+
+  /// Whole `VectorIndexManager.vectorSearch` body after the precondition checks
+  /// (vector_index_manager.dart:514-588) in one call: query prep, exact search, nodeId -> PK,
+  /// score. Returns (primaryKey, distance, score) triples, ascending distance; [] on error.
+  static List<(String, double, double)> vectorSearchPk(
+      int handle, List<double> queryVector, int topK,
+      {double? distanceThreshold, int pkCapacity = 65536}) {
+    final lib = _open();
+    if (lib == null || topK <= 0) return const [];
+    final fn = lib.lookupFunction<_SearchPkN, _SearchPkD>('tsc_vector_search_pk');
+    final q = calloc<Double>(queryVector.isEmpty ? 1 : queryVector.length);
+    final ids = calloc<Int64>(topK);
+    final dist = calloc<Double>(topK);
+    final score = calloc<Double>(topK);
+    final pkBytes = calloc<Uint8>(pkCapacity);
+    final offs = calloc<Uint64>(topK + 1);
+    final count = calloc<Uint32>();
+    try {
+      for (var i = 0; i < queryVector.length; i++) {
+        q[i] = queryVector[i];
+      }
+      final rc = fn(handle, q, queryVector.length, topK, distanceThreshold ?? double.nan, ids,
+          dist, score, pkBytes, pkCapacity, offs, count);
+      if (rc != 0) return const [];
+      final raw = pkBytes.asTypedList(pkCapacity);
+      return [
+        for (var i = 0; i < count.value; i++)
+          (utf8.decode(raw.sublist(offs[i], offs[i + 1])), dist[i], score[i])
+      ];
+    } finally {
+      calloc.free(q);
+      calloc.free(ids);
+      calloc.free(dist);
+      calloc.free(score);
+      calloc.free(pkBytes);
+      calloc.free(offs);
+      calloc.free(count);
     }
   }
 }

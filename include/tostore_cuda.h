@@ -215,6 +215,26 @@ int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len,
                           uint32_t k, double distance_threshold, int64_t *out_ids,
                           double *out_dist, double *out_score, uint32_t *out_count);
 
+/* ---- nodeId -> primary key side table. Takes the place of the
+ * `<index>__nid2pk` B+Tree lookups after the engine call
+ * (core/vector_index_manager.dart:553-588; maintained at flush :1276-1293): a dense
+ * host-memory table so that result assembly costs k array reads instead of k B+Tree
+ * descents. key i = utf8[offsets[i], offsets[i+1]); an EMPTY key is the tombstone
+ * mapping (value [1], :1283-1286): such rows are dropped from results. ---- */
+int32_t tsc_index_set_primary_keys(uint64_t handle, uint64_t first_node_id,
+                                   const uint8_t *utf8, const uint64_t *offsets, uint64_t n);
+/* out_len = 0 when the node has no (or a tombstoned) mapping; TSC_ERR_BAD_ARG when the
+ * key does not fit `capacity` (out_len still reports the needed size). */
+int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *out_utf8,
+                                  uint32_t capacity, uint32_t *out_len);
+/* tsc_vector_search + the reference's result assembly (:576-587): results whose node
+ * has no mapping are dropped, the rest stay in ascending distance order. out_pk_utf8
+ * receives the concatenated keys, out_pk_offsets [k+1] their boundaries. */
+int32_t tsc_vector_search_pk(uint64_t handle, const double *values, uint64_t len, uint32_t k,
+                             double distance_threshold, int64_t *out_ids, double *out_dist,
+                             double *out_score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
+                             uint64_t *out_pk_offsets, uint32_t *out_count);
+
 /* ---- row-range sharding across GPUs (one process per GPU) ---- */
 /* Merge n_parts per-shard results ([n_parts, nq, k] ids/dist as produced by
  * tsc_search_device on each shard and all-gathered by the caller or by
@@ -249,6 +269,25 @@ int32_t tsc_debug_gemm_keys(uint64_t handle, const float *queries, uint32_t nq,
 /* self-test hook: the warp-sliced CRC-32 of the page validator, re-enacted on the
  * host (no GPU needed); must equal CRC-32/IEEE (Crc32.of, btree_page.dart:64-89). */
 uint32_t tsc_selftest_crc32(const uint8_t *data, uint32_t len);
+
+/* self-test hook: the program translation and per-row evaluation of
+ * tsc_index_filter_where re-run on host arrays (no GPU needed). col_values is
+ * [n_cols][n_rows] raw 8-byte values, col_is_null [n_cols][n_rows] bytes, out_match
+ * [n_rows] bytes. */
+int32_t tsc_selftest_where(const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                           uint32_t n_in_args, uint32_t n_cols, const uint32_t *col_ids,
+                           const uint8_t *col_types, const uint64_t *col_values,
+                           const uint8_t *col_is_null, uint64_t n_rows, uint8_t *out_match);
+
+/* self-test hooks (no GPU): a host-only index object that carries only the primary-key
+ * table (every compute entry point fails on it; release with tsc_index_destroy), and the
+ * result-assembly step of tsc_vector_search_pk applied to caller-supplied hits
+ * (ids / dist / score [k], *inout_count valid entries; compacted in place). */
+int32_t tsc_selftest_host_index(uint64_t capacity_rows, uint64_t first_node_id,
+                                uint64_t *out_handle);
+int32_t tsc_selftest_pk_assemble(uint64_t handle, uint32_t k, int64_t *ids, double *dist,
+                                 double *score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
+                                 uint64_t *out_pk_offsets, uint32_t *inout_count);
 
 #ifdef __cplusplus
 }

@@ -369,3 +369,37 @@ def test_sparse_where_filter_uses_per_row_scan(dt, dims):
                         oi, od = oracle.search(rows, Qp[q], metric, k, deleted=dead, filter=mask)
                         assert_same(ids, dist, cnt, q, oi, od, k, f"dt{dt} d{dims} m{metric} f{frac}")
                 ix.set_deleted(np.nonzero(dead)[0], deleted=False)
+
+
+def test_primary_key_side_table_and_pk_search():
+    """nodeId -> PK side table (role of `__nid2pk`, vector_index_manager.dart:553-588):
+    unmapped / tombstone-mapped nodes are dropped from the assembled result, the rest keep
+    ascending distance order; keys round-trip byte for byte (multi-byte utf-8 included)."""
+    n, d, k = 400, 24, 12
+    rows = oracle.synth_rows(31, 0, n, d)
+    q = oracle.synth_rows(32, 0, 1, d)[0].astype(np.float64)
+    T = t()
+    with T.GpuVectorIndex(d, 0, capacity_rows=n, k_max=16, nq_max=4) as ix:
+        ix.append_rows(rows)
+        pks = [f"用户-{i}" if i % 3 == 0 else f"user_{i:05d}" for i in range(n)]
+        ix.set_primary_keys(pks)
+        assert ix.get_primary_key(0) == "用户-0" and ix.get_primary_key(n - 1) == pks[n - 1]
+        assert ix.get_primary_key(n + 5) is None
+        oi, od = oracle.search(rows, q.astype(np.float32), 0, k)
+        got_pk, ids, dist, score = ix.vector_search_pk(q, k)
+        assert got_pk == [pks[i] for i in oi] and (ids == oi).all()
+        assert (dist.view(np.int64) == od.view(np.int64)).all()
+        assert np.allclose(score, 1.0 / (1.0 + od), rtol=0, atol=0)
+        # tombstone the mapping of the best and the 3rd hit: they vanish, order is kept
+        ix.set_primary_keys([None], first_node_id=int(oi[0]))
+        ix.set_primary_keys([""], first_node_id=int(oi[2]))
+        got_pk2, ids2, dist2, _ = ix.vector_search_pk(q, k)
+        keep = [j for j in range(k) if j not in (0, 2)]
+        assert got_pk2 == [pks[oi[j]] for j in keep] and (ids2 == oi[keep]).all()
+        assert (dist2.view(np.int64) == od[keep].view(np.int64)).all()
+        with pytest.raises(T.TscError):
+            ix.vector_search_pk(q, k, pk_capacity=8)                 # keys do not fit
+        with pytest.raises(T.TscError):
+            ix.set_primary_keys(["x"], first_node_id=n + 100)        # outside the shard
+        ix.clear()
+        assert ix.get_primary_key(0) is None

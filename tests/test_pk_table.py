@@ -1,0 +1,82 @@
+"""nodeId -> primary key side table (role of the reference's `__nid2pk` B+Tree,
+core/vector_index_manager.dart:553-588, :1276-1293): host-memory logic of the library,
+exercised WITHOUT a GPU through the self-test hooks (a host-only index object and the
+result-assembly step of tsc_vector_search_pk)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from tostore_b200 import GpuVectorIndex, TscError
+from tostore_b200 import _native as N
+
+
+class HostIndex(GpuVectorIndex):
+    """GpuVectorIndex bound to a host-only self-test handle (primary-key table only)."""
+
+    def __init__(self, capacity, first_node_id=0):
+        self._lib = N.lib()
+        self.first_node_id = first_node_id
+        h = C.c_uint64(0)
+        N.check(self._lib.tsc_selftest_host_index(capacity, first_node_id, C.byref(h)), "host_index")
+        self.handle = h.value
+
+    def assemble(self, ids, dist, score, k, cap=4096):
+        ids = np.array(list(ids) + [-1] * (k - len(ids)), dtype=np.int64)
+        n = C.c_uint32(len(dist))
+        dist = np.array(list(dist) + [np.nan] * (k - len(dist)), dtype=np.float64)
+        score = np.array(list(score) + [np.nan] * (k - len(score)), dtype=np.float64)
+        pkb = np.zeros(cap, dtype=np.uint8)
+        offs = np.zeros(k + 1, dtype=np.uint64)
+        N.check(self._lib.tsc_selftest_pk_assemble(self.handle, k, ids.ctypes.data, dist.ctypes.data,
+                                                   score.ctypes.data, pkb.ctypes.data, cap,
+                                                   offs.ctypes.data, C.byref(n)), "pk_assemble")
+        raw = pkb.tobytes()
+        pks = [raw[int(offs[i]): int(offs[i + 1])].decode() for i in range(n.value)]
+        return pks, ids, dist, score, n.value, offs
+
+
+def test_set_get_overwrite_and_bounds():
+    with HostIndex(100, first_node_id=1000) as ix:
+        pks = [f"user_{i}" if i % 4 else f"用户-{i}" for i in range(60)]
+        ix.set_primary_keys(pks, first_node_id=1000)
+        assert [ix.get_primary_key(1000 + i) for i in range(60)] == pks
+        assert ix.get_primary_key(999) is None and ix.get_primary_key(1060) is None
+        assert ix.get_primary_key(5_000_000) is None
+        ix.set_primary_keys(["replaced", None, ""], first_node_id=1010)        # update + tombstones
+        assert ix.get_primary_key(1010) == "replaced"
+        assert ix.get_primary_key(1011) is None and ix.get_primary_key(1012) is None
+        assert ix.get_primary_key(1013) == pks[13]
+        ix.set_primary_keys(["tail"], first_node_id=1099)                       # sparse: gap stays unmapped
+        assert ix.get_primary_key(1099) == "tail" and ix.get_primary_key(1080) is None
+        with pytest.raises(TscError):
+            ix.set_primary_keys(["x"], first_node_id=1100)                      # beyond capacity
+        with pytest.raises(TscError):
+            ix.set_primary_keys(["x"], first_node_id=10)                        # below the shard
+        ix.set_primary_keys([], first_node_id=1000)                             # no-op
+
+
+def test_result_assembly_drops_unmapped_and_keeps_order():
+    with HostIndex(50) as ix:
+        ix.set_primary_keys([f"pk{i}" for i in range(40)])
+        ix.set_primary_keys([None], first_node_id=7)                            # tombstone mapping
+        hits = [5, 7, 39, 45, 0]                                                # 7 tombstoned, 45 unmapped
+        dist = [0.1, 0.2, 0.3, 0.4, 0.5]
+        score = [0.9, 0.8, 0.7, 0.6, 0.5]
+        pks, ids, d, s, n, offs = ix.assemble(hits, dist, score, k=8)
+        assert n == 3 and pks == ["pk5", "pk39", "pk0"]
+        assert ids[:3].tolist() == [5, 39, 0] and d[:3].tolist() == [0.1, 0.3, 0.5]
+        assert s[:3].tolist() == [0.9, 0.7, 0.5]
+        assert (ids[3:] == -1).all() and np.isnan(d[3:]).all() and np.isnan(s[3:]).all()
+        assert offs.tolist() == [0, 3, 7, 10] + [10] * 5
+        with pytest.raises(TscError):
+            ix.assemble(hits, dist, score, k=8, cap=5)                          # keys do not fit
+        pks, *_ , n, _ = ix.assemble([], [], [], k=4)
+        assert n == 0 and pks == []
+
+
+def test_host_only_handle_refuses_compute():
+    with HostIndex(10) as ix:
+        with pytest.raises(TscError):
+            ix.search(np.zeros((1, 4), dtype=np.float32), 1) if hasattr(ix, "dims") else \
+                N.check(ix._lib.tsc_search(ix.handle, None, 1, 1, float("nan"), None, None, None), "tsc_search")

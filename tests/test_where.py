@@ -143,6 +143,68 @@ def test_compiled_program_equals_oracle(ci):
     assert got == want
 
 
+def _selftest(prog: W.WhereProgram, columns, n_rows, col_map=COLS):
+    """Run the library's own translation + per-row evaluation (the code the kernel runs)
+    on the host through tsc_selftest_where."""
+    import ctypes as C
+    from tostore_b200 import _native as N
+    names = list(col_map)
+    ids = np.array([col_map[n][0] for n in names], dtype=np.uint32)
+    types = np.array([col_map[n][1] for n in names], dtype=np.uint8)
+    vals = np.zeros((len(names), n_rows), dtype=np.uint64)
+    nulls = np.ones((len(names), n_rows), dtype=np.uint8)
+    for ci, name in enumerate(names):
+        for r, v in enumerate(columns[name][:n_rows]):
+            if v is None:
+                continue
+            nulls[ci, r] = 0
+            vals[ci, r] = (np.array([v], dtype=np.int64) if types[ci] == I64
+                           else np.array([v], dtype=np.float64)).view(np.uint64)[0]
+    ops, n_ops, raw, n_args = prog.buffers()
+    out = np.zeros(n_rows, dtype=np.uint8)
+    N.check(N.lib().tsc_selftest_where(C.cast(ops, C.c_void_p), n_ops, raw.ctypes.data, n_args,
+                                       len(names), ids.ctypes.data, types.ctypes.data,
+                                       vals.ctypes.data, nulls.ctypes.data, n_rows, out.ctypes.data),
+            "tsc_selftest_where")
+    return out.astype(bool).tolist()
+
+
+@pytest.mark.parametrize("ci", range(len(CONDITIONS)))
+def test_library_evaluation_equals_oracle_on_host(ci):
+    """where_build + where_eval_row (shared by the kernel) against the oracle, no GPU."""
+    cols = _columns(n=300, seed=17)
+    n = len(cols["age"])
+    cond = CONDITIONS[ci]
+    want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
+    assert _selftest(W.compile_condition(cond, COLS), cols, n) == want
+
+
+def test_library_rejects_malformed_programs():
+    from tostore_b200 import TscError
+    cols = {"age": [1, 2], "score": [0.5, 1.5], "year": [2000, 2001]}
+    bad = W.WhereProgram()
+    bad._node(W.W_AND, 2)                                   # pops from an empty stack
+    with pytest.raises(TscError):
+        _selftest(bad, cols, 2)
+    two = W.WhereProgram()
+    two._leaf(W.OP_TRUE)
+    two._leaf(W.OP_TRUE)                                    # leaves two values
+    with pytest.raises(TscError):
+        _selftest(two, cols, 2)
+    unk = W.compile_condition({"age": 1}, {"age": (99, I64)})
+    with pytest.raises(TscError):
+        _selftest(unk, cols, 2)
+    lst = W.compile_condition({"age": {"IN": [1, 2, 3]}}, COLS)
+    lst.ops[0].args_offset = 5                              # IN list outside in_args
+    with pytest.raises(TscError):
+        _selftest(lst, cols, 2)
+    wide = W.WhereProgram()                                 # 63-ary AND is the widest allowed
+    for _ in range(63):
+        wide._leaf(W.OP_TRUE)
+    wide._node(W.W_AND, 63)
+    assert _selftest(wide, cols, 2) == [True, True]
+
+
 def test_builder_map_form():
     qc = W.QueryCondition().where("age", ">", 30).where("score", "<=", 1.5).orWhere("year", "IN", [1, 2])
     assert qc.build() == {"OR": [{"AND": [{"age": {">": 30}}, {"score": {"<=": 1.5}}]},
@@ -238,3 +300,36 @@ def test_gpu_filter_where_large_selectivity_and_sparse_scan():
         ids, dist, cnt = ix.search(q, 10)
         oi, od = oracle.search_synth(77, n, d, 0, q, 0, 10, filter=want)
         assert (ids[0] == oi).all() and (dist[0].view(np.int64) == od.view(np.int64)).all()
+
+
+@pytest.mark.gpu
+def test_store_vector_search_with_where():
+    """`GpuVectorStore.vectorSearch(where=...)`: the additive WHERE + kNN call of config 5."""
+    import oracle
+    from tostore_b200 import (GpuVectorStore, QueryCondition, VectorData, VectorDistanceMetric,
+                              VectorFieldConfig, VectorIndexConfig, VectorPrecision)
+    n, d = 500, 16
+    rows = oracle.synth_rows(91, 0, n, d)
+    rng = np.random.default_rng(2)
+    price = [None if i % 17 == 0 else int(rng.integers(0, 100)) for i in range(n)]
+    rating = [float(np.round(rng.random() * 5, 2)) for _ in range(n)]
+    st = GpuVectorStore(capacity_rows=1024)
+    try:
+        st.createVectorIndex("items", "emb", VectorFieldConfig(d, VectorPrecision.float32),
+                             VectorIndexConfig(VectorDistanceMetric.l2),
+                             attributeFields={"price": "integer", "rating": "double"})
+        st.batchInsert("items", [{"id": f"pk{i}", "emb": VectorData.fromList(rows[i]),
+                                  "price": price[i], "rating": rating[i]} for i in range(n)])
+        q = oracle.synth_rows(92, 0, 1, d)[0]
+        qc = QueryCondition().where("price", "<", 40).where("rating", ">=", 2).orWhere("price", "IS", None)
+        want = np.array(wo.evaluate_columns(qc.build(), {"price": price, "rating": rating},
+                                            {"price": "i64", "rating": "f64"}), dtype=bool)
+        res = st.vectorSearch("items", fieldName="emb", queryVector=VectorData.fromList(q), topK=7, where=qc)
+        oi, od = oracle.search(rows, q, 0, 7, filter=want)
+        assert [r.primaryKey for r in res] == [f"pk{i}" for i in oi]
+        assert [r.distance for r in res] == od.tolist()
+        res2 = st.vectorSearch("items", fieldName="emb", queryVector=VectorData.fromList(q), topK=7)
+        oi2, _ = oracle.search(rows, q, 0, 7)
+        assert [r.primaryKey for r in res2] == [f"pk{i}" for i in oi2]      # where=None clears it
+    finally:
+        st.close()

@@ -117,14 +117,26 @@ def main():
     esz = 4 if dt == 0 else 2
     bytes_per_gpu = per * d * esz * live_frac
 
+    # results of the last query to the host, then leave the process group BEFORE the oracle
+    # runs: the CPU check takes seconds to minutes and must not sit inside a collective
+    # (a rank waiting at a barrier for 10 min trips the NCCL watchdog)
+    i = nqs - 1
+    ids, dd, cnt_i = o_ids[i].cpu().numpy(), o_dist[i].cpu().numpy(), int(o_cnt[i])
+    ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
     check = None
     if args.check and rank == 0:
-        i = nqs - 1
         t0 = time.perf_counter()
-        oi, od = oracle.search_synth(SEED, n_total, d, dt, Q[i], metric, k, filter=mask_all)
-        ids, dd = o_ids[i].cpu().numpy(), o_dist[i].cpu().numpy()
+        # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
+        threads = len(os.sched_getaffinity(0))
+        oi, od = oracle.search_synth(SEED, n_total, d, dt, Q[i], metric, k, filter=mask_all,
+                                     threads=threads)
         check = {"oracle_rows": n_total, "oracle_s": time.perf_counter() - t0,
-                 "ids_identical": bool((ids[: len(oi)] == oi).all() and int(o_cnt[i]) == len(oi)),
+                 "oracle_threads": threads,
+                 "ids_identical": bool((ids[: len(oi)] == oi).all() and cnt_i == len(oi)),
                  "dist_bit_identical": bool((dd[: len(od)].view(np.int64) == od.view(np.int64)).all())}
 
     if rank == 0:
@@ -142,10 +154,6 @@ def main():
                "scan_frac_of_measured_hbm": bytes_per_gpu / hot_ms / 1e6 / peak,
                "exchange_and_select_ms": step_ms - hot_ms, "check": check}
         print(json.dumps(out), flush=True)
-    ix.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

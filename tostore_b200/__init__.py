@@ -10,12 +10,13 @@ from .engine import (DEV_BF16, DEV_F16, DEV_F32, METRIC_COSINE, METRIC_INNER_PRO
 from .vector_store import (DeviceDType, GpuVectorStore, VectorData, VectorDistanceMetric,
                            VectorFieldConfig, VectorIndexConfig, VectorPrecision,
                            VectorSearchResult)
+from .where import QueryCondition, compile_condition
 from ._native import LIB_PATH, TscError
 
 __all__ = [
     "GpuVectorIndex", "GpuVectorStore", "VectorData", "VectorDistanceMetric",
     "VectorFieldConfig", "VectorIndexConfig", "VectorPrecision", "VectorSearchResult",
-    "DeviceDType", "TscError", "LIB_PATH",
+    "DeviceDType", "TscError", "LIB_PATH", "QueryCondition", "compile_condition",
     "METRIC_L2", "METRIC_INNER_PRODUCT", "METRIC_COSINE", "SRC_F64", "SRC_F32", "SRC_I8",
     "DEV_F32", "DEV_BF16", "DEV_F16",
 ]

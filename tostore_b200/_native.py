@@ -25,6 +25,8 @@ EXPORTS = (
     "tsc_stats_get", "tsc_stats_reset", "tsc_index_device_rows", "tsc_selftest_crc32",
     "tsc_debug_gemm_keys",
     "tsc_index_column_create", "tsc_index_column_append", "tsc_index_filter_where",
+    "tsc_selftest_where", "tsc_selftest_host_index", "tsc_selftest_pk_assemble",
+    "tsc_index_set_primary_keys", "tsc_index_get_primary_key", "tsc_vector_search_pk",
 )
 
 TSC_OK = 0
@@ -107,6 +109,13 @@ def lib():
     L.tsc_index_column_create.argtypes = [u64, u32, C.c_uint8]
     L.tsc_index_column_append.argtypes = [u64, u32, u64, vp, vp, u64]
     L.tsc_index_filter_where.argtypes = [u64, vp, u32, vp, u32, C.POINTER(u64)]
+    L.tsc_selftest_where.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, vp, u64, vp]
+    L.tsc_selftest_host_index.argtypes = [u64, u64, C.POINTER(u64)]
+    L.tsc_selftest_pk_assemble.argtypes = [u64, u32, vp, vp, vp, vp, u64, vp, C.POINTER(u32)]
+    L.tsc_index_set_primary_keys.argtypes = [u64, u64, vp, vp, u64]
+    L.tsc_index_get_primary_key.argtypes = [u64, u64, vp, u32, C.POINTER(u32)]
+    L.tsc_vector_search_pk.argtypes = [u64, vp, u64, u32, C.c_double, vp, vp, vp, vp, u64, vp,
+                                       C.POINTER(u32)]
     L.tsc_selftest_crc32.argtypes = [vp, u32]
     L.tsc_selftest_crc32.restype = u32
     for name in EXPORTS:

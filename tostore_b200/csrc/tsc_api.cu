@@ -44,6 +44,13 @@ static Index *lookup(uint64_t h) {
 
 Index *lookup_index(uint64_t h) { return lookup(h); }
 
+uint64_t register_index(Index *ix) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  uint64_t h = g_next_handle++;
+  g_index[h] = ix;
+  return h;
+}
+
 struct Ticket {
   Index *ix;
   uint64_t handle;
@@ -64,6 +71,10 @@ static cudaError_t dev_alloc(Index *ix, T **p, size_t n) {
 }
 
 static void free_index(Index *ix) {
+  if (ix->host_only) {
+    delete ix;
+    return;
+  }
   cudaSetDevice(ix->device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
   cudaFree(ix->d_rows);
@@ -456,6 +467,9 @@ int32_t tsc_index_clear(uint64_t handle) {
   ix->deleted_rows = 0;
   ix->has_deleted = ix->has_filter = ix->live_dirty = false;
   for (auto &c : ix->columns) c.rows = 0;
+  ix->pk_off.clear();
+  ix->pk_len.clear();
+  ix->pk_arena.clear();
   return TSC_OK;
 }
 

@@ -46,6 +46,7 @@ struct Index {
   std::mutex mu;
   tsc_index_desc desc{};
   int device = 0;
+  bool host_only = false;   // self-test object without device memory (tsc_selftest_host_index)
   int sm_count = 148;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
@@ -91,6 +92,11 @@ struct Index {
 
   ScanConfig scan;
 
+  // nodeId -> primary key side table (host memory; role of the `__nid2pk` B+Tree)
+  std::vector<uint64_t> pk_off;       // per shard row: start in pk_arena
+  std::vector<uint32_t> pk_len;       // per shard row: byte length, 0 = unmapped / tombstone
+  std::vector<char> pk_arena;         // append-only utf-8 bytes
+
   // attribute columns for the WHERE prefilter
   std::vector<AttrColumn> columns;
   uint64_t *d_where_args = nullptr;   // IN-list keys
@@ -117,6 +123,7 @@ struct Index {
 };
 
 Index *lookup_index(uint64_t handle);   // NULL + error string when unknown
+uint64_t register_index(Index *ix);
 int32_t ensure_stage_bytes(Index *ix, size_t bytes);
 
 // launchers implemented per translation unit

@@ -1,0 +1,163 @@
+// tsc_pk.cu — nodeId -> primary key side table and PK-returning search
+// (include/tostore_cuda.h: tsc_index_set_primary_keys / _get_primary_key,
+// tsc_vector_search_pk). Host memory only; the reference keeps this mapping in the
+// `<index>__nid2pk` B+Tree (core/vector_index_manager.dart:553-588, :1276-1293).
+#include <string.h>
+
+#include "tsc_index.h"
+
+using namespace tsc;
+
+extern "C" {
+
+int32_t tsc_index_set_primary_keys(uint64_t handle, uint64_t first_node_id, const uint8_t *utf8,
+                                   const uint64_t *offsets, uint64_t n) {
+  Index *ix = lookup_index(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  if (n == 0) return TSC_OK;
+  if (!offsets || (!utf8 && offsets[n] != offsets[0])) {
+    set_error("set_primary_keys: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  std::lock_guard<std::mutex> lk(ix->mu);
+  const uint64_t base = ix->desc.first_node_id;
+  if (first_node_id < base || first_node_id - base + n > ix->capacity) {
+    set_error("set_primary_keys: node ids [%llu, %llu) outside shard [%llu, %llu)",
+              (unsigned long long)first_node_id, (unsigned long long)(first_node_id + n),
+              (unsigned long long)base, (unsigned long long)(base + ix->capacity));
+    return TSC_ERR_BAD_ARG;
+  }
+  for (uint64_t i = 0; i < n; i++)
+    if (offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 0xFFFFFFFFull) {
+      set_error("set_primary_keys: offsets must be non-decreasing (entry %llu)",
+                (unsigned long long)i);
+      return TSC_ERR_BAD_ARG;
+    }
+  const uint64_t row0 = first_node_id - base;
+  try {
+    if (ix->pk_off.size() < row0 + n) {
+      ix->pk_off.resize(row0 + n, 0);
+      ix->pk_len.resize(row0 + n, 0);
+    }
+    const uint64_t arena0 = ix->pk_arena.size();
+    ix->pk_arena.insert(ix->pk_arena.end(), (const char *)utf8 + offsets[0],
+                        (const char *)utf8 + offsets[n]);
+    for (uint64_t i = 0; i < n; i++) {
+      ix->pk_off[row0 + i] = arena0 + (offsets[i] - offsets[0]);
+      ix->pk_len[row0 + i] = (uint32_t)(offsets[i + 1] - offsets[i]);
+    }
+  } catch (const std::bad_alloc &) {
+    set_error("set_primary_keys: out of host memory");
+    return TSC_ERR_OOM;
+  }
+  return TSC_OK;
+}
+
+int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *out_utf8,
+                                  uint32_t capacity, uint32_t *out_len) {
+  Index *ix = lookup_index(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  if (!out_len || (!out_utf8 && capacity)) {
+    set_error("get_primary_key: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  std::lock_guard<std::mutex> lk(ix->mu);
+  *out_len = 0;
+  const uint64_t base = ix->desc.first_node_id;
+  if (node_id < base || node_id - base >= ix->pk_len.size()) return TSC_OK;
+  const uint64_t r = node_id - base;
+  *out_len = ix->pk_len[r];
+  if (ix->pk_len[r] > capacity) {
+    set_error("get_primary_key: key of %u bytes does not fit %u", ix->pk_len[r], capacity);
+    return TSC_ERR_BAD_ARG;
+  }
+  memcpy(out_utf8, ix->pk_arena.data() + ix->pk_off[r], ix->pk_len[r]);
+  return TSC_OK;
+}
+
+// Result assembly after the engine call (vector_index_manager.dart:576-587): drop hits
+// whose node has no primary-key mapping, keep ascending distance order, compact in place.
+static int32_t pk_assemble(Index *ix, uint32_t k, int64_t *out_ids, double *out_dist,
+                           double *out_score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
+                           uint64_t *out_pk_offsets, uint32_t *out_count) {
+  std::lock_guard<std::mutex> lk(ix->mu);
+  const uint64_t base = ix->desc.first_node_id;
+  uint32_t kept = 0;
+  uint64_t used = 0;
+  out_pk_offsets[0] = 0;
+  for (uint32_t j = 0; j < *out_count && j < k; j++) {
+    const uint64_t nid = (uint64_t)out_ids[j];
+    const uint64_t r = nid - base;
+    // `if (pk == null) continue;` vector_index_manager.dart:578-579
+    if (out_ids[j] < 0 || nid < base || r >= ix->pk_len.size() || ix->pk_len[r] == 0) continue;
+    if (used + ix->pk_len[r] > pk_capacity) {
+      set_error("vector_search_pk: keys need more than %llu bytes",
+                (unsigned long long)pk_capacity);
+      return TSC_ERR_BAD_ARG;
+    }
+    memcpy(out_pk_utf8 + used, ix->pk_arena.data() + ix->pk_off[r], ix->pk_len[r]);
+    used += ix->pk_len[r];
+    out_ids[kept] = out_ids[j];
+    out_dist[kept] = out_dist[j];
+    out_score[kept] = out_score[j];
+    out_pk_offsets[++kept] = used;
+  }
+  for (uint32_t j = kept; j < k; j++) {
+    out_ids[j] = -1;
+    out_dist[j] = out_score[j] = __builtin_nan("");
+    out_pk_offsets[j + 1] = used;
+  }
+  *out_count = kept;
+  return TSC_OK;
+}
+
+int32_t tsc_vector_search_pk(uint64_t handle, const double *values, uint64_t len, uint32_t k,
+                             double threshold, int64_t *out_ids, double *out_dist,
+                             double *out_score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
+                             uint64_t *out_pk_offsets, uint32_t *out_count) {
+  Index *ix = lookup_index(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  if (!out_pk_offsets || (!out_pk_utf8 && pk_capacity)) {
+    set_error("vector_search_pk: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  int32_t rc = tsc_vector_search(handle, values, len, k, threshold, out_ids, out_dist, out_score,
+                                 out_count);
+  if (rc != TSC_OK) return rc;
+  return pk_assemble(ix, k, out_ids, out_dist, out_score, out_pk_utf8, pk_capacity, out_pk_offsets,
+                     out_count);
+}
+
+// Self-test hooks (no GPU): a host-only index object that carries nothing but the
+// primary-key table, and the result-assembly step of tsc_vector_search_pk applied to
+// caller-supplied hits. Every compute entry point fails on such a handle (no device
+// memory behind it); release it with tsc_index_destroy.
+int32_t tsc_selftest_host_index(uint64_t capacity_rows, uint64_t first_node_id,
+                                uint64_t *out_handle) {
+  if (!out_handle || capacity_rows == 0) {
+    set_error("selftest_host_index: bad argument");
+    return TSC_ERR_BAD_ARG;
+  }
+  Index *ix = new Index();
+  ix->desc.struct_size = sizeof(tsc_index_desc);
+  ix->desc.first_node_id = first_node_id;
+  ix->desc.capacity_rows = capacity_rows;
+  ix->capacity = capacity_rows;
+  ix->host_only = true;
+  *out_handle = register_index(ix);
+  return TSC_OK;
+}
+
+int32_t tsc_selftest_pk_assemble(uint64_t handle, uint32_t k, int64_t *ids, double *dist,
+                                 double *score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
+                                 uint64_t *out_pk_offsets, uint32_t *inout_count) {
+  Index *ix = lookup_index(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  if (!ids || !dist || !score || !out_pk_offsets || !inout_count) {
+    set_error("selftest_pk_assemble: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  return pk_assemble(ix, k, ids, dist, score, out_pk_utf8, pk_capacity, out_pk_offsets, inout_count);
+}
+
+}  // extern "C"

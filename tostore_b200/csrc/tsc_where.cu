@@ -14,6 +14,96 @@ static AttrColumn *find_column(Index *ix, uint32_t id) {
   return nullptr;
 }
 
+struct WhereColInfo {
+  uint32_t id;
+  uint8_t type;
+};
+
+// Validate a caller's postfix program and translate it into the device form: operands
+// become order-preserving keys of the leaf's column type, columns become slots.
+// Shared by tsc_index_filter_where and the host self-test.
+static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                           uint32_t n_in_args, const WhereColInfo *cinfo, uint32_t n_cinfo,
+                           WhereProgram *prog, uint32_t *slot_ids, uint32_t *n_slots_out,
+                           std::vector<uint64_t> *keys_out) {
+  memset(prog, 0, sizeof *prog);
+  uint32_t n_slots = 0;
+  std::vector<uint64_t> &keys = *keys_out;
+  keys.assign(n_in_args, 0);
+  std::vector<uint8_t> keyed(n_in_args, 0);
+  int depth = 0;   // stack depth check: the program must leave exactly one value
+  for (uint32_t i = 0; i < n_ops; i++) {
+    const tsc_where_op &o = ops[i];
+    WhereDevOp &d = prog->ops[i];
+    d.kind = o.kind;
+    d.op = o.op;
+    d.n = o.n;
+    if (o.kind == TSC_W_AND || o.kind == TSC_W_OR) {
+      if ((int)o.n > depth || o.n > 63) {
+        set_error("filter_where: step %u pops %u values, stack holds %d", i, o.n, depth);
+        return TSC_ERR_BAD_ARG;
+      }
+      depth -= (int)o.n - 1;
+      continue;
+    }
+    if (o.kind != TSC_W_LEAF || o.op >= kOpCount) {
+      set_error("filter_where: step %u has unknown kind %u / op %u", i, o.kind, o.op);
+      return TSC_ERR_BAD_ARG;
+    }
+    if (++depth > kWhereMaxOps) {
+      set_error("filter_where: stack deeper than %d", kWhereMaxOps);
+      return TSC_ERR_BAD_ARG;
+    }
+    if (o.op == TSC_OP_TRUE || o.op == TSC_OP_FALSE) continue;
+    const WhereColInfo *c = nullptr;
+    for (uint32_t j = 0; j < n_cinfo; j++)
+      if (cinfo[j].id == o.column_id) c = &cinfo[j];
+    if (!c) {
+      set_error("filter_where: step %u names unknown column %u", i, o.column_id);
+      return TSC_ERR_BAD_ARG;
+    }
+    uint32_t s = 0;
+    while (s < n_slots && slot_ids[s] != o.column_id) s++;
+    if (s == n_slots) slot_ids[n_slots++] = o.column_id;
+    d.col = s;
+    const bool f64 = c->type == TSC_COL_F64;
+    auto fkey = [](double v) {
+      uint64_t b;
+      memcpy(&b, &v, 8);
+      return where_key_f64_bits(b);
+    };
+    d.lo = f64 ? fkey(o.f_lo) : where_key_i64(o.i_lo);
+    d.hi = f64 ? fkey(o.f_hi) : where_key_i64(o.i_hi);
+    if (o.op == TSC_OP_IN || o.op == TSC_OP_NOT_IN) {
+      if ((uint64_t)o.args_offset + o.n > n_in_args) {
+        set_error("filter_where: step %u IN list [%u, %u) outside in_args (%u)", i, o.args_offset,
+                  o.args_offset + o.n, n_in_args);
+        return TSC_ERR_BAD_ARG;
+      }
+      d.args_off = o.args_offset;
+      for (uint32_t j = 0; j < o.n; j++) {
+        const uint32_t a = o.args_offset + j;
+        uint64_t raw;
+        memcpy(&raw, (const uint8_t *)in_args + (size_t)a * 8, 8);
+        const uint64_t k = f64 ? where_key_f64_bits(raw) : (raw ^ 0x8000000000000000ull);
+        if (keyed[a] && keys[a] != k) {
+          set_error("filter_where: IN value %u is shared by columns of different types", a);
+          return TSC_ERR_BAD_ARG;
+        }
+        keys[a] = k;
+        keyed[a] = 1;
+      }
+    }
+  }
+  if (n_ops && depth != 1) {
+    set_error("filter_where: program leaves %d values on the stack (must be 1)", depth);
+    return TSC_ERR_BAD_ARG;
+  }
+  prog->n_ops = n_ops;
+  *n_slots_out = n_slots;
+  return TSC_OK;
+}
+
 extern "C" {
 
 int32_t tsc_index_column_create(uint64_t handle, uint32_t column_id, uint8_t col_type) {
@@ -116,85 +206,22 @@ int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_
   }
   std::lock_guard<std::mutex> lk(ix->mu);
   WhereProgram prog;
-  memset(&prog, 0, sizeof prog);
   WhereCols cols;
   memset(&cols, 0, sizeof cols);
-  uint32_t slot_of[kWhereMaxCols];
+  std::vector<WhereColInfo> info;
+  for (auto &c : ix->columns) info.push_back({c.id, c.type});
+  uint32_t slot_ids[kWhereMaxCols];
   uint32_t n_slots = 0;
-  std::vector<uint64_t> keys(n_in_args);
-  std::vector<uint8_t> keyed(n_in_args, 0);
-  int depth = 0;   // stack depth check: the program must leave exactly one value
-  for (uint32_t i = 0; i < n_ops; i++) {
-    const tsc_where_op &o = ops[i];
-    WhereDevOp &d = prog.ops[i];
-    d.kind = o.kind;
-    d.op = o.op;
-    d.n = o.n;
-    if (o.kind == TSC_W_AND || o.kind == TSC_W_OR) {
-      if ((int)o.n > depth || o.n > 63) {
-        set_error("filter_where: step %u pops %u values, stack holds %d", i, o.n, depth);
-        return TSC_ERR_BAD_ARG;
-      }
-      depth -= (int)o.n - 1;
-      continue;
-    }
-    if (o.kind != TSC_W_LEAF || o.op >= kOpCount) {
-      set_error("filter_where: step %u has unknown kind %u / op %u", i, o.kind, o.op);
-      return TSC_ERR_BAD_ARG;
-    }
-    if (++depth > kWhereMaxOps) {
-      set_error("filter_where: stack deeper than %d", kWhereMaxOps);
-      return TSC_ERR_BAD_ARG;
-    }
-    if (o.op == TSC_OP_TRUE || o.op == TSC_OP_FALSE) continue;
-    AttrColumn *c = find_column(ix, o.column_id);
-    if (!c) {
-      set_error("filter_where: step %u names unknown column %u", i, o.column_id);
-      return TSC_ERR_BAD_ARG;
-    }
-    uint32_t s = 0;
-    while (s < n_slots && slot_of[s] != o.column_id) s++;
-    if (s == n_slots) {
-      slot_of[n_slots++] = o.column_id;
-      cols.values[s] = c->d_values;
-      cols.nulls[s] = c->d_null;
-      cols.is_f64[s] = c->type == TSC_COL_F64;
-    }
-    d.col = s;
-    const bool f64 = c->type == TSC_COL_F64;
-    auto fkey = [](double v) {
-      uint64_t b;
-      memcpy(&b, &v, 8);
-      return where_key_f64_bits(b);
-    };
-    d.lo = f64 ? fkey(o.f_lo) : where_key_i64(o.i_lo);
-    d.hi = f64 ? fkey(o.f_hi) : where_key_i64(o.i_hi);
-    if (o.op == TSC_OP_IN || o.op == TSC_OP_NOT_IN) {
-      if ((uint64_t)o.args_offset + o.n > n_in_args) {
-        set_error("filter_where: step %u IN list [%u, %u) outside in_args (%u)", i, o.args_offset,
-                  o.args_offset + o.n, n_in_args);
-        return TSC_ERR_BAD_ARG;
-      }
-      d.args_off = o.args_offset;
-      for (uint32_t j = 0; j < o.n; j++) {
-        const uint32_t a = o.args_offset + j;
-        uint64_t raw;
-        memcpy(&raw, (const uint8_t *)in_args + (size_t)a * 8, 8);
-        const uint64_t k = f64 ? where_key_f64_bits(raw) : (raw ^ 0x8000000000000000ull);
-        if (keyed[a] && keys[a] != k) {
-          set_error("filter_where: IN value %u is shared by columns of different types", a);
-          return TSC_ERR_BAD_ARG;
-        }
-        keys[a] = k;
-        keyed[a] = 1;
-      }
-    }
+  std::vector<uint64_t> keys;
+  int32_t brc = where_build(ops, n_ops, in_args, n_in_args, info.data(), (uint32_t)info.size(), &prog,
+                            slot_ids, &n_slots, &keys);
+  if (brc != TSC_OK) return brc;
+  for (uint32_t s = 0; s < n_slots; s++) {
+    AttrColumn *c = find_column(ix, slot_ids[s]);
+    cols.values[s] = c->d_values;
+    cols.nulls[s] = c->d_null;
+    cols.is_f64[s] = c->type == TSC_COL_F64;
   }
-  if (n_ops && depth != 1) {
-    set_error("filter_where: program leaves %d values on the stack (must be 1)", depth);
-    return TSC_ERR_BAD_ARG;
-  }
-  prog.n_ops = n_ops;
   TSC_CUDA(cudaSetDevice(ix->device));
   cudaStream_t st = ix->stream;
   if (n_in_args > ix->where_args_cap) {
@@ -223,6 +250,43 @@ int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_
   ix->has_filter = true;
   ix->live_dirty = true;
   if (out_matched) *out_matched = matched;
+  return TSC_OK;
+}
+
+// Self-test hook (no GPU): the same program translation (where_build) and the same
+// per-row evaluation (where_eval_row) as tsc_index_filter_where, over host arrays.
+// col_values [n_cols][n_rows] raw 8-byte values, col_is_null [n_cols][n_rows] bytes.
+int32_t tsc_selftest_where(const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                           uint32_t n_in_args, uint32_t n_cols, const uint32_t *col_ids,
+                           const uint8_t *col_types, const uint64_t *col_values,
+                           const uint8_t *col_is_null, uint64_t n_rows, uint8_t *out_match) {
+  if ((n_ops && !ops) || n_ops > (uint32_t)kWhereMaxOps || (n_in_args && !in_args) ||
+      n_in_args > 4096 || n_cols > (uint32_t)kWhereMaxCols || (n_rows && !out_match)) {
+    set_error("selftest_where: bad argument");
+    return TSC_ERR_BAD_ARG;
+  }
+  std::vector<WhereColInfo> info;
+  for (uint32_t i = 0; i < n_cols; i++) info.push_back({col_ids[i], col_types[i]});
+  static WhereProgram prog;   // 2 KB: keep it off small thread stacks
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  uint32_t slot_ids[kWhereMaxCols];
+  uint32_t n_slots = 0;
+  std::vector<uint64_t> keys;
+  int32_t rc = where_build(ops, n_ops, in_args, n_in_args, info.data(), n_cols, &prog, slot_ids,
+                           &n_slots, &keys);
+  if (rc != TSC_OK) return rc;
+  uint32_t src[kWhereMaxCols];   // slot -> index into the caller's column arrays
+  for (uint32_t s = 0; s < n_slots; s++)
+    for (uint32_t i = 0; i < n_cols; i++)
+      if (col_ids[i] == slot_ids[s]) src[s] = i;
+  for (uint64_t row = 0; row < n_rows; row++)
+    out_match[row] = where_eval_row(prog, keys.data(), [&](uint32_t c, uint64_t &key, bool &isnull) {
+      const uint64_t raw = col_values[(size_t)src[c] * n_rows + row];
+      key = col_types[src[c]] == TSC_COL_F64 ? where_key_f64_bits(raw)
+                                             : (raw ^ 0x8000000000000000ull);
+      isnull = col_is_null[(size_t)src[c] * n_rows + row] != 0;
+    }) ? 1 : 0;
   return TSC_OK;
 }
 

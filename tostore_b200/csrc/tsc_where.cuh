@@ -59,6 +59,57 @@ __host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
   return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
 
+// One row of the program. `load(slot, key, isnull)` fetches the row's value of a column
+// as an order-preserving key; shared by the kernel and by the host self-test
+// (tsc_selftest_where), so the CPU test-suite exercises the same evaluation code.
+template <class Load>
+__host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog,
+                                                        const uint64_t *args, Load load) {
+  uint64_t stack = 0;
+  uint32_t last_col = 0xFFFFFFFFu;
+  uint64_t key = 0;
+  bool isnull = true;
+  for (uint32_t i = 0; i < prog.n_ops; i++) {
+    const WhereDevOp &op = prog.ops[i];
+    bool r;
+    if (op.kind == kWLeaf) {
+      if (op.op < kOpTrue && op.col != last_col) {
+        last_col = op.col;
+        load(op.col, key, isnull);
+      }
+      switch (op.op) {
+        case kOpEq: r = !isnull && key == op.lo; break;
+        case kOpNe: r = isnull || key != op.lo; break;
+        case kOpGt: r = !isnull && key > op.lo; break;
+        case kOpGe: r = !isnull && key >= op.lo; break;
+        case kOpLt: r = !isnull && key < op.lo; break;
+        case kOpLe: r = !isnull && key <= op.lo; break;
+        case kOpBetween: r = !isnull && key >= op.lo && key <= op.hi; break;
+        case kOpIn:
+        case kOpNotIn: {
+          bool any = false;
+          for (uint32_t j = 0; j < op.n; j++) any |= (key == args[op.args_off + j]);
+          r = op.op == kOpIn ? (!isnull && any) : (isnull || !any);
+          break;
+        }
+        case kOpIsNull: r = isnull; break;
+        case kOpIsNotNull: r = !isnull; break;
+        case kOpTrue: r = true; break;
+        default: r = false; break;
+      }
+      stack = (stack << 1) | (r ? 1ull : 0ull);
+    } else {
+      // n-ary AND / OR over the top n stack bits (n <= 63, checked on the host)
+      const uint32_t n = op.n;
+      const uint64_t m = (1ull << n) - 1ull;
+      const uint64_t top = stack & m;
+      r = (n == 0) ? true : (op.kind == kWAnd ? top == m : top != 0);
+      stack = ((stack >> n) << 1) | (r ? 1ull : 0ull);
+    }
+  }
+  return prog.n_ops == 0 || (stack & 1ull);
+}
+
 // One thread per row, one warp per 32-row bitmap word (ballot), grid-stride over words.
 // HBM traffic: 8 bytes per row per leaf (coalesced 256-byte warp loads) + 4 bytes per 32
 // rows written; a leaf on the column the previous leaf used re-uses the loaded value.
@@ -72,56 +123,14 @@ where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_consta
   unsigned long long local = 0;
   for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
     const uint64_t row = w * 32 + lane;
-    const bool valid = row < n_rows;
-    uint64_t stack = 0;
-    uint32_t last_col = 0xFFFFFFFFu;
-    uint64_t key = 0;
-    bool isnull = true;
-    for (uint32_t i = 0; i < prog.n_ops; i++) {
-      const WhereDevOp &op = prog.ops[i];
-      bool r;
-      if (op.kind == kWLeaf) {
-        if (op.op < kOpTrue && op.col != last_col) {
-          last_col = op.col;
-          isnull = true;
-          if (valid) {
-            const uint64_t raw = __ldg(cols.values[op.col] + row);
-            key = cols.is_f64[op.col] ? where_key_f64_bits(raw) : (raw ^ 0x8000000000000000ull);
-            const uint32_t *nb = cols.nulls[op.col];
-            isnull = nb ? ((__ldg(nb + (row >> 5)) >> (row & 31)) & 1u) : false;
-          }
-        }
-        switch (op.op) {
-          case kOpEq: r = !isnull && key == op.lo; break;
-          case kOpNe: r = isnull || key != op.lo; break;
-          case kOpGt: r = !isnull && key > op.lo; break;
-          case kOpGe: r = !isnull && key >= op.lo; break;
-          case kOpLt: r = !isnull && key < op.lo; break;
-          case kOpLe: r = !isnull && key <= op.lo; break;
-          case kOpBetween: r = !isnull && key >= op.lo && key <= op.hi; break;
-          case kOpIn:
-          case kOpNotIn: {
-            bool any = false;
-            for (uint32_t j = 0; j < op.n; j++) any |= (key == __ldg(args + op.args_off + j));
-            r = op.op == kOpIn ? (!isnull && any) : (isnull || !any);
-            break;
-          }
-          case kOpIsNull: r = isnull; break;
-          case kOpIsNotNull: r = !isnull; break;
-          case kOpTrue: r = true; break;
-          default: r = false; break;
-        }
-        stack = (stack << 1) | (r ? 1ull : 0ull);
-      } else {
-        const uint32_t n = op.n;
-        const uint64_t m = (n >= 64) ? ~0ull : ((1ull << n) - 1ull);
-        const uint64_t top = stack & m;
-        r = (n == 0) ? true : (op.kind == kWAnd ? top == m : top != 0);
-        stack = (n >= 64) ? 0ull : (stack >> n);
-        stack = (stack << 1) | (r ? 1ull : 0ull);
-      }
+    bool res = false;
+    if (row < n_rows) {
+      res = where_eval_row(prog, args, [&](uint32_t c, uint64_t &key, bool &isnull) {
+        const uint64_t raw = __ldg(cols.values[c] + row);
+        key = cols.is_f64[c] ? where_key_f64_bits(raw) : (raw ^ 0x8000000000000000ull);
+        isnull = (__ldg(cols.nulls[c] + (row >> 5)) >> (row & 31)) & 1u;
+      });
     }
-    const bool res = valid && (prog.n_ops == 0 || (stack & 1ull));
     const unsigned bits = __ballot_sync(0xFFFFFFFFu, res);
     if (lane == 0) {
       out_bits[w] = bits;

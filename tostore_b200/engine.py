@@ -224,6 +224,48 @@ class GpuVectorIndex:
         n = cnt.value
         return ids[:n], dist[:n], score[:n]
 
+    # -- nodeId -> primary key side table (role of `__nid2pk`) ------------------------
+    def set_primary_keys(self, pks, first_node_id: Optional[int] = None) -> None:
+        """pks: sequence of str (None / '' = tombstone mapping) for consecutive node ids."""
+        enc = [b"" if p is None else str(p).encode("utf-8") for p in pks]
+        offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+        blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+        if first_node_id is None:
+            first_node_id = self.first_node_id
+        N.check(self._lib.tsc_index_set_primary_keys(self.handle, int(first_node_id),
+                                                     blob.ctypes.data, offs.ctypes.data, len(enc)),
+                "tsc_index_set_primary_keys")
+
+    def get_primary_key(self, node_id: int) -> Optional[str]:
+        buf = (C.c_uint8 * 4096)()
+        n = C.c_uint32(0)
+        N.check(self._lib.tsc_index_get_primary_key(self.handle, int(node_id), buf, 4096,
+                                                    C.byref(n)), "tsc_index_get_primary_key")
+        return bytes(buf[: n.value]).decode("utf-8") if n.value else None
+
+    def vector_search_pk(self, values, k: int, threshold: Optional[float] = None,
+                         pk_capacity: int = 1 << 16):
+        """`vector_search` + result assembly inside the library: (pks, ids, dist, score);
+        results whose node has no primary-key mapping are dropped."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        ids = np.empty(k, dtype=np.int64)
+        dist = np.empty(k, dtype=np.float64)
+        score = np.empty(k, dtype=np.float64)
+        pkb = np.empty(pk_capacity, dtype=np.uint8)
+        offs = np.zeros(k + 1, dtype=np.uint64)
+        cnt = C.c_uint32(0)
+        thr = math.nan if threshold is None else float(threshold)
+        N.check(self._lib.tsc_vector_search_pk(self.handle, v.ctypes.data, v.size, k, thr,
+                                               ids.ctypes.data, dist.ctypes.data,
+                                               score.ctypes.data, pkb.ctypes.data, pk_capacity,
+                                               offs.ctypes.data, C.byref(cnt)),
+                "tsc_vector_search_pk")
+        n = cnt.value
+        raw = pkb.tobytes()
+        pks = [raw[int(offs[i]): int(offs[i + 1])].decode("utf-8") for i in range(n)]
+        return pks, ids[:n], dist[:n], score[:n]
+
     # -- sharding --------------------------------------------------------------------
     @staticmethod
     def comm_unique_id() -> bytes:

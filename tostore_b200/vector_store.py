@@ -15,7 +15,8 @@ What is *not* here: tables, B+Trees, WAL, transactions, schema migration. Rows
 become visible to search as soon as they are appended (the reference makes them
 visible at flush); nodeId = insertion order, exactly as
 `meta.nextNodeId++` (src/core/ngh_graph_engine.dart:321-322). The nodeId -> primary
-key B+Tree of the reference (`__nid2pk`) is a dense host-side list here.
+key B+Tree of the reference (`__nid2pk`) is a dense host-memory table inside the
+library (`tsc_index_set_primary_keys`, `tsc_vector_search_pk`).
 
 The Dart production binding is dart/tostore_cuda_bindings.dart; this module is
 the equivalent host layer in the one host language this image can run.
@@ -28,6 +29,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
+from . import where as _where
 from .engine import GpuVectorIndex
 
 
@@ -97,6 +99,8 @@ class _VectorIndex:
     engine: GpuVectorIndex
     nid2pk: List[Optional[str]] = field(default_factory=list)   # role of `__nid2pk`
     pk2nid: Dict[str, int] = field(default_factory=dict)        # role of `__pk2nid`
+    # numeric table fields mirrored column-wise on the GPU for WHERE: name -> (column id, type)
+    attributes: Dict[str, tuple] = field(default_factory=dict)
 
 
 class GpuVectorStore:
@@ -112,16 +116,26 @@ class GpuVectorStore:
 
     # -- schema -------------------------------------------------------------------------
     def createVectorIndex(self, tableName: str, fieldName: str, fieldConfig: VectorFieldConfig,
-                          indexConfig: Optional[VectorIndexConfig] = None) -> None:
+                          indexConfig: Optional[VectorIndexConfig] = None,
+                          attributeFields: Optional[Dict[str, str]] = None) -> None:
         """`TableSchema` vector field + `IndexSchema(type: IndexType.vector)`.
-        Unlike the reference (no validation) bad dims raise."""
+        Unlike the reference (no validation) bad dims raise.
+        attributeFields (new, additive): numeric fields of the table — name ->
+        'integer' | 'double' (DataType names, model/table_schema.dart) — kept column-wise
+        on the GPU so `vectorSearch(where=...)` can prefilter on them."""
         cfg = indexConfig or VectorIndexConfig()
         eng = GpuVectorIndex(fieldConfig.dimensions, int(cfg.distanceMetric),
                              capacity_rows=self._capacity, src_precision=1,
                              dev_dtype=int(self._dtype), device_id=self._device_id,
                              k_max=self._k_max, nq_max=64)
-        self._indexes.setdefault(tableName, []).append(
-            _VectorIndex(tableName, fieldName, fieldConfig, cfg, eng))
+        ix = _VectorIndex(tableName, fieldName, fieldConfig, cfg, eng)
+        for cid, (name, dtype) in enumerate((attributeFields or {}).items()):
+            if dtype not in ("integer", "double"):
+                raise ValueError(f"attribute field {name!r}: only integer / double fields have a GPU column")
+            t = _where.COL_I64 if dtype == "integer" else _where.COL_F64
+            eng.column_create(cid, t)
+            ix.attributes[name] = (cid, t)
+        self._indexes.setdefault(tableName, []).append(ix)
 
     def _find(self, tableName: str, fieldName: str) -> Optional[_VectorIndex]:
         for ix in self._indexes.get(tableName, ()):      # vector_index_manager.dart:484-499
@@ -158,7 +172,7 @@ class GpuVectorStore:
         (`prepareVectorBatchChunk`, compute/vector_batch_prepare_compute.dart:34-67)."""
         n_done = 0
         for ix in self._indexes.get(tableName, ()):
-            vecs, pks = [], []
+            vecs, pks, kept = [], [], []
             for rec in records:
                 val = rec.get(ix.fieldName)
                 if val is None:
@@ -168,11 +182,16 @@ class GpuVectorStore:
                     continue
                 vecs.append(self._to_float32(val, ix.field.dimensions))
                 pks.append(str(pk))
+                kept.append(rec)
             if not vecs:
                 continue
             rows = self._store_round_trip(np.stack(vecs), ix.field.precision)
             start = len(ix.nid2pk)                      # startNodeId = meta.nextNodeId
             ix.engine.append_rows(rows, first_node_id=start)
+            for name, (cid, t) in ix.attributes.items():
+                ix.engine.column_append(cid, [_where._convert(r[name], t) if r.get(name) is not None
+                                              else None for r in kept], first_node_id=start)
+            ix.engine.set_primary_keys(pks, first_node_id=start)     # `__nid2pk` deltas (:1276-1293)
             for j, pk in enumerate(pks):
                 ix.nid2pk.append(pk)
                 ix.pk2nid[pk] = start + j
@@ -195,6 +214,8 @@ class GpuVectorStore:
                     nids.append(nid)
             if nids:
                 ix.engine.set_deleted(nids, True)
+                for nid in nids:                                 # tombstone mapping, value [1]
+                    ix.engine.set_primary_keys([None], first_node_id=nid)
                 n = max(n, len(nids))
         return n
 
@@ -217,20 +238,27 @@ class GpuVectorStore:
     # -- ToStore.vectorSearch (tostore.dart:493-511) --------------------------------------
     def vectorSearch(self, tableName: str, *, fieldName: str, queryVector: VectorData,
                      topK: int = 10, efSearch: Optional[int] = None,
-                     distanceThreshold: Optional[float] = None) -> List[VectorSearchResult]:
+                     distanceThreshold: Optional[float] = None,
+                     where=None) -> List[VectorSearchResult]:
+        """`where` (new, additive): a `QueryCondition` / its map form over the index's
+        attribute fields; evaluated on the GPU into the prefilter bitmap before the scan.
+        `where=None` searches every live row (and clears a previous condition)."""
         ix = self._find(tableName, fieldName)
         if ix is None or not ix.nid2pk:                  # :485-504 -> const []
             return []
         _ = efSearch                                     # exact scan: no expansion factor
+        if where is not None:
+            cond = where.build() if hasattr(where, "build") else where
+            ix.engine.filter_where(_where.compile_condition(cond, ix.attributes))
+            ix.where_active = True
+        elif getattr(ix, "where_active", False):
+            ix.engine.set_filter(None)
+            ix.where_active = False
         values = queryVector.values if isinstance(queryVector, VectorData) else queryVector
-        ids, dist, score = ix.engine.vector_search(values, topK, distanceThreshold)
-        out = []
-        for nid, d, s in zip(ids.tolist(), dist.tolist(), score.tolist()):
-            pk = ix.nid2pk[nid] if 0 <= nid < len(ix.nid2pk) else None
-            if pk is None:                               # :578-579 (deleted / unmapped)
-                continue
-            out.append(VectorSearchResult(primaryKey=pk, distance=d, score=s))
-        return out                                       # already ascending (:587)
+        # query prep, search, nodeId -> PK (:553-588) and score all happen inside the library
+        pks, _ids, dist, score = ix.engine.vector_search_pk(values, topK, distanceThreshold)
+        return [VectorSearchResult(primaryKey=pk, distance=d, score=s)
+                for pk, d, s in zip(pks, dist.tolist(), score.tolist())]   # ascending (:587)
 
     def close(self) -> None:
         for lst in self._indexes.values():
