@@ -113,6 +113,8 @@ typedef _SearchPkN = Int32 Function(
 typedef _SearchPkD = int Function(
     int, Pointer<Double>, int, int, double, Pointer<Int64>, Pointer<Double>,
     Pointer<Double>, Pointer<Uint8>, int, Pointer<Uint64>, Pointer<Uint32>);
+typedef _LoadNghN = Int32 Function(Uint64, Pointer<Utf8>, Uint32, Pointer<Void>);
+typedef _LoadNghD = int Function(int, Pointer<Utf8>, int, Pointer<Void>);
 typedef _LastErrorN = Pointer<Utf8> Function();
 typedef _LastErrorD = Pointer<Utf8> Function();
 
@@ -433,6 +435,21 @@ class TostoreCuda {
       calloc.free(pkBytes);
       calloc.free(offs);
       calloc.free(count);
+    }
+  }
+  /// Cold start: stream `<indexDir>/ngh/{rawvec,graph}/dir_k/p<n>.ngh` into the GPU index
+  /// (`tsc_index_load_ngh`: reader thread + pinned double buffer inside the library;
+  /// pages are validated and decoded on the GPU). `indexDir` is the directory that holds
+  /// `ngh/meta.json` (core/path_manager.dart:317-324).
+  static bool loadNgh(int handle, String indexDir, {bool tombstones = true}) {
+    final lib = _open();
+    if (lib == null) return false;
+    final fn = lib.lookupFunction<_LoadNghN, _LoadNghD>('tsc_index_load_ngh');
+    final dir = indexDir.toNativeUtf8();
+    try {
+      return fn(handle, dir, tombstones ? 1 : 0, nullptr) == 0;
+    } finally {
+      calloc.free(dir);
     }
   }
 }

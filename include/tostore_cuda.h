@@ -132,6 +132,33 @@ int32_t tsc_index_append_pages(uint64_t handle, uint64_t first_logical_page,
 int32_t tsc_index_append_synthetic(uint64_t handle, uint64_t seed,
                                    uint64_t first_node_id, uint64_t n_rows);
 
+/* ---- cold start from an existing on-disk index ----
+ * index_dir is the directory that holds `ngh/meta.json`, `ngh/rawvec/dir_k/p<n>.ngh` and
+ * `ngh/graph/dir_k/p<n>.ngh` (core/path_manager.dart:317-324). The loader reads only the
+ * partition files that hold this shard's node ids [first_node_id, first_node_id +
+ * capacity_rows) ∩ [0, nextNodeId), on a reader thread that runs one 64 MiB chunk ahead of
+ * the GPU (pinned double buffer), and feeds them to tsc_index_append_pages /
+ * tsc_index_apply_graph_pages. dims and precision of the index on disk must equal the
+ * GPU index's dims / src_precision. */
+enum { TSC_LOAD_TOMBSTONES = 1 };     /* also read the graph pages' deleted flags */
+typedef struct tsc_ngh_info {
+  uint32_t struct_size;
+  uint32_t dims;                     /* meta.json "dimensions"                     */
+  uint8_t metric;                    /* TSC_METRIC_* ("distanceMetric", default cosine) */
+  uint8_t precision;                 /* TSC_SRC_*    ("precision", default float32)      */
+  uint16_t reserved;
+  uint32_t page_size;                /* "nghPageSize", default 16384               */
+  uint32_t max_degree;               /* "maxDegree", default 64                    */
+  uint32_t reserved2;
+  uint64_t next_node_id;             /* "nextNodeId": rows are node ids [0, next)  */
+  uint64_t max_partition_file_size;  /* "maxPartitionFileSize", default 16 MiB     */
+  uint64_t files_read, pages_read, bytes_read;   /* filled by tsc_index_load_ngh   */
+  double seconds;
+} tsc_ngh_info;
+int32_t tsc_ngh_read_meta(const char *index_dir, tsc_ngh_info *out);   /* host only */
+int32_t tsc_index_load_ngh(uint64_t handle, const char *index_dir, uint32_t flags,
+                           tsc_ngh_info *out /* optional */);
+
 /* ---- liveness ---- */
 int32_t tsc_index_set_deleted(uint64_t handle, const uint64_t *node_ids,
                               uint64_t n, uint8_t deleted);
@@ -279,6 +306,13 @@ int32_t tsc_selftest_where(const tsc_where_op *ops, uint32_t n_ops, const void *
                            const uint8_t *col_types, const uint64_t *col_values,
                            const uint8_t *col_is_null, uint64_t n_rows, uint8_t *out_match);
 
+/* self-test hook (no GPU): the directory walk / chunking / double-buffered reader of
+ * tsc_index_load_ngh with a host sink that records, per chunk, the first logical page, the
+ * page count and the CRC-32 of the chunk's bytes. category 0 = rawvec, 1 = graph. */
+int32_t tsc_selftest_ngh_walk(const char *index_dir, uint32_t category, uint64_t node_lo,
+                              uint64_t node_hi, uint32_t chunk_pages, uint64_t *out_first_page,
+                              uint64_t *out_n_pages, uint32_t *out_crc, uint32_t max_chunks,
+                              uint32_t *out_n_chunks);
 /* self-test hooks (no GPU): a host-only index object that carries only the primary-key
  * table (every compute entry point fails on it; release with tsc_index_destroy), and the
  * result-assembly step of tsc_vector_search_pk applied to caller-supplied hits

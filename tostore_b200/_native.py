@@ -25,6 +25,7 @@ EXPORTS = (
     "tsc_stats_get", "tsc_stats_reset", "tsc_index_device_rows", "tsc_selftest_crc32",
     "tsc_debug_gemm_keys",
     "tsc_index_column_create", "tsc_index_column_append", "tsc_index_filter_where",
+    "tsc_ngh_read_meta", "tsc_index_load_ngh", "tsc_selftest_ngh_walk",
     "tsc_selftest_where", "tsc_selftest_host_index", "tsc_selftest_pk_assemble",
     "tsc_index_set_primary_keys", "tsc_index_get_primary_key", "tsc_vector_search_pk",
 )
@@ -61,6 +62,17 @@ class Stats(C.Structure):
         ("last_path", C.c_uint32), ("reserved", C.c_uint32),
         ("hot_launches", C.c_uint64), ("hot_ms_total", C.c_double),
         ("hot_bytes_total", C.c_double), ("hot_flops_total", C.c_double),
+    ]
+
+
+class NghInfo(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("dims", C.c_uint32),
+        ("metric", C.c_uint8), ("precision", C.c_uint8), ("reserved", C.c_uint16),
+        ("page_size", C.c_uint32), ("max_degree", C.c_uint32), ("reserved2", C.c_uint32),
+        ("next_node_id", C.c_uint64), ("max_partition_file_size", C.c_uint64),
+        ("files_read", C.c_uint64), ("pages_read", C.c_uint64), ("bytes_read", C.c_uint64),
+        ("seconds", C.c_double),
     ]
 
 
@@ -109,6 +121,10 @@ def lib():
     L.tsc_index_column_create.argtypes = [u64, u32, C.c_uint8]
     L.tsc_index_column_append.argtypes = [u64, u32, u64, vp, vp, u64]
     L.tsc_index_filter_where.argtypes = [u64, vp, u32, vp, u32, C.POINTER(u64)]
+    L.tsc_ngh_read_meta.argtypes = [C.c_char_p, C.POINTER(NghInfo)]
+    L.tsc_index_load_ngh.argtypes = [u64, C.c_char_p, u32, C.POINTER(NghInfo)]
+    L.tsc_selftest_ngh_walk.argtypes = [C.c_char_p, u32, u64, u64, u32, vp, vp, vp, u32,
+                                        C.POINTER(u32)]
     L.tsc_selftest_where.argtypes = [vp, u32, vp, u32, u32, vp, vp, vp, vp, u64, vp]
     L.tsc_selftest_host_index.argtypes = [u64, u64, C.POINTER(u64)]
     L.tsc_selftest_pk_assemble.argtypes = [u64, u32, vp, vp, vp, vp, u64, vp, C.POINTER(u32)]

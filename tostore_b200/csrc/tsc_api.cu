@@ -692,15 +692,21 @@ int32_t tsc_index_apply_graph_pages(uint64_t handle, uint64_t first_logical_page
     int32_t rc = stage_and_check_pages(ix, pages + p0 * page_size, np, page_size, kPtGraph,
                                        first_logical_page + p0);
     if (rc != TSC_OK) return rc;
-    // slots per page come from the page itself (slotCount); all pages of one
-    // index share it (NghPageSizer.nodesPerGraphPage, ngh_page.dart:559-566)
-    uint16_t cnt = 0;
-    TSC_CUDA(cudaMemcpy(&cnt, ix->d_stage + kPageHeader, 2, cudaMemcpyDeviceToHost));
+    // slots per page = NghPageSizer.nodesPerGraphPage (ngh_page.dart:559-566), from the
+    // maxDegree the page itself records; a page's own slotCount may be smaller (last page)
+    uint16_t hdr[2] = {0, 0};   // [slotCount][maxDegree]
+    TSC_CUDA(cudaMemcpy(hdr, ix->d_stage + kPageHeader, 4, cudaMemcpyDeviceToHost));
+    const int64_t usable = (int64_t)page_size - 20 - 4 - 64;
+    const uint32_t per_page = usable > 0 ? (uint32_t)(usable / (2 + (int64_t)hdr[1] * 4)) : 0;
+    if (per_page == 0) {
+      set_error("apply_graph_pages: page size %u holds no slot of degree %u", page_size, hdr[1]);
+      return TSC_ERR_PAGE;
+    }
     uint32_t set_before = 0;
     TSC_CUDA(cudaMemsetAsync(ix->d_delta, 0, 4, ix->stream));
     graph_flags_kernel<<<(unsigned)(np < 2048 ? np : 2048), 128, 0, ix->stream>>>(
-        ix->d_stage, np, page_size, (first_logical_page + p0) * cnt, ix->desc.first_node_id,
-        ix->rows, ix->d_deleted, (uint32_t *)ix->d_delta);
+        ix->d_stage, np, page_size, per_page, (first_logical_page + p0) * per_page,
+        ix->desc.first_node_id, ix->rows, ix->d_deleted, (uint32_t *)ix->d_delta);
     TSC_CUDA(cudaGetLastError());
     ix->launches++;
     TSC_CUDA(cudaMemcpyAsync(&set_before, ix->d_delta, 4, cudaMemcpyDeviceToHost, ix->stream));

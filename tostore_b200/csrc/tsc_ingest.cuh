@@ -199,17 +199,20 @@ __global__ void page_decode_kernel(const uint8_t *pages, uint32_t page_size, uin
   }
 }
 
-// graph pages -> deleted bitmap. nodes_per_page slots per page; slot layout
-// [flags:u8][degree:u8][maxDegree x u32]; bit 0x01 = tombstone.
+// graph pages -> deleted bitmap. Page p of the call holds node ids starting at first_node +
+// p * per_page (per_page = NghPageSizer.nodesPerGraphPage, ngh_page.dart:559-566; a page
+// may be filled to fewer slots than that); slot layout [flags:u8][degree:u8][maxDegree x u32];
+// bit 0x01 = tombstone.
 __global__ void graph_flags_kernel(const uint8_t *pages, uint64_t n_pages, uint32_t page_size,
-                                   uint64_t first_node, uint64_t shard_first, uint64_t shard_rows,
-                                   uint32_t *deleted_bits, uint32_t *n_set) {
+                                   uint32_t per_page, uint64_t first_node, uint64_t shard_first,
+                                   uint64_t shard_rows, uint32_t *deleted_bits, uint32_t *n_set) {
   for (uint64_t pg = blockIdx.x; pg < n_pages; pg += gridDim.x) {
     const uint8_t *pay = pages + pg * page_size + kPageHeader;
     uint32_t cnt = ld_u16(pay), deg = ld_u16(pay + 2);
     uint32_t slot = 2 + deg * 4;
+    if (cnt > per_page) cnt = per_page;
     for (uint32_t s = threadIdx.x; s < cnt; s += blockDim.x) {
-      uint64_t node = first_node + pg * cnt + s;
+      uint64_t node = first_node + pg * per_page + s;
       if (node < shard_first || node >= shard_first + shard_rows) continue;
       uint64_t r = node - shard_first;
       uint32_t bit = 1u << (r & 31);

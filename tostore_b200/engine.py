@@ -88,6 +88,16 @@ class GpuVectorIndex:
                                                      int(n_rows)),
                 "tsc_index_append_synthetic")
 
+    def load_ngh(self, index_dir: str, tombstones: bool = True) -> N.NghInfo:
+        """Cold start from an on-disk ToStore NGH index directory (the one that holds
+        `ngh/meta.json`): the library's reader thread streams this shard's partition
+        files through pinned double buffers into append_pages / apply_graph_pages."""
+        info = N.NghInfo(struct_size=C.sizeof(N.NghInfo))
+        N.check(self._lib.tsc_index_load_ngh(self.handle, str(index_dir).encode("utf-8"),
+                                             1 if tombstones else 0, C.byref(info)),
+                "tsc_index_load_ngh")
+        return info
+
     # -- liveness ----------------------------------------------------------------
     def set_deleted(self, node_ids, deleted: bool = True) -> None:
         ids = np.ascontiguousarray(node_ids, dtype=np.uint64)

@@ -97,10 +97,32 @@ def iter_partition_pages(index_dir: str, category: str, meta: NghMeta, per_page:
             yield part * ppp, data
 
 
-def load_ngh_index(index_dir: str, make_index: Callable, load_tombstones: bool = True):
+def read_meta_native(index_dir: str) -> NghMeta:
+    """meta.json through the library's own parser (`tsc_ngh_read_meta`)."""
+    import ctypes as C
+
+    from . import _native as N
+    info = N.NghInfo(struct_size=C.sizeof(N.NghInfo))
+    N.check(N.lib().tsc_ngh_read_meta(str(index_dir).encode("utf-8"), C.byref(info)),
+            "tsc_ngh_read_meta")
+    return NghMeta(dimensions=info.dims, metric=info.metric, precision=info.precision,
+                   next_node_id=info.next_node_id, page_size=info.page_size,
+                   max_partition_file_size=info.max_partition_file_size,
+                   max_degree=info.max_degree)
+
+
+def load_ngh_index(index_dir: str, make_index: Callable, load_tombstones: bool = True,
+                   native: bool = True):
     """`make_index(meta)` must return a `GpuVectorIndex` whose dims / metric /
     src_precision match `meta` and whose capacity covers `meta.next_node_id` (or the
-    shard's share of it). Returns (index, meta)."""
+    shard's share of it). Returns (index, meta). native=True (default) uses the
+    library's pipelined loader (`tsc_index_load_ngh`: reader thread + pinned double
+    buffer); native=False walks the files from Python, one blocking call per file."""
+    if native:
+        meta = read_meta_native(index_dir)
+        ix = make_index(meta)
+        ix.load_ngh(index_dir, tombstones=load_tombstones)
+        return ix, meta
     meta = read_meta(index_dir)
     ix = make_index(meta)
     for first_page, data in iter_partition_pages(index_dir, "rawvec", meta,
