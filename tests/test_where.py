@@ -333,3 +333,53 @@ def test_store_vector_search_with_where():
         assert [r.primaryKey for r in res2] == [f"pk{i}" for i in oi2]      # where=None clears it
     finally:
         st.close()
+
+
+# ---- property test: random condition trees through the library's evaluator (host) ------------
+from hypothesis import HealthCheck, given, settings, strategies as st   # noqa: E402
+
+_SPECIAL_F = [0.0, -0.0, math.nan, math.inf, -math.inf, 1.5, -1.5, 2.0, 1e308, -1e-308]
+_ints = st.integers(-6, 6) | st.sampled_from([-(1 << 63), (1 << 63) - 1, 1 << 40])
+_floats = st.sampled_from(_SPECIAL_F) | st.floats(-4, 4, allow_nan=False).map(lambda x: round(x, 1))
+_operand = _ints | _floats
+
+
+def _leaf():
+    field = st.sampled_from(["age", "score", "year"])
+    simple = st.tuples(st.sampled_from(["=", "!=", "<>", ">", ">=", "<", "<="]), _operand | st.none())
+    between = st.tuples(st.just("BETWEEN"), st.fixed_dictionaries({"start": _operand, "end": _operand}))
+    inlist = st.tuples(st.sampled_from(["IN", "NOT IN"]), st.lists(_operand | st.none(), max_size=5))
+    isnull = st.tuples(st.sampled_from(["IS", "IS NOT"]), st.none())
+    opmap = st.lists(simple | between | inlist | isnull, min_size=0, max_size=3).map(dict)
+    value = opmap | _operand | st.none()
+    return st.dictionaries(field, value, min_size=1, max_size=2)
+
+
+_tree = st.recursive(_leaf(), lambda kids: st.fixed_dictionaries({"AND": st.lists(kids, max_size=3)})
+                     | st.fixed_dictionaries({"OR": st.lists(kids, max_size=3)}), max_leaves=6)
+
+
+def _ok_for_int_fields(cond):
+    """NaN / inf operands cannot be converted for an integer field (Dart's round() throws)."""
+    try:
+        wo.normalize_condition(cond, TYPES)
+        return True
+    except (ValueError, OverflowError):
+        return False
+
+
+@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.filter_too_much])
+@given(_tree, st.integers(0, 1000))
+def test_property_random_trees_library_equals_oracle(cond, seed):
+    if not _ok_for_int_fields(cond):
+        with pytest.raises((ValueError, OverflowError)):
+            W.compile_condition(cond, COLS)
+        return
+    cols = _columns(n=64, seed=seed)
+    n = len(cols["age"])
+    prog = W.compile_condition(cond, COLS)
+    if len(prog.ops) > W.MAX_OPS:
+        return
+    want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
+    assert _selftest(prog, cols, n) == want
+    assert _interpret(prog, cols, n) == want
