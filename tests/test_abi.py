@@ -31,9 +31,57 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     from tostore_b200 import _native as N
+    from tostore_b200 import where as W
     assert C.sizeof(N.IndexDesc) == 40          # 4+4+4(4xu8)+4+8+8+4+4
     assert C.sizeof(N.Stats) == 112
     assert N.IndexDesc.capacity_rows.offset == 16 and N.IndexDesc.k_max.offset == 32
+    assert C.sizeof(W.WhereOp) == 48 and W.WhereOp.i_lo.offset == 8 and W.WhereOp.args_offset.offset == 40
+    assert C.sizeof(N.NghInfo) == 72 and N.NghInfo.next_node_id.offset == 24
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (what dart:ffi / cgo / any
+    FFI generator consumes), struct sizes must equal the ctypes mirrors, and a C program
+    must link against the .so and get the no-GPU error path (no C++ runtime needed by the
+    caller)."""
+    import shutil
+    import subprocess
+    from tostore_b200 import _native as N
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "caller.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "tostore_cuda.h"
+_Static_assert(sizeof(tsc_index_desc) == 40, "tsc_index_desc");
+_Static_assert(sizeof(tsc_stats) == 112, "tsc_stats");
+_Static_assert(sizeof(tsc_where_op) == 48, "tsc_where_op");
+_Static_assert(sizeof(tsc_ngh_info) == 72, "tsc_ngh_info");
+int main(void) {
+  if (tsc_version() != TSC_ABI_VERSION) return 2;
+  tsc_index_desc d;
+  memset(&d, 0, sizeof d);
+  d.struct_size = sizeof d;
+  d.dims = 0;                              /* rejected before any CUDA call */
+  uint64_t h = 0;
+  int32_t rc = tsc_index_create(&d, &h);
+  printf("%d %s|%s\n", rc, tsc_status_name(rc), tsc_last_error());
+  uint8_t check[9] = {'1','2','3','4','5','6','7','8','9'};
+  printf("%08x\n", tsc_selftest_crc32(check, 9));
+  return rc == TSC_ERR_BAD_DIMS ? 0 : 3;
+}
+""")
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(N.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-ltostore_cuda",
+                           f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith("-3 TSC_ERR_BAD_DIMS|") and "dims" in lines[0]
+    assert lines[1] == "cbf43926"                 # CRC-32/IEEE check value
 
 
 def test_no_cpu_fallback_without_gpu():

@@ -383,3 +383,52 @@ def test_property_random_trees_library_equals_oracle(cond, seed):
     want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
     assert _selftest(prog, cols, n) == want
     assert _interpret(prog, cols, n) == want
+
+
+# ---- committed golden fixtures (tests/golden/golden_where.json) ------------------------------
+def _dec(v):
+    if isinstance(v, dict) and set(v) == {"f"}:
+        return float.fromhex(v["f"])
+    if isinstance(v, list):
+        return [_dec(x) for x in v]
+    if isinstance(v, dict):
+        return {k: _dec(x) for k, x in v.items()}
+    return v
+
+
+def _golden_where():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_where.json")) as f:
+        g = json.load(f)
+    cols = _dec(g["columns"])
+    cmap = {"price": (0, I64), "rating": (1, F64), "stock": (2, I64)}
+    return g, cols, cmap
+
+
+def test_golden_where_fixtures_pin_oracle_and_library():
+    g, cols, cmap = _golden_where()
+    for case in g["cases"]:
+        cond = _dec(case["cond"])
+        want = [c == "1" for c in case["match"]]
+        assert wo.evaluate_columns(cond, cols, g["types"], n_rows=g["rows"]) == want
+        assert _selftest(W.compile_condition(cond, cmap), cols, g["rows"], col_map=cmap) == want
+
+
+@pytest.mark.gpu
+def test_gpu_golden_where_fixtures():
+    import oracle
+    from tostore_b200 import GpuVectorIndex
+    g, cols, cmap = _golden_where()
+    n = g["rows"]
+    with GpuVectorIndex(16, 0, capacity_rows=n, k_max=16, nq_max=4) as ix:
+        ix.append_rows(oracle.synth_rows(5, 0, n, 16))
+        for name, (cid, t) in cmap.items():
+            ix.column_create(cid, t)
+            ix.column_append(cid, cols[name])
+        for case in g["cases"]:
+            cond = _dec(case["cond"])
+            assert ix.filter_where(W.compile_condition(cond, cmap)) == case["match"].count("1")
+            ids, _, cnt = ix.search(oracle.synth_rows(6, 0, 1, 16)[0], 16)
+            live = {i for i, c in enumerate(case["match"]) if c == "1"}
+            assert set(ids[0, : cnt[0]].tolist()) <= live and cnt[0] == min(16, len(live))
