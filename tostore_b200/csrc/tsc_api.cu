@@ -406,6 +406,13 @@ int32_t tsc_index_create(const tsc_index_desc *d, uint64_t *out_handle) {
     ok(dev_alloc(ix, &ix->d_norm2, (size_t)ix->capacity));
     ok(dev_alloc(ix, &ix->d_q16, (size_t)ix->nq_max * ix->qld));
     ok(dev_alloc(ix, &ix->d_progress, (size_t)4096));
+  } else if (const char *ev = getenv("TSC_GEMM_TF32")) {
+    // opt-in (experimental, not yet measured): batches over an fp32 column on the tensor
+    // cores as tf32 instead of looping the scan kernel 8 queries at a time
+    if (atoi(ev) == 1) {
+      ix->tf32 = true;
+      ok(dev_alloc(ix, &ix->d_norm2, (size_t)ix->capacity));
+    }
   }
   if (const char *ev = getenv("TSC_GEMM_MIN_NQ")) ix->gemm_min_nq = (uint32_t)atoi(ev);
   ok(dev_alloc(ix, &ix->d_cand, (size_t)ix->nq_max * ix->cand_lists * ix->kprime_max));

@@ -30,15 +30,17 @@ static int32_t load_encode() {
   return TSC_OK;
 }
 
-// 2-D map over a row-major [rows, ld] 16-bit matrix, box = [box_rows, 64], 128B swizzle
+// 2-D map over a row-major [rows, ld] matrix, box = [box_rows, 128 bytes of K], 128B swizzle
+// (64 elements of a 16-bit type, 32 of fp32)
 static int32_t make_map(CUtensorMap *m, int dtype, const void *ptr, uint64_t rows, uint32_t ld,
                         uint32_t row_bytes, uint32_t box_rows) {
   cuuint64_t dims[2] = {ld, rows};
   cuuint64_t strides[1] = {row_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)kGemmBK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)(dtype == kF32 ? kGemmBK / 2 : kGemmBK), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
-                                          : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                           : dtype == kF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                         2, const_cast<void *>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -51,15 +53,19 @@ static int32_t make_map(CUtensorMap *m, int dtype, const void *ptr, uint64_t row
 }
 
 bool gemm_supported(const Index *ix, uint32_t kprime) {
-  return ix->desc.dev_dtype != TSC_DEV_F32 && kprime <= (uint32_t)kGemmMaxKp && ix->d_norm2 &&
-         ix->d_q16;
+  if (kprime > (uint32_t)kGemmMaxKp || !ix->d_norm2) return false;
+  // fp32 columns: only with the opt-in tf32 tensor path (TSC_GEMM_TF32=1 at index creation)
+  return ix->desc.dev_dtype == TSC_DEV_F32 ? ix->tf32 : ix->d_q16 != nullptr;
 }
 
 int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_t st) {
   if (!ix->d_norm2 || n == 0) return TSC_OK;
   unsigned blocks = (unsigned)((n + 7) / 8 < (uint64_t)ix->sm_count * 16 ? (n + 7) / 8
                                                                        : ix->sm_count * 16);
-  if (ix->desc.dev_dtype == TSC_DEV_BF16)
+  if (ix->desc.dev_dtype == TSC_DEV_F32)
+    row_norms_kernel<kF32><<<blocks, 256, 0, st>>>(ix->d_rows, first_row, n, ix->ld,
+                                                   ix->row_bytes, ix->d_norm2);
+  else if (ix->desc.dev_dtype == TSC_DEV_BF16)
     row_norms_kernel<kBF16><<<blocks, 256, 0, st>>>(ix->d_rows, first_row, n, ix->ld,
                                                     ix->row_bytes, ix->d_norm2);
   else
@@ -71,9 +77,9 @@ int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_
 }
 
 // SS kernel for one CTA (CG = 1) or a CTA pair (CG = 2) per tile
-template <int CG, int KPR>
+template <int CG, int KPR, int KIND = 0>
 static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, float *dbg_keys,
-                         uint32_t *out_lists, cudaStream_t st) {
+                         uint32_t *out_lists, cudaStream_t st, const void *a_rows = nullptr) {
   const int dtype = ix->desc.dev_dtype;
   const uint32_t q_units = (p.q_tiles + CG - 1) / CG;
   uint32_t slices = (uint32_t)(ix->sm_count / CG) / q_units;
@@ -94,26 +100,30 @@ static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, 
     return TSC_ERR_UNSUPPORTED;
   }
   CUtensorMap map_q, map_b;
-  int32_t rc = make_map(&map_q, dtype, ix->d_q16, nq, ix->ld, ix->row_bytes, kGemmBM);
+  // A operand: queries in the storage type (16-bit copy, or the caller's fp32 rows for tf32)
+  int32_t rc = make_map(&map_q, dtype, KIND == 1 ? a_rows : (const void *)ix->d_q16, nq, ix->ld,
+                        ix->row_bytes, kGemmBM);
   if (rc != TSC_OK) return rc;
   rc = make_map(&map_b, dtype, ix->d_rows, ix->rows, ix->ld, ix->row_bytes, GemmGeom<CG>::kBRows);
   if (rc != TSC_OK) return rc;
 
-  static bool attr_done[64] = {false};   // per (CG, KPR) instantiation
+  // the tf32 variant has no EXP (profiling) instantiation: it falls back to the plain one
+  constexpr bool kHasExp = KIND == 0;
+  static bool attr_done[64] = {false};   // per (CG, KPR, KIND) instantiation
   if (!attr_done[ix->device & 63]) {
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG, false, KPR>,
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG, false, KPR, KIND>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true, CG, false, KPR>,
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<true, CG, false, KPR, KIND>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG, true, KPR>,
+    TSC_CUDA(cudaFuncSetAttribute(gemm_topk_kernel<false, CG, kHasExp, KPR, KIND>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
     attr_done[ix->device & 63] = true;
   }
   // diagnostics (never set in production): TSC_GEMM_EXP = experiment bit mask,
   // TSC_GEMM_PROF=1 prints the per-role wait / work cycle averages of this launch
   const char *prof_env = getenv("TSC_GEMM_PROF");
-  const bool prof = prof_env && atoi(prof_env) != 0 && ix->d_progress && !dbg_keys;
-  const bool exp_kernel = (p.exp_flags != 0 || prof) && !dbg_keys;
+  const bool prof = kHasExp && prof_env && atoi(prof_env) != 0 && ix->d_progress && !dbg_keys;
+  const bool exp_kernel = kHasExp && (p.exp_flags != 0 || prof) && !dbg_keys;
   if (prof) {
     TSC_CUDA(cudaMemsetAsync(ix->d_progress, 0, kProfSlots * 8, st));
     p.prof = reinterpret_cast<unsigned long long *>(ix->d_progress);
@@ -135,11 +145,14 @@ static int32_t launch_ss(Index *ix, GemmParams p, uint32_t nq, uint32_t kprime, 
   rc = hot_timer_begin(ix, st, &slot);
   if (rc != TSC_OK) return rc;
   if (dbg_keys)
-    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, CG, false, KPR>, map_q, map_b, p, idesc));
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<true, CG, false, KPR, KIND>, map_q, map_b, p,
+                                idesc));
   else if (exp_kernel)
-    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG, true, KPR>, map_q, map_b, p, idesc));
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG, kHasExp, KPR, KIND>, map_q, map_b,
+                                p, idesc));
   else
-    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG, false, KPR>, map_q, map_b, p, idesc));
+    TSC_CUDA(cudaLaunchKernelEx(&cfg, gemm_topk_kernel<false, CG, false, KPR, KIND>, map_q, map_b, p,
+                                idesc));
   ix->launches++;
   *out_lists = p.n_slices * 2;
   // algorithmic work: 2 * nq * N * d flops; corpus bytes read once
@@ -171,15 +184,19 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
   int32_t rc = load_encode();
   if (rc != TSC_OK) return rc;
   const int dtype = ix->desc.dev_dtype;
-  convert_queries_kernel<<<(nq * ix->qld + 255) / 256, 256, 0, st>>>(d_q, nq * ix->qld, ix->d_q16,
-                                                                     dtype);
-  TSC_CUDA(cudaGetLastError());
-  ix->launches++;
+  const bool tf32 = dtype == TSC_DEV_F32;
+  if (!tf32) {
+    convert_queries_kernel<<<(nq * ix->qld + 255) / 256, 256, 0, st>>>(d_q, nq * ix->qld, ix->d_q16,
+                                                                       dtype);
+    TSC_CUDA(cudaGetLastError());
+    ix->launches++;
+  }
 
   GemmParams p{};
   p.n_rows = ix->rows;
   p.nq = nq;
-  p.k_blocks = (ix->desc.dims + kGemmBK - 1) / kGemmBK;
+  const uint32_t bk = tf32 ? kGemmBK / 2 : kGemmBK;   // elements per 128-byte K block
+  p.k_blocks = (ix->desc.dims + bk - 1) / bk;
   p.q_tiles = (nq + kGemmBM - 1) / kGemmBM;
   p.n_tiles = (uint32_t)((ix->rows + kGemmBN - 1) / kGemmBN);
   uint32_t slices = (uint32_t)ix->sm_count / p.q_tiles;
@@ -200,7 +217,7 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
   const char *tsenv = getenv("TSC_GEMM_TS");
   // (measured slower than the SS kernel on B200 - 64-column tiles pay too many
   // accumulator hand-offs - so it is opt-in: TSC_GEMM_TS=1)
-  const bool use_ts = ix->desc.dims <= (uint32_t)kTsMaxDims && tsenv && atoi(tsenv) == 1;
+  const bool use_ts = !tf32 && ix->desc.dims <= (uint32_t)kTsMaxDims && tsenv && atoi(tsenv) == 1;
   if (use_ts) {
     p.k_blocks = (ix->desc.dims + kTsBK - 1) / kTsBK;
     p.n_tiles = (uint32_t)((ix->rows + kTsBN - 1) / kTsBN);
@@ -243,6 +260,13 @@ int32_t launch_gemm(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, u
   // CTA pairs (cta_group::2) whenever the query tiles pair up evenly; TSC_GEMM_2CTA=0/1 overrides
   bool pair = (p.q_tiles % 2) == 0;
   if (const char *ce = getenv("TSC_GEMM_2CTA")) pair = atoi(ce) != 0;
+  if (tf32) {   // fp32 storage, tf32 multiply: the queries are used as they are (fp32, padded)
+    if (kprime <= 20)
+      return pair ? launch_ss<2, 20, 1>(ix, p, nq, kprime, dbg_keys, out_lists, st, d_q)
+                  : launch_ss<1, 20, 1>(ix, p, nq, kprime, dbg_keys, out_lists, st, d_q);
+    return pair ? launch_ss<2, 32, 1>(ix, p, nq, kprime, dbg_keys, out_lists, st, d_q)
+                : launch_ss<1, 32, 1>(ix, p, nq, kprime, dbg_keys, out_lists, st, d_q);
+  }
   if (kprime <= 20)
     return pair ? launch_ss<2, 20>(ix, p, nq, kprime, dbg_keys, out_lists, st)
                 : launch_ss<1, 20>(ix, p, nq, kprime, dbg_keys, out_lists, st);

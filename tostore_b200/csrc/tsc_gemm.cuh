@@ -122,6 +122,16 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t a_desc, uint64
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with fp32 operands read as tf32 (10-bit mantissa, low 13 bits ignored): UMMA K = 8
+__device__ __forceinline__ void umma_ss_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // mbarrier arrives once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -159,9 +169,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major
+// kind::f16 / kind::tf32 instruction descriptor: fp32 accumulate, A/B both K-major
 __host__ __device__ inline uint32_t umma_idesc_f16(int dtype, int m, int n) {
-  uint32_t fmt = dtype == kBF16 ? 1u : 0u;  // F16 = 0, BF16 = 1
+  uint32_t fmt = dtype == kBF16 ? 1u : (dtype == kF32 ? 2u : 0u);  // F16 = 0, BF16 = 1, TF32 = 2
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
@@ -230,6 +240,15 @@ __device__ __forceinline__ void umma_ss2(uint32_t tmem_d, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_ss2_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive (once the MMAs issued so far have completed) on the barrier at this smem
 // offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit2(uint32_t bar) {
@@ -289,7 +308,10 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // KPR = capacity of the per-thread candidate list (registers): 20 or 32 >= kprime
 // (10 warps put 3 on one scheduler: 16,384 / 96 caps a thread at 168 registers, which is
 // why the epilogue reads its 128 columns in two batches of 64 instead of all at once.)
-template <bool DBG, int CG, bool EXP, int KPR>
+// KIND = 0: 16-bit storage (kind::f16, 64 elements per 128-byte K block);
+// KIND = 1: fp32 storage multiplied as tf32 (kind::tf32, 32 elements per K block; opt-in,
+// TSC_GEMM_TF32=1). The byte geometry of a stage is identical for both.
+template <bool DBG, int CG, bool EXP, int KPR, int KIND = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_b,
                  const GemmParams p, const uint32_t idesc) {
@@ -311,6 +333,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   const uint32_t qt = (unit % q_units) * CG + crank;          // this CTA's query tile
   const uint32_t slice = unit / q_units;
   const uint32_t xf = EXP ? p.exp_flags : 0u;
+  constexpr int kBKElems = KIND == 1 ? kGemmBK / 2 : kGemmBK;   // elements per 128-byte K block
   long long t_w0 = 0, t_w1 = 0, t_w2 = 0;   // EXP: cycle sums of this warp's role
   auto tick = [&]() -> long long { return EXP ? clock64() : 0ll; };
 
@@ -359,17 +382,17 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
             if (crank == 0) mbar_expect_tx(smem_u32(&full[s]), 2 * bytes);
             if (!skip_a)
-              tma_load_2d_2sm(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK),
+              tma_load_2d_2sm(a_dst, &map_q, bar, (int32_t)(kb * kBKElems),
                               (int32_t)(qt * kGemmBM), pol_q);
-            tma_load_2d_2sm(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK),
+            tma_load_2d_2sm(b_dst, &map_b, bar, (int32_t)(kb * kBKElems),
                             (int32_t)(ctl * kGemmBN + crank * GemmGeom<CG>::kBRows), pol_b);
           } else {
             const uint32_t bar = smem_u32(&full[s]);
             mbar_expect_tx(bar, bytes);
             if (!skip_a)
-              tma_load_2d(a_dst, &map_q, bar, (int32_t)(kb * kGemmBK), (int32_t)(qt * kGemmBM),
+              tma_load_2d(a_dst, &map_q, bar, (int32_t)(kb * kBKElems), (int32_t)(qt * kGemmBM),
                           pol_q);
-            tma_load_2d(b_dst, &map_b, bar, (int32_t)(kb * kGemmBK), (int32_t)(ctl * kGemmBN),
+            tma_load_2d(b_dst, &map_b, bar, (int32_t)(kb * kBKElems), (int32_t)(ctl * kGemmBN),
                         pol_b);
           }
         }
@@ -407,7 +430,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
             for (int k = 0; k < kGemmBK / kGemmUK; k++) {
               // +32 bytes per K step inside the 128-byte swizzle row (units of 16 B)
-              if (CG == 2)
+              if (KIND == 1 && CG == 2)
+                umma_ss2_tf32(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                              (kb | k) != 0);
+              else if (KIND == 1)
+                umma_ss_tf32(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
+                             (kb | k) != 0);
+              else if (CG == 2)
                 umma_ss2(d_tmem, desc_hi | (a_lo + k * 2), desc_hi | (b_lo + k * 2), idesc,
                          (kb | k) != 0);
               else

@@ -79,6 +79,7 @@ struct Index {
   int *d_progress = nullptr;       // lockstep counters of the tensor-core path
   uint16_t *d_q16 = nullptr;       // [nq_max, qld] queries in the storage dtype (GEMM path)
   uint32_t gemm_min_nq = 9;        // batches at least this large take the tensor-core path
+  bool tf32 = false;               // fp32 column with the opt-in tf32 tensor path (TSC_GEMM_TF32=1)
   uint64_t *d_cand = nullptr;      // [nq_max][cand_lists][kprime_max]
   uint64_t cand_lists = 0;
   int64_t *d_out_ids = nullptr, *h_out_ids = nullptr;
