@@ -31,6 +31,7 @@ struct ScanConfig {
   int stages = 0;      // S (0 = auto)
   int stage_target = 6144;  // bytes per stage aimed for when R is auto
   int inflight_target = 96 * 1024;  // bytes of bulk copies in flight per CTA when S is auto
+  bool sparse_pf = false;   // sparse scan with the prefetching block cursor (opt-in)
 };
 
 // numeric table field kept column-wise next to the embedding column (tsc_where.cuh)

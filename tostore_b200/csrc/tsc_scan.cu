@@ -19,6 +19,7 @@ int32_t scan_configure(Index *ix) {
   ix->scan.stages = env_int("TSC_SCAN_STAGES", 0);
   ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 6144);
   ix->scan.inflight_target = env_int("TSC_SCAN_INFLIGHT_BYTES", 96 * 1024);
+  ix->scan.sparse_pf = env_int("TSC_SCAN_SPARSE_PF", 0) == 1;   // experimental, see tsc_scan.cuh
   if (ix->scan.warps < 1 || ix->scan.warps > 16 || ix->scan.grid < 1) {
     set_error("bad TSC_SCAN_* override");
     return TSC_ERR_BAD_ARG;
@@ -97,10 +98,13 @@ static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cuda
 template <int METRIC, int DTYPE, int QB>
 static int32_t run_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
   static bool attr_done[64] = {false};
-  auto kern = scan_topk_sparse_kernel<METRIC, DTYPE, QB>;
+  auto kern = ix->scan.sparse_pf ? scan_topk_sparse_kernel<METRIC, DTYPE, QB, true>
+                                 : scan_topk_sparse_kernel<METRIC, DTYPE, QB, false>;
   if (!attr_done[ix->device & 63]) {
-    TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(scan_topk_sparse_kernel<METRIC, DTYPE, QB, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(scan_topk_sparse_kernel<METRIC, DTYPE, QB, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
     attr_done[ix->device & 63] = true;
   }
   int slot = 0;

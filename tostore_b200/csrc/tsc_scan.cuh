@@ -334,7 +334,15 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
 // whose bit is set, so dead rows cost no HBM bytes (rows are whole 16-byte-aligned
 // byte ranges; at d=384 fp32 a row is exactly twelve 128-byte lines). The ring is a
 // queue of S one-row stages; rows are consumed in issue (= increasing id) order.
-template <int METRIC, int DTYPE, int QB>
+//
+// PF = false: a warp takes single bitmap words (32 rows) round-robin and loads each word
+// when the previous one is exhausted — a dependent global load on the issue path.
+// PF = true (opt-in, TSC_SCAN_SPARSE_PF=1; written after the round's GPU budget was spent,
+// not yet measured): a warp takes BLOCKS of 32 consecutive words (1024 rows) round-robin;
+// lane l holds word l of the block (one coalesced 128-byte load), the next block is
+// prefetched while the current one is consumed, and all-zero words are skipped with a
+// ballot — no load latency on the issue path and cheap skipping at low selectivity.
+template <int METRIC, int DTYPE, int QB, bool PF = false>
 __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int E = Chunk<DTYPE>::kElems;
@@ -393,7 +401,47 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
       word += GW;
     }
   };
-  load_word();
+  // PF: block cursor. `cur` / `nxt` = this lane's word of the current / next block,
+  // `nz` = lanes of the current block whose word is non-zero and not yet consumed.
+  const uint64_t n_blocks = (n_words + 31) / 32;
+  uint64_t blk = gw;
+  uint32_t cur = 0, nxt = 0;
+  unsigned nz = 0;
+  auto load_block = [&](uint64_t b) -> uint32_t {
+    const uint64_t w = b * 32 + (uint64_t)lane;
+    uint32_t v = 0;
+    if (b < n_blocks && w < n_words) {
+      v = p.live_mask[w];
+      const uint64_t base_row = w * 32;
+      if (base_row + 32 > p.n_rows) v &= (uint32_t)((1ull << (p.n_rows - base_row)) - 1ull);
+    }
+    return v;
+  };
+  auto next_word = [&]() {   // warp-uniform: advance to the next non-zero word of this warp
+    bits = 0;
+    for (;;) {
+      if (nz) {
+        const int l = __ffs(nz) - 1;
+        nz &= nz - 1;
+        bits = __shfl_sync(0xFFFFFFFFu, cur, l);
+        word = blk * 32 + (uint64_t)l;
+        return;
+      }
+      blk += GW;
+      if (blk >= n_blocks) return;
+      cur = nxt;
+      nxt = load_block(blk + GW);
+      nz = __ballot_sync(0xFFFFFFFFu, cur != 0);
+    }
+  };
+  if (PF) {
+    cur = load_block(blk);
+    nxt = load_block(blk + GW);
+    nz = __ballot_sync(0xFFFFFFFFu, cur != 0);
+    if (blk < n_blocks) next_word();
+  } else {
+    load_word();
+  }
   uint32_t head = 0, tail = 0, inflight = 0, hpar = 0;
   // row ids of the stages in flight (uniform per warp): kept in registers of lane s
   uint32_t my_row = kInvalidRow;
@@ -413,8 +461,12 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
       if (++tail == S) tail = 0;
       inflight++;
       if (!bits) {
-        word += GW;
-        load_word();
+        if (PF) {
+          next_word();
+        } else {
+          word += GW;
+          load_word();
+        }
       }
     }
     if (inflight == 0) break;
