@@ -20,13 +20,43 @@ except Exception:
     pass
 
 
-def run(name, n, d, metric, dt, nq, k, reps, mask_frac=None, warm=3):
+def run(name, n, d, metric, dt, nq, k, reps, mask_frac=None, warm=3, env=None, where=False):
+    """env: library switches read at index creation (e.g. TSC_GEMM_TF32, TSC_SCAN_SPARSE_PF);
+    where: produce the mask on the GPU from two attribute columns (tsc_index_filter_where)
+    instead of uploading a bitmap, and time that call."""
+    for key, val in (env or {}).items():
+        os.environ[key] = val
+    try:
+        _run(name, n, d, metric, dt, nq, k, reps, mask_frac, warm, where)
+    finally:
+        for key in (env or {}):
+            os.environ.pop(key, None)
+
+
+def _run(name, n, d, metric, dt, nq, k, reps, mask_frac, warm, where):
     Q = oracle.synth_rows(99, 0, nq * (reps + warm), d).reshape(reps + warm, nq, d)
     if metric == 2:
         Q = np.stack([np.stack([onp.normalize_f32(q) for q in b]) for b in Q])
     with GpuVectorIndex(d, metric, capacity_rows=n, dev_dtype=dt, k_max=max(k, 16), nq_max=max(nq, 8)) as ix:
         ix.append_synthetic(7, n)
-        if mask_frac is not None:
+        where_ms = None
+        if mask_frac is not None and where:
+            from tostore_b200 import where as W
+            rng = np.random.default_rng(9)
+            ix.column_create(0, W.COL_I64)
+            ix.column_create(1, W.COL_F64)
+            ix.column_append(0, rng.integers(0, 1000, n))
+            ix.column_append(1, rng.random(n))
+            # price < 1000 * sqrt(frac) AND rating < sqrt(frac)  ->  selectivity ~ frac
+            cut = mask_frac ** 0.5
+            prog = W.compile_condition({"AND": [{"price": {"<": int(1000 * cut)}}, {"rating": {"<": cut}}]},
+                                       {"price": (0, W.COL_I64), "rating": (1, W.COL_F64)})
+            ix.filter_where(prog)
+            t0 = time.perf_counter()
+            for _ in range(20):
+                matched = ix.filter_where(prog)
+            where_ms = (time.perf_counter() - t0) / 20 * 1e3
+        elif mask_frac is not None:
             ix.set_filter(np.random.default_rng(9).random(n) < mask_frac)
         for i in range(warm):
             ix.search(Q[i], k)
@@ -52,6 +82,10 @@ def run(name, n, d, metric, dt, nq, k, reps, mask_frac=None, warm=3):
                        tensor_frac_of_measured_sustained=tf / PEAKS["bf16_tflops_sustained"])
         if mask_frac is not None:
             out["filtered_bytes_gbs"] = out["hbm_gbs"] * mask_frac
+        if where_ms is not None:
+            # two 8-byte columns read + one bit per row written (tsc_where.cuh)
+            out.update(where_ms_incl_sync=where_ms, where_matched=int(matched),
+                       where_gbs=n * 16.125 / where_ms / 1e6)
         print(json.dumps(out), flush=True)
 
 
@@ -66,9 +100,23 @@ if "c3" in which:
     run("c3 batch-1024 cosine 10M x 768 bf16 k=10", 10_000_000, 768, 2, 1, 1024, 10, 10)
 if "c3s" in which:
     run("c3s single-query cosine 10M x 768 bf16 k=10 (scan)", 10_000_000, 768, 2, 1, 1, 10, 20)
+if "c2t" in which:      # experimental: fp32 column, batch on the tensor cores as tf32
+    run("c2t batch-1024 L2 10M x 768 fp32 k=10 (tf32 tensor path, TSC_GEMM_TF32=1)", 10_000_000, 768, 0, 0,
+        1024, 10, 5, env={"TSC_GEMM_TF32": "1"})
+if "c2b1024" in which:  # what c2t replaces: the scan kernel looped 8 queries per pass
+    run("c2b1024 batch-1024 L2 10M x 768 fp32 k=10 (scan, 128 passes)", 10_000_000, 768, 0, 0, 1024, 10, 2, warm=1)
 if "c4" in which:
     run("c4 shard: IP 12.5M x 1536 fp16 k=100 (1 of 8 GPUs)", 12_500_000, 1536, 1, 2, 1, 100, 20)
 if "c5" in which:
     run("c5 shard: L2 12.5M x 384 fp32 k=10, 10% WHERE mask (1 of 4 GPUs)", 12_500_000, 384, 0, 0, 1, 10, 20,
         mask_frac=0.10)
     run("c5u shard unfiltered: L2 12.5M x 384 fp32 k=10", 12_500_000, 384, 0, 0, 1, 10, 20)
+if "c5pf" in which:     # experimental: prefetching block cursor in the sparse scan
+    run("c5pf shard: L2 12.5M x 384 fp32 k=10, 10% mask, TSC_SCAN_SPARSE_PF=1", 12_500_000, 384, 0, 0, 1, 10, 20,
+        mask_frac=0.10, env={"TSC_SCAN_SPARSE_PF": "1"})
+    run("c5pf1 shard: 1% mask, TSC_SCAN_SPARSE_PF=1", 12_500_000, 384, 0, 0, 1, 10, 20,
+        mask_frac=0.01, env={"TSC_SCAN_SPARSE_PF": "1"})
+    run("c5s1 shard: 1% mask, default cursor", 12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.01)
+if "c5w" in which:      # mask produced on the GPU by the WHERE kernel from two attribute columns
+    run("c5w shard: L2 12.5M x 384 fp32 k=10, WHERE price<316 AND rating<0.316 (~10%) evaluated on the GPU",
+        12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.10, where=True)

@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of the next round: everything written after round 1 ran out of GPU budget.
+# 1 GPU, a few minutes. Keep --timeout small; never wrap multi-minute CPU work in a
+# multi-GPU call (round 1 lost 130 GPU-minutes that way).
+set +e
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+L=gpurun_out/r2_first.log
+nvidia-smi -L | tee $L
+which dart flutter 2>&1 | tee -a $L      # a Dart SDK on the box would let the real reference run
+echo "== pytest gpu (default)" | tee -a $L
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee -a $L
+echo "== pytest gpu (experimental paths)" | tee -a $L
+TSC_TEST_TF32=1 TSC_TEST_SPARSE_PF=1 timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -m gpu -q -k "tf32 or sparse" 2>&1 | tail -12 | tee -a $L
+echo "== bench" | tee -a $L
+timeout 600 python bench.py 2>gpurun_out/r2_bench.err | tee gpurun_out/r2_bench.json | tee -a $L
+echo "== configs (new paths)" | tee -a $L
+timeout 900 python tools/bench_configs.py c5 c5pf c5w c2t 2>&1 | tee gpurun_out/r2_configs.jsonl | tee -a $L
+echo "== ncu where kernel" | tee -a $L
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:where_eval -c 3 python tools/bench_configs.py c5w 2>&1 | grep -E "where_eval|gpu__time|dram__" | tee -a $L
