@@ -334,6 +334,9 @@ def run_b200(args):
                          "traffic_source": traffic_src,
                          "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)" if which == "measured"
                          else "fallback 6650 GB/s (B200_PROFILING.md)",
+                         "peak_note": "MEASURED_PEAKS hbm_gbs is a torch copy (read + write) figure; a "
+                                      "read-only stream pays no write turnarounds, so frac can exceed 1 "
+                                      "(DESIGN.md K1: 90 % of the 8.18 TB/s ncu reports as DRAM peak)",
                          "kernel": "scan_topk_kernel<L2,f32,QB=1>",
                          "kernel_ms": hot_ms, "algorithmic_bytes_per_launch": hot_bytes,
                          "kernel_share_of_step": hot_ms / (total_ms / steps) if total_ms else None},
