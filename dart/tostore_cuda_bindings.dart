@@ -445,7 +445,7 @@ class TostoreCuda {
     final lib = _open();
     if (lib == null) return false;
     final fn = lib.lookupFunction<_LoadNghN, _LoadNghD>('tsc_index_load_ngh');
-    final dir = indexDir.toNativeUtf8();
+    final dir = indexDir.toNativeUtf8(allocator: calloc);
     try {
       return fn(handle, dir, tombstones ? 1 : 0, nullptr) == 0;
     } finally {
