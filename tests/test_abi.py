@@ -136,3 +136,23 @@ def test_product_path_never_touches_the_oracle():
                                  if not l.lstrip().startswith(("#", "//", "*", "/*", '"""')))
                 assert not re.search(r"^\s*(import|from)\s+oracle", code, flags=re.M), f
                 assert "liboracle" not in code and "tso_" not in code.replace("tso_synth_value", ""), f
+
+
+def test_c_example_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """examples/minimal.c (the whole C ABI end to end) builds as C99 against the header and
+    the .so; on a host without a GPU it reports TSC_ERR_CUDA instead of computing anything."""
+    import shutil
+    import subprocess
+    import torch
+    from tostore_b200 import _native as N
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = tmp_path / "minimal"
+    libdir = os.path.dirname(N.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "minimal.c"), "-o", str(exe), "-L", libdir,
+                           "-ltostore_cuda", f"-Wl,-rpath,{libdir}", "-lm"])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the example would run for real (see tools/gpu_r2_first.sh)")
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 1 and "TSC_ERR_CUDA" in out.stderr
