@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default=os.environ.get("TSC_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
+                    help="N>1: ncclAllGather + merge (default, measured) or the experimental "
+                         "one-kernel exchange over NVLink peer memory")
     return ap.parse_args()
 
 
@@ -210,7 +213,9 @@ def run_b200(args):
     ix = GpuVectorIndex(d, METRIC_L2, capacity_rows=max(hi - lo, 1), device_id=local,
                         first_node_id=lo, k_max=16, nq_max=8)
     ix.append_synthetic(SEED, hi - lo, first_node_id=lo)
-    if world > 1:
+    if world > 1 and args.exchange == "p2p":
+        ix.comm_init_p2p(dist, world, rank)
+    elif world > 1:
         uid = [GpuVectorIndex.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ix.comm_init(uid[0], world, rank)
@@ -325,7 +330,10 @@ def run_b200(args):
             "config": {"workload": f"single-query L2, N={n} d={d} fp32, k={k} on {world}xB200 "
                                    "(BASELINE config 2: HBM-bound scan + top-k + exact fp64 re-rank)",
                        "rows_per_gpu": hi - lo, "sharding": "row-range" if world > 1 else "none",
-                       "exchange": "ncclAllGather of per-shard top-k (in-library)" if world > 1 else "none",
+                       "exchange": ("none" if world == 1 else
+                                    "one-kernel push over NVLink peer memory (experimental)"
+                                    if args.exchange == "p2p" else
+                                    "ncclAllGather of per-shard top-k (in-library)"),
                        "l2_flush": "inputs larger than L2 (each pass streams the whole shard; "
                                    f"{(hi - lo) * d * 4 / 1e9:.2f} GB per GPU vs 126 MB L2)",
                        "queries": "distinct synthetic query per step"},

@@ -282,6 +282,15 @@ int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
                            int64_t *d_out_ids, double *d_out_dist,
                            uint32_t *d_out_counts, void *cuda_stream);
 
+/* Experimental alternative to tsc_comm_init (not yet measured): the
+ * exchange + merge as ONE kernel over NVLink peer memory — every rank pushes its k pairs
+ * straight into the peers' receive buffers and spins on release flags — instead of
+ * ncclAllGather + merge. One process per GPU. export returns this rank's 64-byte CUDA IPC
+ * handle; the caller all-gathers the n_ranks handles (any host transport) and hands the
+ * [n_ranks][64] array to import; afterwards tsc_search_sharded takes this path. */
+int32_t tsc_comm_p2p_export(uint64_t handle, int32_t n_ranks, int32_t rank, uint8_t *out_ipc64);
+int32_t tsc_comm_p2p_import(uint64_t handle, const uint8_t *all_ipc);
+
 /* ---- observability ---- */
 int32_t tsc_stats_get(uint64_t handle, tsc_stats *out);
 int32_t tsc_stats_reset(uint64_t handle);        /* zero the hot_* accumulators  */

@@ -18,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, exchange="nccl"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -31,9 +31,12 @@ def _worker(rank, world, port, ret):
         lo, hi = shard_rows(n, world, rank)
         ix = GpuVectorIndex(d, 2, capacity_rows=hi - lo, device_id=rank, first_node_id=lo, k_max=16, nq_max=8)
         ix.append_synthetic(21, hi - lo, first_node_id=lo)
-        uid = [GpuVectorIndex.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ix.comm_init(uid[0], world, rank)
+        if exchange == "p2p":
+            ix.comm_init_p2p(dist, world, rank)
+        else:
+            uid = [GpuVectorIndex.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ix.comm_init(uid[0], world, rank)
         from oracle import oracle_np as onp
         Q = np.stack([onp.normalize_f32(q) for q in oracle.synth_rows(22, 0, nq, d)])
         dq = torch.from_numpy(Q).cuda()
@@ -52,7 +55,11 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_sharded_search_nccl_all_gather():
+# exchange="p2p": the one-kernel exchange over NVLink peer memory (tsc_exchange.cuh), written
+# without a GPU at hand — runs only with TSC_TEST_P2P=1 until verified on a multi-GPU box
+@pytest.mark.parametrize("exchange", ["nccl", pytest.param("p2p", marks=pytest.mark.skipif(
+    os.environ.get("TSC_TEST_P2P") != "1", reason="experimental: set TSC_TEST_P2P=1"))])
+def test_sharded_search_nccl_all_gather(exchange):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -61,7 +68,7 @@ def test_sharded_search_nccl_all_gather():
     world, port = min(torch.cuda.device_count(), 8), _free_port()   # 2, 4 or 8 shards
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, ret, exchange), nprocs=world, join=True)
         n, d, k, nq = 200_000, 256, 10, 6
         rows = oracle.synth_rows(21, 0, n, d)
         Q = np.stack([onp.normalize_f32(q) for q in oracle.synth_rows(22, 0, nq, d)])

@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "p2p"])
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -70,7 +71,9 @@ def main():
         rng = np.random.default_rng(SEED + 2)
         mask_all = rng.random(n_total) < mask_frac
         ix.set_filter(mask_all[lo:lo + per])
-    if world > 1:
+    if world > 1 and args.exchange == "p2p":
+        ix.comm_init_p2p(dist, world, rank)
+    elif world > 1:
         uid = [GpuVectorIndex.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ix.comm_init(uid[0], world, rank)
@@ -145,7 +148,7 @@ def main():
             peak = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
         except Exception:
             pass
-        out = {"config": args.config, "gpus": world, "gpus_named_by_baseline": named,
+        out = {"config": args.config, "gpus": world, "exchange": args.exchange, "gpus_named_by_baseline": named,
                "rows_total": n_total, "rows_per_gpu": per, "dims": d, "metric": metric, "dev_dtype": dt,
                "k": k, "mask_frac": mask_frac, "steps": args.steps, "ms_per_query": step_ms,
                "qps": 1e3 / step_ms, "scan_kernel_ms_max_over_ranks": hot_ms,

@@ -22,6 +22,7 @@ EXPORTS = (
     "tsc_search", "tsc_search_submit", "tsc_search_poll", "tsc_search_wait",
     "tsc_search_device", "tsc_vector_search", "tsc_merge_shards",
     "tsc_comm_unique_id", "tsc_comm_init", "tsc_search_sharded",
+    "tsc_comm_p2p_export", "tsc_comm_p2p_import",
     "tsc_stats_get", "tsc_stats_reset", "tsc_index_device_rows", "tsc_selftest_crc32",
     "tsc_debug_gemm_keys",
     "tsc_index_column_create", "tsc_index_column_append", "tsc_index_filter_where",
@@ -113,6 +114,8 @@ def lib():
     L.tsc_merge_shards.argtypes = [u64, vp, vp, u32, u32, u32, vp, vp, vp, vp]
     L.tsc_comm_unique_id.argtypes = [vp]
     L.tsc_comm_init.argtypes = [u64, vp, i32, i32]
+    L.tsc_comm_p2p_export.argtypes = [u64, i32, i32, vp]
+    L.tsc_comm_p2p_import.argtypes = [u64, vp]
     L.tsc_search_sharded.argtypes = [u64, vp, u32, u32, C.c_double, vp, vp, vp, vp]
     L.tsc_stats_get.argtypes = [u64, C.POINTER(Stats)]
     L.tsc_stats_reset.argtypes = [u64]

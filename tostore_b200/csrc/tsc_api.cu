@@ -95,6 +95,10 @@ static void free_index(Index *ix) {
   cudaFree(ix->d_page_status);
   cudaFree(ix->d_gather_send);
   cudaFree(ix->d_gather_recv);
+  for (int r = 0; r < ix->n_ranks && r < 8; r++)
+    if (ix->x_peer[r] && ix->x_peer[r] != ix->d_xbuf) cudaIpcCloseMemHandle(ix->x_peer[r]);
+  cudaFree(ix->d_xbuf);
+  if (ix->h_xstatus) cudaFreeHost(ix->h_xstatus);
   cudaFree(ix->d_where_args);
   for (auto &c : ix->columns) {
     cudaFree(c.d_values);
@@ -982,11 +986,11 @@ int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
                            uint32_t *d_out_counts, void *cuda_stream) {
   Index *ix = lookup(handle);
   if (!ix) return TSC_ERR_BAD_HANDLE;
-  if (!ix->nccl_comm) {
-    set_error("search_sharded: tsc_comm_init has not been called");
+  if (!ix->nccl_comm && !ix->p2p_ready) {
+    set_error("search_sharded: neither tsc_comm_init nor tsc_comm_p2p_import has been called");
     return TSC_ERR_NCCL;
   }
-  // per-shard exact top-k into the send block [ids | dist], then one all-gather
+  // per-shard exact top-k into the send block [ids | dist], then one exchange step
   const size_t nk = (size_t)nq * k;
   int64_t *s_ids = (int64_t *)ix->d_gather_send;
   double *s_dist = (double *)(ix->d_gather_send + nk * 8);
@@ -995,11 +999,88 @@ int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
   if (rc != TSC_OK) return rc;
   std::lock_guard<std::mutex> lk(ix->mu);
   cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : ix->stream;
+  if (ix->p2p_ready)   // opt-in: one kernel over NVLink peer memory (tsc_exchange.cuh)
+    return launch_exchange(ix, s_ids, s_dist, nq, k, d_out_ids, d_out_dist, d_out_counts, st);
   TSC_NCCL(g_nccl.AllGather(ix->d_gather_send, ix->d_gather_recv, nk * 16, /*ncclUint8*/ 1,
                             ix->nccl_comm, st));
   return launch_merge(ix, (const int64_t *)ix->d_gather_recv,
                       (const double *)(ix->d_gather_recv + nk * 8), nk * 2, (uint32_t)ix->n_ranks,
                       nq, k, d_out_ids, d_out_dist, d_out_counts, st);
+}
+
+// ---- opt-in P2P exchange setup (experimental; see tsc_exchange.cuh) --------------------------
+// export: allocate this rank's receive buffer and return its CUDA IPC handle (64 bytes);
+// the caller all-gathers the handles of all ranks (any host transport) and passes them to
+// import, which maps every peer's buffer. One process per GPU (IPC handles cannot be opened
+// by the process that made them).
+int32_t tsc_comm_p2p_export(uint64_t handle, int32_t n_ranks, int32_t rank, uint8_t *out_ipc64) {
+  Index *ix = lookup(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  if (!out_ipc64 || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks) {
+    set_error("comm_p2p_export: bad argument (1 <= n_ranks <= 8)");
+    return TSC_ERR_BAD_ARG;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (ix->d_xbuf) {
+    set_error("comm_p2p_export: already exported");
+    return TSC_ERR_BAD_ARG;
+  }
+  TSC_CUDA(cudaSetDevice(ix->device));
+  const uint64_t slot = (uint64_t)ix->nq_max * ix->k_max * 16ull;
+  const uint64_t bytes = ((2ull * n_ranks * slot + 127ull) & ~127ull) + 2ull * n_ranks * ix->nq_max * 4ull;
+  if (bytes > (256ull << 20)) {
+    set_error("comm_p2p_export: nq_max * k_max too large for the peer-memory exchange (%llu MB)",
+              (unsigned long long)(bytes >> 20));
+    return TSC_ERR_UNSUPPORTED;
+  }
+  TSC_CUDA(cudaMalloc((void **)&ix->d_xbuf, bytes));
+  TSC_CUDA(cudaMemset(ix->d_xbuf, 0, bytes));          // flags = 0, epochs start at 1
+  TSC_CUDA(cudaHostAlloc((void **)&ix->h_xstatus, 4, cudaHostAllocMapped));
+  *ix->h_xstatus = 0;
+  TSC_CUDA(cudaHostGetDevicePointer((void **)&ix->d_xstatus, ix->h_xstatus, 0));
+  if (!ix->d_gather_send) {
+    size_t part = (size_t)ix->nq_max * ix->k_max * 16;
+    TSC_CUDA(dev_alloc(ix, &ix->d_gather_send, part));
+  }
+  ix->xbuf_bytes = bytes;
+  ix->xslot_bytes = slot;
+  ix->device_bytes += bytes;
+  ix->n_ranks = n_ranks;
+  ix->rank = rank;
+  cudaIpcMemHandle_t hnd;
+  TSC_CUDA(cudaIpcGetMemHandle(&hnd, ix->d_xbuf));
+  memcpy(out_ipc64, &hnd, 64);
+  return TSC_OK;
+}
+
+int32_t tsc_comm_p2p_import(uint64_t handle, const uint8_t *all_ipc) {
+  Index *ix = lookup(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (!all_ipc || !ix->d_xbuf) {
+    set_error("comm_p2p_import: NULL handles or tsc_comm_p2p_export not called");
+    return TSC_ERR_BAD_ARG;
+  }
+  TSC_CUDA(cudaSetDevice(ix->device));
+  for (int r = 0; r < ix->n_ranks; r++) {
+    if (r == ix->rank) {
+      ix->x_peer[r] = ix->d_xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, all_ipc + (size_t)r * 64, 64);
+    void *ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("comm_p2p_import: cannot map rank %d's buffer: %s", r, cudaGetErrorString(e));
+      cudaGetLastError();
+      return TSC_ERR_CUDA;
+    }
+    ix->x_peer[r] = (uint8_t *)ptr;
+  }
+  ix->p2p_ready = true;
+  return TSC_OK;
 }
 
 // Test hook: raw fp32 ranking keys of the tensor-core path for every (query, row),

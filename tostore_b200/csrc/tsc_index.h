@@ -108,6 +108,14 @@ struct Index {
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
   uint8_t *d_gather_send = nullptr, *d_gather_recv = nullptr;
+  // opt-in P2P exchange (tsc_exchange.cuh): receive buffer exported to the peers over CUDA IPC
+  uint8_t *d_xbuf = nullptr;
+  uint64_t xbuf_bytes = 0, xslot_bytes = 0;
+  uint8_t *x_peer[8] = {};          // receive buffers of all ranks (own entry = d_xbuf)
+  bool p2p_ready = false;
+  uint32_t xepoch = 0;
+  uint32_t *h_xstatus = nullptr;    // mapped host word, set by the kernel on timeout
+  uint32_t *d_xstatus = nullptr;    // device alias of h_xstatus
 
   // dominant-kernel timing: ring of event pairs, resolved lazily
   static constexpr int kTimers = 128;
@@ -137,6 +145,9 @@ int32_t launch_select(Index *ix, const float *d_q, uint32_t nq, uint32_t k, uint
 int32_t launch_merge(Index *ix, const int64_t *d_part_ids, const double *d_part_dist,
                      uint64_t part_stride, uint32_t n_parts, uint32_t nq, uint32_t k,
                      int64_t *d_ids, double *d_dist, uint32_t *d_counts, cudaStream_t st);
+int32_t launch_exchange(Index *ix, const int64_t *d_src_ids, const double *d_src_dist, uint32_t nq,
+                        uint32_t k, int64_t *d_ids, double *d_dist, uint32_t *d_counts,
+                        cudaStream_t st);
 int32_t scan_configure(Index *ix);
 bool gemm_supported(const Index *ix, uint32_t kprime);
 int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_t st);

@@ -1,4 +1,7 @@
 // tsc_select.cu — host launchers for K5 (tsc_select.cuh).
+#include <stdlib.h>
+
+#include "tsc_exchange.cuh"
 #include "tsc_index.h"
 #include "tsc_select.cuh"
 
@@ -77,6 +80,52 @@ int32_t launch_merge(Index *ix, const int64_t *d_part_ids, const double *d_part_
     return TSC_ERR_BAD_ARG;
   }
   merge_shards_kernel<<<nq, 256, smem, st>>>(p);
+  TSC_CUDA(cudaGetLastError());
+  ix->launches++;
+  return TSC_OK;
+}
+
+// K9 (opt-in): push this shard's top-k to every rank over peer memory, wait, merge.
+int32_t launch_exchange(Index *ix, const int64_t *d_src_ids, const double *d_src_dist, uint32_t nq,
+                        uint32_t k, int64_t *d_ids, double *d_dist, uint32_t *d_counts,
+                        cudaStream_t st) {
+  if (!ix->p2p_ready) {
+    set_error("exchange: tsc_comm_p2p_import has not been called");
+    return TSC_ERR_NCCL;
+  }
+  if (ix->h_xstatus && *reinterpret_cast<volatile uint32_t *>(ix->h_xstatus) != 0) {
+    set_error("exchange: an earlier peer-memory exchange timed out (a rank fell behind or died)");
+    return TSC_ERR_NCCL;
+  }
+  ExchangeParams p{};
+  p.src_ids = d_src_ids;
+  p.src_dist = d_src_dist;
+  for (int r = 0; r < ix->n_ranks; r++) p.peer_base[r] = ix->x_peer[r];
+  p.n_ranks = (uint32_t)ix->n_ranks;
+  p.rank = (uint32_t)ix->rank;
+  p.nq = nq;
+  p.k = k;
+  p.k_stride = ix->k_max;
+  p.nq_max = ix->nq_max;
+  p.slot_bytes = ix->xslot_bytes;
+  p.flag_off = exchange_flag_off(p.n_ranks, p.slot_bytes);
+  p.epoch = ++ix->xepoch;
+  p.sort_cap = next_pow2(p.n_ranks * k);
+  if (p.sort_cap < 2) p.sort_cap = 2;
+  p.out_ids = d_ids;
+  p.out_dist = d_dist;
+  p.out_counts = d_counts;
+  p.status = ix->d_xstatus;
+  // ~2 s at 2 GHz unless overridden (TSC_P2P_TIMEOUT_MS)
+  long long ms = 2000;
+  if (const char *ev = getenv("TSC_P2P_TIMEOUT_MS")) ms = atoll(ev) > 0 ? atoll(ev) : ms;
+  p.timeout_cycles = ms * 2000000ll;
+  const size_t smem = (size_t)p.sort_cap * sizeof(Pair128);
+  if (smem > 48 * 1024) {
+    set_error("exchange: n_ranks*k=%u too large", p.n_ranks * k);
+    return TSC_ERR_BAD_ARG;
+  }
+  exchange_merge_kernel<<<nq, 256, smem, st>>>(p);
   TSC_CUDA(cudaGetLastError());
   ix->launches++;
   return TSC_OK;

@@ -287,6 +287,18 @@ class GpuVectorIndex:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         N.check(self._lib.tsc_comm_init(self.handle, buf, n_ranks, rank), "tsc_comm_init")
 
+    def comm_init_p2p(self, dist, n_ranks: int, rank: int) -> None:
+        """Experimental: peer-memory exchange instead of NCCL (tsc_exchange.cuh). `dist` is an
+        initialised torch.distributed module (any backend) used only to all-gather the
+        64-byte CUDA IPC handles of the receive buffers."""
+        buf = (C.c_uint8 * 64)()
+        N.check(self._lib.tsc_comm_p2p_export(self.handle, n_ranks, rank, buf), "tsc_comm_p2p_export")
+        handles = [None] * n_ranks
+        dist.all_gather_object(handles, bytes(buf))
+        blob = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(b"".join(handles))
+        N.check(self._lib.tsc_comm_p2p_import(self.handle, blob), "tsc_comm_p2p_import")
+        dist.barrier()          # every rank has mapped every buffer before the first search
+
     def merge_shards(self, d_part_ids: int, d_part_dist: int, n_parts: int, nq: int, k: int,
                      d_ids: int, d_dist: int, d_counts: int, stream: int = 0) -> None:
         N.check(self._lib.tsc_merge_shards(self.handle, d_part_ids, d_part_dist, n_parts, nq, k,
