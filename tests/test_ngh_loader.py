@@ -177,3 +177,36 @@ def test_load_and_search(tmp_path, prec):
         oi, od = oracle.search(decoded, q, 2, k, deleted=dead)
         assert cnt[0] == k and (ids[0] == oi).all()
         assert (dist[0].view(np.int64) == od.view(np.int64)).all()
+
+
+# ---- property test: the library's meta.json parser against Python's json ------------------
+from hypothesis import given, settings, strategies as st   # noqa: E402
+
+_junk = st.recursive(st.none() | st.booleans() | st.integers(-10, 10 ** 12) | st.floats(allow_nan=False, allow_infinity=False)
+                     | st.text(max_size=12),
+                     lambda kids: st.lists(kids, max_size=3) | st.dictionaries(
+                         st.sampled_from(["dimensions", "nextNodeId", "nghPageSize", "name", "x", "maxDegree"]),
+                         kids, max_size=3), max_leaves=8)
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.integers(1, 4096), st.sampled_from(["l2", "innerProduct", "cosine", "weird", None]),
+       st.sampled_from(["float64", "float32", "int8", None]), st.integers(0, 10 ** 10),
+       st.sampled_from([4096, 16384, 65536]), st.integers(1, 64),
+       st.dictionaries(st.text(min_size=1, max_size=10).filter(
+           lambda k: k not in {"dimensions", "distanceMetric", "precision", "nextNodeId", "nghPageSize",
+                               "maxPartitionFileSize", "maxDegree"}), _junk, max_size=5),
+       st.booleans())
+def test_property_native_meta_parser_equals_python_json(tmp_path_factory, dims, metric, prec, nxt, ps, files,
+                                                        extra, pretty):
+    import json
+    d = tmp_path_factory.mktemp("meta")
+    (d / "ngh").mkdir()
+    j = dict(extra)
+    j.update({"dimensions": dims, "nextNodeId": nxt, "nghPageSize": ps, "maxPartitionFileSize": ps * files * 4})
+    if metric is not None:
+        j["distanceMetric"] = metric
+    if prec is not None:
+        j["precision"] = prec
+    (d / "ngh" / "meta.json").write_text(json.dumps(j, indent=2 if pretty else None, ensure_ascii=not pretty))
+    assert L.read_meta_native(str(d)) == L.read_meta(str(d))
