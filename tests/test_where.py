@@ -432,3 +432,42 @@ def test_gpu_golden_where_fixtures():
             ids, _, cnt = ix.search(oracle.synth_rows(6, 0, 1, 16)[0], 16)
             live = {i for i, c in enumerate(case["match"]) if c == "1"}
             assert set(ids[0, : cnt[0]].tolist()) <= live and cnt[0] == min(16, len(live))
+
+
+@pytest.mark.gpu
+def test_store_update_rewrites_row_and_attributes_in_place():
+    """`GpuVectorStore.update` (additive; the reference drops embedding updates,
+    core/index_manager.dart:3125-3133): same nodeId, new vector / attribute values."""
+    import oracle
+    from tostore_b200 import (GpuVectorStore, VectorData, VectorDistanceMetric, VectorFieldConfig,
+                              VectorIndexConfig, VectorPrecision)
+    n, d = 300, 16
+    rows = oracle.synth_rows(93, 0, n, d)
+    price = list(range(n))
+    st = GpuVectorStore(capacity_rows=512)
+    try:
+        st.createVectorIndex("items", "emb", VectorFieldConfig(d, VectorPrecision.float32),
+                             VectorIndexConfig(VectorDistanceMetric.l2), attributeFields={"price": "integer"})
+        st.batchInsert("items", [{"id": f"pk{i}", "emb": VectorData.fromList(rows[i]), "price": price[i]}
+                                 for i in range(n)])
+        q = oracle.synth_rows(94, 0, 1, d)[0]
+        # move pk7 onto the query itself: it must become the nearest neighbour at distance 0
+        assert st.update("items", "pk7", {"emb": VectorData.fromList(q)}) == 1
+        rows2 = rows.copy()
+        rows2[7] = q
+        res = st.vectorSearch("items", fieldName="emb", queryVector=VectorData.fromList(q), topK=5)
+        oi, od = oracle.search(rows2, q, 0, 5)
+        assert [r.primaryKey for r in res] == [f"pk{i}" for i in oi] and res[0].primaryKey == "pk7"
+        assert res[0].distance == 0.0 and [r.distance for r in res] == od.tolist()
+        # attribute update: pk7 leaves the WHERE set, pk8 becomes NULL (NULL != x is true)
+        assert st.update("items", "pk7", {"price": 1000}) == 1 and st.update("items", "pk8", {"price": None}) == 1
+        price2 = list(price)
+        price2[7], price2[8] = 1000, None
+        for cond in ({"price": {"<": 100}}, {"price": {"!=": 5}}):
+            want = np.array(wo.evaluate_columns(cond, {"price": price2}, {"price": "i64"}), dtype=bool)
+            res = st.vectorSearch("items", fieldName="emb", queryVector=VectorData.fromList(q), topK=6, where=cond)
+            oi, _ = oracle.search(rows2, q, 0, 6, filter=want)
+            assert [r.primaryKey for r in res] == [f"pk{i}" for i in oi]
+        assert st.update("items", "nope", {"price": 1}) == 0
+    finally:
+        st.close()

@@ -201,6 +201,30 @@ class GpuVectorStore:
     def insert(self, tableName: str, record: Dict[str, object], primaryKey: str = "id") -> int:
         return self.batchInsert(tableName, [record], primaryKey)
 
+    def update(self, tableName: str, primaryKey: object, record: Dict[str, object]) -> int:
+        """Overwrite the embedding and / or attribute fields of an existing row in place
+        (same nodeId). Additive: the reference does not forward embedding updates to the
+        vector index at all (core/index_manager.dart:3125-3133); here
+        the row in HBM, its norm and its attribute columns are rewritten, so the next
+        search sees the new values. Fields absent from `record` keep their value."""
+        n = 0
+        for ix in self._indexes.get(tableName, ()):
+            nid = ix.pk2nid.get(str(primaryKey))
+            if nid is None:
+                continue
+            val = record.get(ix.fieldName)
+            if val is not None:
+                row = self._store_round_trip(self._to_float32(val, ix.field.dimensions)[None, :],
+                                             ix.field.precision)
+                ix.engine.append_rows(row, first_node_id=nid)
+            for name, (cid, t) in ix.attributes.items():
+                if name in record:
+                    v = record[name]
+                    ix.engine.column_append(cid, [None if v is None else _where._convert(v, t)],
+                                            first_node_id=nid)
+            n += 1
+        return n
+
     def delete(self, tableName: str, primaryKeys: Iterable[object]) -> int:
         """Tombstone rows (deleteBatch, ngh_graph_engine.dart:411-445; mapping
         tombstone, vector_index_manager.dart:416-434)."""
