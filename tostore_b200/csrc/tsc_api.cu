@@ -1022,6 +1022,13 @@ int32_t tsc_comm_p2p_export(uint64_t handle, int32_t n_ranks, int32_t rank, uint
   }
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   std::lock_guard<std::mutex> lk(ix->mu);
+  // one CTA per query spins on its peers' CTA of the same query: every CTA of a launch must
+  // be resident at once or two ranks could wait on each other's unscheduled CTAs
+  if (ix->nq_max > 512) {
+    set_error("comm_p2p_export: nq_max=%u > 512 is not supported by the peer-memory exchange",
+              ix->nq_max);
+    return TSC_ERR_UNSUPPORTED;
+  }
   if (ix->d_xbuf) {
     set_error("comm_p2p_export: already exported");
     return TSC_ERR_BAD_ARG;

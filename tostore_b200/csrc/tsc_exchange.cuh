@@ -13,6 +13,8 @@
 // Buffers are double-buffered by epoch parity. A rank can be at most one epoch ahead of a
 // peer (it cannot finish epoch e+1 without that peer's e+1 flags, which the peer only sends
 // after it finished reading epoch e), so a slot is never overwritten while it is read.
+// One CTA per query waits for the peers' CTA of the same query, so all CTAs of a launch must
+// be co-resident (nq_max <= 512 is enforced at export; 148 SMs x >= 4 CTAs of 256 threads).
 // The spin has a clock64 timeout: on expiry a status word in mapped host memory is set and
 // the query returns empty instead of hanging the GPU.
 //
