@@ -1,0 +1,434 @@
+// tostore_vector.hpp — C++ host layer over the C ABI (tostore_cuda.h), mirroring the slice
+// of ToStore's Dart API that serves vector search: same type names, argument meaning and
+// error behaviour as the reference (paths relative to /root/reference/lib):
+//
+//   VectorData, VectorFieldConfig, VectorPrecision, VectorDistanceMetric, VectorIndexConfig
+//                                                   src/model/table_schema.dart:2109-2675
+//   VectorSearchResult                              src/model/query_result.dart:207-228
+//   ToStore.vectorSearch(tableName, fieldName:, queryVector:, topK: 10, efSearch:,
+//                        distanceThreshold:)        tostore.dart:493-511
+//   VectorIndexManager.vectorSearch / writeChanges  src/core/vector_index_manager.dart:297-589
+//   QueryCondition (where / or / whereIn / whereBetween ...), operator semantics
+//                                                   src/query/query_condition.dart:117-660,
+//                                                   src/handler/value_matcher.dart:570-612
+//
+// The reference's host language is Dart (binding source: dart/tostore_cuda_bindings.dart);
+// this header is the same host layer in the compiled language this build image has, and
+// tostore_b200/vector_store.py is its Python twin (the one the pytest suite drives).
+// Header-only; link with -ltostore_cuda. Like `vectorSearch` in the reference, lookups that
+// miss (unknown table / field, empty index) return an empty list instead of throwing;
+// library failures throw TscError. There is no CPU fallback.
+#ifndef TOSTORE_VECTOR_HPP
+#define TOSTORE_VECTOR_HPP
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <variant>
+#include <vector>
+
+#include "tostore_cuda.h"
+
+namespace tostore {
+
+enum class VectorPrecision : uint8_t { float64 = 0, float32 = 1, int8 = 2 };        // enum order :2481-2498
+enum class VectorDistanceMetric : uint8_t { l2 = 0, innerProduct = 1, cosine = 2 }; // enum order :2511-2531
+enum class DeviceDType : uint8_t { float32 = 0, bfloat16 = 1, float16 = 2 };         // new: storage in HBM
+enum class DataType : uint8_t { integer = 0, doubleType = 1 };                       // attribute fields
+
+struct TscError : std::runtime_error {
+  int32_t status;
+  TscError(int32_t s, const std::string &where)
+      : std::runtime_error(where + ": " + tsc_status_name(s) + ": " + tsc_last_error()), status(s) {}
+};
+inline void check(int32_t rc, const char *where) {
+  if (rc != TSC_OK) throw TscError(rc, where);
+}
+
+struct VectorData {
+  std::vector<double> values;
+  static VectorData fromList(std::vector<double> v) { return VectorData{std::move(v)}; }
+  int dimensions() const { return (int)values.size(); }
+};
+
+struct VectorFieldConfig {
+  int dimensions = 0;
+  VectorPrecision precision = VectorPrecision::float64;
+};
+
+struct VectorIndexConfig {
+  VectorDistanceMetric distanceMetric = VectorDistanceMetric::cosine;
+  std::optional<int> maxDegree, efSearch, constructionEf, pqSubspaces;   // accepted, unused: the
+  std::optional<double> pruneAlpha;                                       // exact scan has no graph
+};
+
+struct VectorSearchResult {
+  std::string primaryKey;
+  double distance = 0.0;
+  double score = 0.0;
+};
+
+// ---- QueryCondition: builds the postfix program tsc_index_filter_where evaluates ----------
+using Value = std::variant<std::monostate, int64_t, double>;   // monostate = null
+
+class QueryCondition {
+ public:
+  // `where` ANDs onto the current group, `orWhere` starts an alternative
+  // (query_condition.dart:117-260); operators as in `_buildCondition` (:478-520).
+  QueryCondition &where(const std::string &field, const std::string &op, Value v = {}) {
+    groups_.back().push_back(Leaf{field, upper(op), {std::move(v)}});
+    return *this;
+  }
+  QueryCondition &orWhere(const std::string &field, const std::string &op, Value v = {}) {
+    groups_.emplace_back();
+    return where(field, op, std::move(v));
+  }
+  QueryCondition &whereIn(const std::string &field, std::vector<Value> vs) {
+    groups_.back().push_back(Leaf{field, "IN", std::move(vs)});
+    return *this;
+  }
+  QueryCondition &whereNotIn(const std::string &field, std::vector<Value> vs) {
+    groups_.back().push_back(Leaf{field, "NOT IN", std::move(vs)});
+    return *this;
+  }
+  QueryCondition &whereBetween(const std::string &field, Value start, Value end) {
+    groups_.back().push_back(Leaf{field, "BETWEEN", {std::move(start), std::move(end)}});
+    return *this;
+  }
+  QueryCondition &whereNull(const std::string &field) { return where(field, "IS"); }
+  QueryCondition &whereNotNull(const std::string &field) { return where(field, "IS NOT"); }
+  bool isEmpty() const {
+    for (auto &g : groups_)
+      if (!g.empty()) return false;
+    return true;
+  }
+
+  struct Program {
+    std::vector<tsc_where_op> ops;
+    std::vector<uint64_t> in_args;   // raw 8-byte values typed like the leaf's column
+  };
+  // columns: field name -> (column id, type). Operands are converted to the field's type
+  // exactly like FieldSchema.convertValue (table_schema.dart:1371-1421): integer fields
+  // round doubles half away from zero, double fields widen integers.
+  Program compile(const std::map<std::string, std::pair<uint32_t, DataType>> &columns) const {
+    Program p;
+    size_t n_groups = 0;
+    for (auto &g : groups_) {
+      if (g.empty()) continue;
+      for (auto &leaf : g) emit(leaf, columns, &p);
+      if (g.size() != 1) p.ops.push_back(node(TSC_W_AND, (uint16_t)g.size()));
+      n_groups++;
+    }
+    if (n_groups > 1) p.ops.push_back(node(TSC_W_OR, (uint16_t)n_groups));
+    if (p.ops.size() > 64) throw std::invalid_argument("condition compiles to more than 64 steps");
+    return p;
+  }
+
+ private:
+  struct Leaf {
+    std::string field, op;
+    std::vector<Value> args;
+  };
+  std::vector<std::vector<Leaf>> groups_{1};
+
+  static std::string upper(std::string s) {
+    for (auto &c : s) c = (char)std::toupper((unsigned char)c);
+    return s;
+  }
+  static tsc_where_op node(uint8_t kind, uint16_t n) {
+    tsc_where_op o;
+    std::memset(&o, 0, sizeof o);
+    o.kind = kind;
+    o.n = n;
+    return o;
+  }
+  static int64_t dartRound(double x) {   // double.round(): half away from zero, clamped to int64
+    if (std::isnan(x) || std::isinf(x))
+      throw std::invalid_argument("cannot convert NaN / infinity to an integer field operand");
+    const double a = std::fabs(x);
+    double r = a;
+    if (a < 4503599627370496.0) {
+      r = std::floor(a);
+      if (a - r >= 0.5) r += 1.0;
+    }
+    if (r >= 9223372036854775808.0) return x >= 0 ? INT64_MAX : INT64_MIN;
+    return x >= 0 ? (int64_t)r : -(int64_t)r;
+  }
+  static void setOperand(tsc_where_op *o, DataType t, const Value &v, bool hi) {
+    if (t == DataType::integer) {
+      const int64_t x = std::holds_alternative<double>(v) ? dartRound(std::get<double>(v)) : std::get<int64_t>(v);
+      (hi ? o->i_hi : o->i_lo) = x;
+    } else {
+      const double x = std::holds_alternative<int64_t>(v) ? (double)std::get<int64_t>(v) : std::get<double>(v);
+      (hi ? o->f_hi : o->f_lo) = x;
+    }
+  }
+  static void emit(const Leaf &leaf, const std::map<std::string, std::pair<uint32_t, DataType>> &columns,
+                   Program *p) {
+    auto it = columns.find(leaf.field);
+    if (it == columns.end()) throw std::invalid_argument("WHERE names field '" + leaf.field + "' which has no attribute column");
+    const DataType t = it->second.second;
+    tsc_where_op o = node(TSC_W_LEAF, 0);
+    o.column_id = it->second.first;
+    const bool null0 = leaf.args.empty() || std::holds_alternative<std::monostate>(leaf.args[0]);
+    static const std::map<std::string, uint8_t> simple = {{"=", TSC_OP_EQ}, {"!=", TSC_OP_NE}, {"<>", TSC_OP_NE},
+                                                          {">", TSC_OP_GT}, {">=", TSC_OP_GE}, {"<", TSC_OP_LT},
+                                                          {"<=", TSC_OP_LE}};
+    auto s = simple.find(leaf.op);
+    if (s != simple.end()) {
+      if (null0) {   // matcher(value, null): 0 iff value is null, else +1 (value_matcher.dart:160-163)
+        switch (s->second) {
+          case TSC_OP_EQ: o.op = TSC_OP_IS_NULL; break;
+          case TSC_OP_NE: case TSC_OP_GT: case TSC_OP_GE: o.op = TSC_OP_IS_NOT_NULL; break;
+          default: o.op = TSC_OP_FALSE; break;
+        }
+      } else {
+        o.op = s->second;
+        setOperand(&o, t, leaf.args[0], false);
+      }
+    } else if (leaf.op == "BETWEEN") {
+      if (leaf.args.size() != 2 || null0 || std::holds_alternative<std::monostate>(leaf.args[1])) {
+        o.op = TSC_OP_FALSE;
+      } else {
+        o.op = TSC_OP_BETWEEN;
+        setOperand(&o, t, leaf.args[0], false);
+        setOperand(&o, t, leaf.args[1], true);
+      }
+    } else if (leaf.op == "IN" || leaf.op == "NOT IN") {
+      o.op = leaf.op == "IN" ? TSC_OP_IN : TSC_OP_NOT_IN;
+      o.args_offset = (uint32_t)p->in_args.size();
+      for (auto &v : leaf.args) {
+        if (std::holds_alternative<std::monostate>(v)) continue;   // never equal to a non-null value
+        tsc_where_op tmp = node(TSC_W_LEAF, 0);
+        setOperand(&tmp, t, v, false);
+        uint64_t raw;
+        if (t == DataType::integer) std::memcpy(&raw, &tmp.i_lo, 8);
+        else std::memcpy(&raw, &tmp.f_lo, 8);
+        p->in_args.push_back(raw);
+        o.n++;
+      }
+    } else if (leaf.op == "IS") {
+      o.op = null0 ? TSC_OP_IS_NULL : TSC_OP_FALSE;
+    } else if (leaf.op == "IS NOT") {
+      o.op = null0 ? TSC_OP_IS_NOT_NULL : TSC_OP_FALSE;
+    } else {
+      throw std::invalid_argument("operator '" + leaf.op + "' has no columnar GPU form (numeric fields only)");
+    }
+    p->ops.push_back(o);
+  }
+};
+
+// ---- one record of a batch insert ---------------------------------------------------------
+struct Record {
+  std::string id;                          // primary key ("" -> skipped, like prepareVectorBatchChunk)
+  std::optional<VectorData> embedding;     // absent -> skipped
+  std::map<std::string, Value> fields;     // attribute fields (numeric); absent / monostate -> NULL
+};
+
+// ---- the slice of ToStore / VectorIndexManager that serves vectorSearch --------------------
+class GpuVectorStore {
+ public:
+  explicit GpuVectorStore(int deviceId = 0, uint64_t capacityRows = 1u << 20,
+                          DeviceDType deviceDType = DeviceDType::float32, uint32_t kMax = 128)
+      : device_(deviceId), capacity_(capacityRows), dtype_(deviceDType), k_max_(kMax) {}
+  ~GpuVectorStore() { close(); }
+  GpuVectorStore(const GpuVectorStore &) = delete;
+  GpuVectorStore &operator=(const GpuVectorStore &) = delete;
+
+  // TableSchema vector field + IndexSchema(type: IndexType.vector). attributeFields (new,
+  // additive): numeric table fields mirrored column-wise on the GPU for vectorSearch(where:).
+  void createVectorIndex(const std::string &tableName, const std::string &fieldName,
+                         const VectorFieldConfig &fieldConfig, const VectorIndexConfig &indexConfig = {},
+                         const std::map<std::string, DataType> &attributeFields = {}) {
+    tsc_index_desc d;
+    std::memset(&d, 0, sizeof d);
+    d.struct_size = sizeof d;
+    d.dims = (uint32_t)fieldConfig.dimensions;
+    d.metric = (uint8_t)indexConfig.distanceMetric;
+    d.src_precision = TSC_SRC_F32;       // rows cross the boundary as fp32 (`_toFloat32`)
+    d.dev_dtype = (uint8_t)dtype_;
+    d.device_id = device_;
+    d.capacity_rows = capacity_;
+    d.k_max = k_max_;
+    d.nq_max = 64;
+    auto ix = std::make_unique<Index>();
+    check(tsc_index_create(&d, &ix->handle), "tsc_index_create");
+    ix->fieldName = fieldName;
+    ix->field = fieldConfig;
+    ix->config = indexConfig;
+    uint32_t cid = 0;
+    for (auto &kv : attributeFields) {
+      check(tsc_index_column_create(ix->handle, cid, (uint8_t)kv.second), "tsc_index_column_create");
+      ix->attributes[kv.first] = {cid++, kv.second};
+    }
+    tables_[tableName].push_back(std::move(ix));
+  }
+
+  // VectorIndexManager.writeChanges (:297-466): rows become node ids in insertion order
+  // (meta.nextNodeId++, ngh_graph_engine.dart:321-322); `__nid2pk` deltas go to the library.
+  size_t batchInsert(const std::string &tableName, const std::vector<Record> &records) {
+    size_t done = 0;
+    for (auto &ixp : tables_[tableName]) {
+      Index &ix = *ixp;
+      const uint32_t dims = (uint32_t)ix.field.dimensions;
+      std::vector<float> rows;
+      std::vector<const Record *> kept;
+      for (auto &r : records) {
+        if (!r.embedding || r.id.empty()) continue;
+        const size_t base = rows.size();
+        rows.resize(base + dims, 0.0f);                       // _toFloat32: truncate / zero-pad
+        const auto &v = r.embedding->values;
+        for (size_t i = 0; i < v.size() && i < dims; i++) rows[base + i] = (float)v[i];
+        if (ix.field.precision == VectorPrecision::int8)      // what the reference keeps on disk
+          for (size_t i = 0; i < dims; i++) rows[base + i] = int8RoundTrip(rows[base + i]);
+        kept.push_back(&r);
+      }
+      if (kept.empty()) continue;
+      const uint64_t start = ix.nextNodeId;
+      check(tsc_index_append_rows(ix.handle, start, rows.data(), kept.size()), "tsc_index_append_rows");
+      std::string bytes;
+      std::vector<uint64_t> offs{0};
+      for (auto *r : kept) {
+        bytes += r->id;
+        offs.push_back(bytes.size());
+        ix.pk2nid[r->id] = ix.nextNodeId++;
+      }
+      check(tsc_index_set_primary_keys(ix.handle, start, (const uint8_t *)bytes.data(), offs.data(), kept.size()),
+            "tsc_index_set_primary_keys");
+      for (auto &a : ix.attributes) {
+        std::vector<uint64_t> vals(kept.size(), 0);
+        std::vector<uint8_t> nulls(kept.size(), 1);
+        for (size_t i = 0; i < kept.size(); i++) {
+          auto f = kept[i]->fields.find(a.first);
+          if (f == kept[i]->fields.end() || std::holds_alternative<std::monostate>(f->second)) continue;
+          nulls[i] = 0;
+          vals[i] = rawValue(f->second, a.second.second);
+        }
+        check(tsc_index_column_append(ix.handle, a.second.first, start, vals.data(), nulls.data(), kept.size()),
+              "tsc_index_column_append");
+      }
+      done = std::max(done, kept.size());
+    }
+    return done;
+  }
+  size_t insert(const std::string &tableName, const Record &r) { return batchInsert(tableName, {r}); }
+
+  // deleteBatch (ngh_graph_engine.dart:411-445) + tombstone mapping (vector_index_manager.dart:416-434)
+  size_t deleteKeys(const std::string &tableName, const std::vector<std::string> &primaryKeys) {
+    size_t n = 0;
+    for (auto &ixp : tables_[tableName]) {
+      std::vector<uint64_t> nids;
+      for (auto &pk : primaryKeys) {
+        auto it = ixp->pk2nid.find(pk);
+        if (it == ixp->pk2nid.end()) continue;
+        nids.push_back(it->second);
+        ixp->pk2nid.erase(it);
+      }
+      if (nids.empty()) continue;
+      check(tsc_index_set_deleted(ixp->handle, nids.data(), nids.size(), 1), "tsc_index_set_deleted");
+      const uint64_t zero[2] = {0, 0};
+      for (uint64_t nid : nids)
+        check(tsc_index_set_primary_keys(ixp->handle, nid, (const uint8_t *)"", zero, 1), "tsc_index_set_primary_keys");
+      n = std::max(n, nids.size());
+    }
+    return n;
+  }
+
+  // ToStore.vectorSearch (tostore.dart:493-511). `where` (new, additive) is evaluated on the
+  // GPU into the prefilter bitmap; nullptr searches every live row.
+  std::vector<VectorSearchResult> vectorSearch(const std::string &tableName, const std::string &fieldName,
+                                               const VectorData &queryVector, int topK = 10,
+                                               std::optional<int> efSearch = std::nullopt,
+                                               std::optional<double> distanceThreshold = std::nullopt,
+                                               const QueryCondition *where = nullptr) {
+    (void)efSearch;                                   // exact scan: no expansion factor
+    Index *ix = find(tableName, fieldName);
+    if (!ix || ix->nextNodeId == 0 || topK <= 0) return {};   // :485-504 -> const []
+    if (where) {
+      std::map<std::string, std::pair<uint32_t, DataType>> cols(ix->attributes.begin(), ix->attributes.end());
+      auto prog = where->compile(cols);
+      check(tsc_index_filter_where(ix->handle, prog.ops.data(), (uint32_t)prog.ops.size(), prog.in_args.data(),
+                                   (uint32_t)prog.in_args.size(), nullptr), "tsc_index_filter_where");
+      ix->whereActive = true;
+    } else if (ix->whereActive) {
+      check(tsc_index_set_filter(ix->handle, nullptr, 0), "tsc_index_set_filter");
+      ix->whereActive = false;
+    }
+    const uint32_t k = (uint32_t)topK;
+    std::vector<int64_t> ids(k);
+    std::vector<double> dist(k), score(k);
+    std::vector<uint8_t> pks(64 * 1024);
+    std::vector<uint64_t> offs(k + 1);
+    uint32_t count = 0;
+    check(tsc_vector_search_pk(ix->handle, queryVector.values.data(), queryVector.values.size(), k,
+                               distanceThreshold ? *distanceThreshold : std::nan(""), ids.data(), dist.data(),
+                               score.data(), pks.data(), pks.size(), offs.data(), &count),
+          "tsc_vector_search_pk");
+    std::vector<VectorSearchResult> out;
+    for (uint32_t j = 0; j < count; j++)
+      out.push_back({std::string((const char *)pks.data() + offs[j], (size_t)(offs[j + 1] - offs[j])), dist[j], score[j]});
+    return out;                                        // ascending distance (:587)
+  }
+
+  void close() {
+    for (auto &t : tables_)
+      for (auto &ix : t.second)
+        if (ix->handle) {
+          tsc_index_destroy(ix->handle);
+          ix->handle = 0;
+        }
+    tables_.clear();
+  }
+
+ private:
+  struct Index {
+    uint64_t handle = 0;
+    std::string fieldName;
+    VectorFieldConfig field;
+    VectorIndexConfig config;
+    uint64_t nextNodeId = 0;
+    std::map<std::string, uint64_t> pk2nid;                                  // role of `__pk2nid`
+    std::map<std::string, std::pair<uint32_t, DataType>> attributes;
+    bool whereActive = false;
+  };
+  Index *find(const std::string &table, const std::string &field) {
+    auto t = tables_.find(table);
+    if (t == tables_.end()) return nullptr;
+    for (auto &ix : t->second)
+      if (ix->fieldName == field) return ix.get();
+    return nullptr;
+  }
+  static float int8RoundTrip(float v) {   // setVectorFromFloat32 / getVectorAsFloat32, ngh_page.dart:368-412
+    double c = (double)v < -1.0 ? -1.0 : ((double)v > 1.0 ? 1.0 : (double)v);
+    c *= 127.0;
+    const double q = c >= 0 ? std::floor(c + 0.5) : std::ceil(c - 0.5);
+    return (float)(q / 127.0);
+  }
+  static uint64_t rawValue(const Value &v, DataType t) {
+    uint64_t raw;
+    if (t == DataType::integer) {
+      const int64_t x = std::holds_alternative<double>(v) ? (int64_t)std::llround(std::get<double>(v)) : std::get<int64_t>(v);
+      std::memcpy(&raw, &x, 8);
+    } else {
+      const double x = std::holds_alternative<int64_t>(v) ? (double)std::get<int64_t>(v) : std::get<double>(v);
+      std::memcpy(&raw, &x, 8);
+    }
+    return raw;
+  }
+
+  int device_;
+  uint64_t capacity_;
+  DeviceDType dtype_;
+  uint32_t k_max_;
+  std::map<std::string, std::vector<std::unique_ptr<Index>>> tables_;
+};
+
+}  // namespace tostore
+
+#endif  // TOSTORE_VECTOR_HPP

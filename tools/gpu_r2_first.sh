@@ -14,6 +14,8 @@ echo "== pytest gpu (experimental paths)" | tee -a $L
 TSC_TEST_TF32=1 TSC_TEST_SPARSE_PF=1 timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -m gpu -q -k "tf32 or sparse" 2>&1 | tail -12 | tee -a $L
 echo "== C example" | tee -a $L
 gcc -std=c99 -I include examples/minimal.c -L tostore_b200 -ltostore_cuda -Wl,-rpath,$PWD/tostore_b200 -lm -o /tmp/minimal && /tmp/minimal 2>&1 | tee -a $L
+echo "== C++ host layer demo" | tee -a $L
+g++ -std=c++17 -I include examples/vector_store_demo.cc -L tostore_b200 -ltostore_cuda -Wl,-rpath,$PWD/tostore_b200 -o /tmp/vsdemo && /tmp/vsdemo 2>&1 | tail -16 | tee -a $L
 echo "== bench" | tee -a $L
 timeout 600 python bench.py 2>gpurun_out/r2_bench.err | tee gpurun_out/r2_bench.json | tee -a $L
 echo "== configs (new paths)" | tee -a $L
