@@ -20,5 +20,7 @@ echo "== bench" | tee -a $L
 timeout 600 python bench.py 2>gpurun_out/r2_bench.err | tee gpurun_out/r2_bench.json | tee -a $L
 echo "== configs (new paths)" | tee -a $L
 timeout 900 python tools/bench_configs.py c5 c5pf c5w c2t 2>&1 | tee gpurun_out/r2_configs.jsonl | tee -a $L
+echo "== native loader throughput (1M x 768 fp32 = 3.3 GB on disk)" | tee -a $L
+timeout 600 python tools/bench_loader.py --rows 1000000 --dims 768 2>&1 | tail -4 | tee -a $L
 echo "== ncu where kernel" | tee -a $L
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:where_eval -c 3 python tools/bench_configs.py c5w 2>&1 | grep -E "where_eval|gpu__time|dram__" | tee -a $L
