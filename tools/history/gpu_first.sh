@@ -3,7 +3,7 @@
 # Everything is logged under gpurun_out/ (merged back by gpurun).
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 nproc >> gpurun_out/gpu.txt
 echo "== smoke" | tee gpurun_out/first.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== gemm_dev small" | tee gpurun_out/gemm1.log
 timeout 120 python tools/gemm_dev.py 2>&1 | tail -12 | tee -a gpurun_out/gemm1.log
 echo "== gemm_dev 768" | tee -a gpurun_out/gemm1.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== gemm_dev 2cta (timeout 60)" | tee gpurun_out/gemm10.log
 D=768 NR=1000 NQ=300 timeout 60 python tools/gemm_dev.py 2>&1 | tail -8 | tee -a gpurun_out/gemm10.log
 echo "rc=$?" | tee -a gpurun_out/gemm10.log

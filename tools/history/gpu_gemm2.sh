@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== configs" | tee gpurun_out/gemm2.log
 timeout 900 python tools/bench_configs.py c1 c3 c3s c4 c5 c2b 2>&1 | tee gpurun_out/configs.jsonl | tee -a gpurun_out/gemm2.log
 echo "== ncu gemm" | tee -a gpurun_out/gemm2.log

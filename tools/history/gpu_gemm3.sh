@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== pytest gemm" | tee gpurun_out/gemm3.log
 timeout 900 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q 2>&1 | tail -8 | tee -a gpurun_out/gemm3.log
 echo "== c3" | tee -a gpurun_out/gemm3.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== gemm_dev (TS)" | tee gpurun_out/gemm4.log
 D=768 NR=1000 NQ=200 timeout 120 python tools/gemm_dev.py 2>&1 | tail -8 | tee -a gpurun_out/gemm4.log
 echo "== pytest gemm" | tee -a gpurun_out/gemm4.log

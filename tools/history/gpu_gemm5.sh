@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== experiments (TS kernel, results invalid for exp != 0)" | tee gpurun_out/gemm5.log
 for cfg in "0 8" "1 8" "2 8" "3 8" "4 8" "6 8"; do
 set -- $cfg

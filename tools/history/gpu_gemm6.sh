@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 echo "== pytest gemm (SS default)" | tee gpurun_out/gemm6.log
 timeout 900 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q 2>&1 | tail -5 | tee -a gpurun_out/gemm6.log
 echo "== pytest gemm (TS)" | tee -a gpurun_out/gemm6.log

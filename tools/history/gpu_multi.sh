@@ -1,7 +1,7 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 N=${1:-2}
 nvidia-smi -L | tee gpurun_out/multi.log
 echo "== pytest multi" | tee -a gpurun_out/multi.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # session 2, call 1: re-verify the rebuilt library, then the 2-CTA isolation matrix
 set +e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/r1b_1.log
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv | tee $L

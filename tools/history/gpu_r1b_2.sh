@@ -1,7 +1,7 @@
 #!/bin/bash
 # session 2, call 2: raw-accumulator epilogue
 set +e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/r1b_2.log
 echo "== pytest gemm" | tee $L

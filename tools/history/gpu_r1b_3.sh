@@ -1,6 +1,6 @@
 #!/bin/bash
 set +e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/r1b_3.log
 echo "== pytest gemm" | tee $L

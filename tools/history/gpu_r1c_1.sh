@@ -1,7 +1,7 @@
 #!/bin/bash
 # round-1 session c, call 1: verify restored state (gpu tests, bench, configs, ncu launch list)
 set +e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 L=gpurun_out/r1c_1.log
 nvidia-smi -L | tee $L

@@ -1,7 +1,7 @@
 #!/bin/bash
 # multi-GPU call: sharded parity test, headline bench at 1/2/4/../N GPUs, sharded configs C4/C5
 set +e
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 N=${1:-2}
 L=gpurun_out/r1c_multi_$N.log
