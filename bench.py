@@ -175,8 +175,10 @@ def run_reference(args):
         "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"single-query L2, N={args.rows} d={args.dims} fp32, k={args.k} "
-                               "(BASELINE config 2), reference arithmetic restated in C (oracle port); "
-                               "the Dart reference cannot run here (no Dart SDK)",
+                               "(BASELINE config 2)",
+                   "implementation": "reference arithmetic (_exactDistance, fp64, sequential) restated in C "
+                                     "(oracle port, exhaustive scan, OpenMP over rows); the Dart reference "
+                                     "itself cannot run here (no Dart SDK)",
                    "l2_flush": "inputs larger than L2"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0,
@@ -327,8 +329,8 @@ def run_b200(args):
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"single-query L2, N={n} d={d} fp32, k={k} on {world}xB200 "
-                                   "(BASELINE config 2: HBM-bound scan + top-k + exact fp64 re-rank)",
+            "config": {"workload": f"single-query L2, N={n} d={d} fp32, k={k} (BASELINE config 2)",
+                       "implementation": f"HBM-bound scan + in-kernel top-k + exact fp64 re-rank on {world}xB200",
                        "rows_per_gpu": hi - lo, "sharding": "row-range" if world > 1 else "none",
                        "exchange": ("none" if world == 1 else
                                     "one-kernel push over NVLink peer memory (experimental)"
