@@ -24,3 +24,8 @@ echo "== native loader throughput (1M x 768 fp32 = 3.3 GB on disk)" | tee -a $L
 timeout 600 python tools/bench_loader.py --rows 1000000 --dims 768 2>&1 | tail -4 | tee -a $L
 echo "== ncu where kernel" | tee -a $L
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:where_eval -c 3 python tools/bench_configs.py c5w 2>&1 | grep -E "where_eval|gpu__time|dram__" | tee -a $L
+echo "== ncu full: sparse scan (is C5 bound by the bitmap stall or by DRAM page misses?)" | tee -a $L
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_topk_sparse -s 3 -c 1 -o gpurun_out/r2_sparse_full python tools/bench_configs.py c5 > gpurun_out/r2_ncu_sparse.log 2>&1
+tail -2 gpurun_out/r2_ncu_sparse.log | tee -a $L
+TSC_SCAN_SPARSE_PF=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_topk_sparse -s 3 -c 1 -o gpurun_out/r2_sparse_pf_full python tools/bench_configs.py c5 > gpurun_out/r2_ncu_sparse_pf.log 2>&1
+tail -2 gpurun_out/r2_ncu_sparse_pf.log | tee -a $L
