@@ -29,3 +29,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan
 tail -2 gpurun_out/r2_ncu_sparse.log | tee -a $L
 TSC_SCAN_SPARSE_PF=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_topk_sparse -s 3 -c 1 -o gpurun_out/r2_sparse_pf_full python tools/bench_configs.py c5 > gpurun_out/r2_ncu_sparse_pf.log 2>&1
 tail -2 gpurun_out/r2_ncu_sparse_pf.log | tee -a $L
+echo "== microbench: HBM bandwidth for sparse 1.5 KB row reads (roofline denominator for C5)" | tee -a $L
+nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/microbench/gather_bw.cu -o /tmp/gather_bw && timeout 300 /tmp/gather_bw 12500000 1536 2>&1 | tee -a $L
