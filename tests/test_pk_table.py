@@ -80,3 +80,60 @@ def test_host_only_handle_refuses_compute():
         with pytest.raises(TscError):
             ix.search(np.zeros((1, 4), dtype=np.float32), 1) if hasattr(ix, "dims") else \
                 N.check(ix._lib.tsc_search(ix.handle, None, 1, 1, float("nan"), None, None, None), "tsc_search")
+
+
+def test_concurrent_callers_share_one_handle_safely():
+    """Thread-safe per handle (internal mutex): many threads hammer set / get / assemble on
+    one host-only handle while others translate + evaluate WHERE programs; every reader must
+    see either the old or the new key of a row, never a torn one."""
+    import threading
+    from tostore_b200 import where as W
+    n, rounds = 64, 300
+    errors = []
+    with HostIndex(n) as ix:
+        ix.set_primary_keys([f"a{i:04d}" for i in range(n)])
+
+        def writer(tag):
+            try:
+                for r in range(rounds):
+                    ix.set_primary_keys([f"{tag}{(r + i) % 10000:04d}" for i in range(8)], first_node_id=(r * 8) % (n - 8))
+            except Exception as e:          # noqa: BLE001
+                errors.append(e)
+
+        def reader():
+            try:
+                for r in range(rounds):
+                    pk = ix.get_primary_key(r % n)
+                    assert pk is not None and len(pk) == 5 and pk[0] in "abc" and pk[1:].isdigit(), pk
+                    pks, *_ = ix.assemble([r % n, (r + 1) % n], [0.1, 0.2], [0.9, 0.8], k=4)
+                    assert len(pks) == 2 and all(len(p) == 5 for p in pks)
+            except Exception as e:          # noqa: BLE001
+                errors.append(e)
+
+        def evaluator():
+            try:
+                import ctypes as C
+                from tostore_b200 import _native as N
+                prog = W.compile_condition({"x": {"IN": [1, 2, 3]}}, {"x": (0, W.COL_I64)})
+                ops, n_ops, raw, n_args = prog.buffers()
+                ids = np.array([0], dtype=np.uint32)
+                types = np.array([0], dtype=np.uint8)
+                vals = np.arange(16, dtype=np.uint64)
+                nulls = np.zeros(16, dtype=np.uint8)
+                out = np.zeros(16, dtype=np.uint8)
+                for _ in range(rounds):
+                    N.check(N.lib().tsc_selftest_where(C.cast(ops, C.c_void_p), n_ops, raw.ctypes.data, n_args, 1,
+                                                       ids.ctypes.data, types.ctypes.data, vals.ctypes.data,
+                                                       nulls.ctypes.data, 16, out.ctypes.data), "where")
+                    assert out.tolist() == [0, 1, 1, 1] + [0] * 12
+            except Exception as e:          # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=writer, args=("b",)), threading.Thread(target=writer, args=("c",)),
+                   threading.Thread(target=reader), threading.Thread(target=reader),
+                   threading.Thread(target=evaluator), threading.Thread(target=evaluator)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    assert not errors, errors[:3]
