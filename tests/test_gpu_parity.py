@@ -409,3 +409,20 @@ def test_primary_key_side_table_and_pk_search():
             ix.set_primary_keys(["x"], first_node_id=n + 100)        # outside the shard
         ix.clear()
         assert ix.get_primary_key(0) is None
+
+
+def test_baseline_config_1_brute_force_l2_10k_x_128():
+    """BASELINE.json configs[0]: brute-force L2, k=10, 10,000 x 128 fp32 vectors, 1000 queries
+     — every query's ids and fp64 distances against the oracle, through the
+    blocking host-buffer API in batches of 8 (one scan pass each)."""
+    T = t()
+    n, dims, k, nq = 10_000, 128, 10, 1000
+    rows = oracle.synth_rows(0x70570201, 0, n, dims)
+    Q = oracle.synth_rows(0x70570202, 0, nq, dims)
+    with T.GpuVectorIndex(dims, 0, capacity_rows=n, k_max=16, nq_max=8) as ix:
+        ix.append_synthetic(0x70570201, n)
+        for b in range(0, nq, 8):
+            ids, dist, cnt = ix.search(Q[b: b + 8], k)
+            for j in range(ids.shape[0]):
+                oi, od = oracle.search(rows, Q[b + j], 0, k)
+                assert_same(ids, dist, cnt, j, oi, od, k, f"c1 q{b + j}")
