@@ -426,3 +426,17 @@ def test_baseline_config_1_brute_force_l2_10k_x_128():
             for j in range(ids.shape[0]):
                 oi, od = oracle.search(rows, Q[b + j], 0, k)
                 assert_same(ids, dist, cnt, j, oi, od, k, f"c1 q{b + j}")
+
+
+def test_baseline_config_4_shape_ip_fp16_k100():
+    """BASELINE.json configs[3] at reduced N: inner product over d=1536 fp16 rows, k=100 (one
+    shard's arithmetic; the 8-shard exchange is covered by test_gpu_multi / test_sharding_gloo)."""
+    T = t()
+    n, dims, k, seed = 200_000, 1536, 100, 0x70570204
+    Q = oracle.synth_rows(seed + 1, 0, 3, dims)
+    with T.GpuVectorIndex(dims, 1, capacity_rows=n, dev_dtype=2, k_max=128, nq_max=8) as ix:
+        ix.append_synthetic(seed, n)
+        ids, dist, cnt = ix.search(Q, k)
+        for q in range(3):
+            oi, od = oracle.search_synth(seed, n, dims, 2, Q[q], 1, k)
+            assert_same(ids, dist, cnt, q, oi, od, k, f"c4 q{q}")
