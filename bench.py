@@ -157,7 +157,9 @@ def cpu_arm(rows_total: int, dims: int, k: int, sample_rows: int, steps: int, wa
     dt = time.perf_counter() - t0
     scale = sample_rows / rows_total
     qps = steps / dt * scale
+    import shutil
     return {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+            "dart_sdk_on_this_host": bool(shutil.which("dart") or shutil.which("flutter")),
             "sample": f"{steps} queries x {sample_rows} of {rows_total} rows (d={dims}, fp64 scalar "
                       f"_exactDistance + heap top-k, OpenMP row split), QPS scaled x{scale:g} to the full corpus",
             "ms_per_step_sample": dt / steps * 1e3}
