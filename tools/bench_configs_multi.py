@@ -40,6 +40,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config", choices=sorted(CONFIGS))
     ap.add_argument("--rows-per-gpu", type=int, default=0)
+    ap.add_argument("--total-rows", type=int, default=0,
+                    help="strong scaling: split this many rows over the ranks (C4: 100000000 at 2/4/8 GPUs)")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--check", action="store_true")
@@ -56,6 +58,8 @@ def main():
     per, d, metric, dt, k, mask_frac, named = CONFIGS[args.config]
     if per is None:
         per = (10_000_000 + world - 1) // world
+    if args.total_rows:
+        per = (args.total_rows + world - 1) // world
     if args.rows_per_gpu:
         per = args.rows_per_gpu
     per = (per + 31) // 32 * 32
