@@ -319,6 +319,65 @@ class GpuVectorStore {
   }
   size_t insert(const std::string &tableName, const Record &r) { return batchInsert(tableName, {r}); }
 
+  // In-place update of an existing row (same nodeId). Additive: the reference does not
+  // forward embedding updates to the vector index (core/index_manager.dart:3125-3133).
+  size_t update(const std::string &tableName, const std::string &primaryKey, const Record &r) {
+    size_t n = 0;
+    for (auto &ixp : tables_[tableName]) {
+      Index &ix = *ixp;
+      auto it = ix.pk2nid.find(primaryKey);
+      if (it == ix.pk2nid.end()) continue;
+      const uint64_t nid = it->second;
+      if (r.embedding) {
+        const uint32_t dims = (uint32_t)ix.field.dimensions;
+        std::vector<float> row(dims, 0.0f);
+        const auto &v = r.embedding->values;
+        for (size_t i = 0; i < v.size() && i < dims; i++) row[i] = (float)v[i];
+        if (ix.field.precision == VectorPrecision::int8)
+          for (auto &x : row) x = int8RoundTrip(x);
+        check(tsc_index_append_rows(ix.handle, nid, row.data(), 1), "tsc_index_append_rows");
+      }
+      for (auto &a : ix.attributes) {
+        auto f = r.fields.find(a.first);
+        if (f == r.fields.end()) continue;
+        const uint8_t isnull = std::holds_alternative<std::monostate>(f->second) ? 1 : 0;
+        const uint64_t raw = isnull ? 0 : rawValue(f->second, a.second.second);
+        check(tsc_index_column_append(ix.handle, a.second.first, nid, &raw, &isnull, 1), "tsc_index_column_append");
+      }
+      n++;
+    }
+    return n;
+  }
+
+  // Cold start: stream an existing on-disk NGH index (`<indexDir>/ngh/...`) into the GPU
+  // index of (tableName, fieldName); primary keys come from the caller (`__nid2pk`).
+  uint64_t loadIndex(const std::string &tableName, const std::string &fieldName, const std::string &indexDir,
+                     bool tombstones = true) {
+    Index *ix = find(tableName, fieldName);
+    if (!ix) return 0;
+    tsc_ngh_info info;
+    std::memset(&info, 0, sizeof info);
+    info.struct_size = sizeof info;
+    check(tsc_index_load_ngh(ix->handle, indexDir.c_str(), tombstones ? TSC_LOAD_TOMBSTONES : 0, &info),
+          "tsc_index_load_ngh");
+    ix->nextNodeId = std::max<uint64_t>(ix->nextNodeId, info.next_node_id);
+    return info.next_node_id;
+  }
+  void setPrimaryKeys(const std::string &tableName, const std::string &fieldName, uint64_t firstNodeId,
+                      const std::vector<std::string> &pks) {
+    Index *ix = find(tableName, fieldName);
+    if (!ix || pks.empty()) return;
+    std::string bytes;
+    std::vector<uint64_t> offs{0};
+    for (size_t i = 0; i < pks.size(); i++) {
+      bytes += pks[i];
+      offs.push_back(bytes.size());
+      if (!pks[i].empty()) ix->pk2nid[pks[i]] = firstNodeId + i;
+    }
+    check(tsc_index_set_primary_keys(ix->handle, firstNodeId, (const uint8_t *)bytes.data(), offs.data(), pks.size()),
+          "tsc_index_set_primary_keys");
+  }
+
   // deleteBatch (ngh_graph_engine.dart:411-445) + tombstone mapping (vector_index_manager.dart:416-434)
   size_t deleteKeys(const std::string &tableName, const std::vector<std::string> &primaryKeys) {
     size_t n = 0;
