@@ -375,68 +375,3 @@ def test_sparse_where_filter_uses_per_row_scan(dt, dims, pf, monkeypatch):
                         oi, od = oracle.search(rows, Qp[q], metric, k, deleted=dead, filter=mask)
                         assert_same(ids, dist, cnt, q, oi, od, k, f"dt{dt} d{dims} m{metric} f{frac}")
                 ix.set_deleted(np.nonzero(dead)[0], deleted=False)
-
-
-def test_primary_key_side_table_and_pk_search():
-    """nodeId -> PK side table (role of `__nid2pk`, vector_index_manager.dart:553-588):
-    unmapped / tombstone-mapped nodes are dropped from the assembled result, the rest keep
-    ascending distance order; keys round-trip byte for byte (multi-byte utf-8 included)."""
-    n, d, k = 400, 24, 12
-    rows = oracle.synth_rows(31, 0, n, d)
-    q = oracle.synth_rows(32, 0, 1, d)[0].astype(np.float64)
-    T = t()
-    with T.GpuVectorIndex(d, 0, capacity_rows=n, k_max=16, nq_max=4) as ix:
-        ix.append_rows(rows)
-        pks = [f"用户-{i}" if i % 3 == 0 else f"user_{i:05d}" for i in range(n)]
-        ix.set_primary_keys(pks)
-        assert ix.get_primary_key(0) == "用户-0" and ix.get_primary_key(n - 1) == pks[n - 1]
-        assert ix.get_primary_key(n + 5) is None
-        oi, od = oracle.search(rows, q.astype(np.float32), 0, k)
-        got_pk, ids, dist, score = ix.vector_search_pk(q, k)
-        assert got_pk == [pks[i] for i in oi] and (ids == oi).all()
-        assert (dist.view(np.int64) == od.view(np.int64)).all()
-        assert np.allclose(score, 1.0 / (1.0 + od), rtol=0, atol=0)
-        # tombstone the mapping of the best and the 3rd hit: they vanish, order is kept
-        ix.set_primary_keys([None], first_node_id=int(oi[0]))
-        ix.set_primary_keys([""], first_node_id=int(oi[2]))
-        got_pk2, ids2, dist2, _ = ix.vector_search_pk(q, k)
-        keep = [j for j in range(k) if j not in (0, 2)]
-        assert got_pk2 == [pks[oi[j]] for j in keep] and (ids2 == oi[keep]).all()
-        assert (dist2.view(np.int64) == od[keep].view(np.int64)).all()
-        with pytest.raises(T.TscError):
-            ix.vector_search_pk(q, k, pk_capacity=8)                 # keys do not fit
-        with pytest.raises(T.TscError):
-            ix.set_primary_keys(["x"], first_node_id=n + 100)        # outside the shard
-        ix.clear()
-        assert ix.get_primary_key(0) is None
-
-
-def test_baseline_config_1_brute_force_l2_10k_x_128():
-    """BASELINE.json configs[0]: brute-force L2, k=10, 10,000 x 128 fp32 vectors, 1000 queries
-     — every query's ids and fp64 distances against the oracle, through the
-    blocking host-buffer API in batches of 8 (one scan pass each)."""
-    T = t()
-    n, dims, k, nq = 10_000, 128, 10, 1000
-    rows = oracle.synth_rows(0x70570201, 0, n, dims)
-    Q = oracle.synth_rows(0x70570202, 0, nq, dims)
-    with T.GpuVectorIndex(dims, 0, capacity_rows=n, k_max=16, nq_max=8) as ix:
-        ix.append_synthetic(0x70570201, n)
-        for b in range(0, nq, 8):
-            ids, dist, cnt = ix.search(Q[b: b + 8], k)
-            for j in range(ids.shape[0]):
-                oi, od = oracle.search(rows, Q[b + j], 0, k)
-                assert_same(ids, dist, cnt, j, oi, od, k, f"c1 q{b + j}")
-
-
-def test_baseline_config_4_shape_ip_fp16_k100():
-    """BASELINE.json configs[3] at reduced N: inner product over d=1536 fp16 rows, k=100 (one
-    shard's arithmetic; the 8-shard exchange is covered by test_gpu_multi / test_sharding_gloo)."""
-    T = t()
-    n, dims, k, seed = 200_000, 1536, 100, 0x70570204
-    Q = oracle.synth_rows(seed + 1, 0, 3, dims)
-    with T.GpuVectorIndex(dims, 1, capacity_rows=n, dev_dtype=2, k_max=128, nq_max=8) as ix:
-        ix.append_synthetic(seed, n)
-        ids, dist, cnt = ix.search(Q, k)
-        for q in range(3):
-            oi, od = oracle.search_synth(seed, n, dims, 2, Q[q], 1, k)
-            assert_same(ids, dist, cnt, q, oi, od, k, f"c4 q{q}")
