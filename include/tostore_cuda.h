@@ -306,8 +306,10 @@ int32_t tsc_debug_gemm_keys(uint64_t handle, const float *queries, uint32_t nq,
  * host (no GPU needed); must equal CRC-32/IEEE (Crc32.of, btree_page.dart:64-89). */
 uint32_t tsc_selftest_crc32(const uint8_t *data, uint32_t len);
 
-/* self-test hook: the program translation and per-row evaluation of
- * tsc_index_filter_where re-run on host arrays (no GPU needed). col_values is
+/* self-test hook — NOT a fallback: no product entry point calls it, and
+ * tsc_index_filter_where always runs where_eval_kernel on the GPU (TSC_ERR_CUDA without
+ * one). It re-runs the program translation and the per-row evaluator the kernel shares
+ * (a __host__ __device__ function) on host arrays so the CPU test tier can pin them. col_values is
  * [n_cols][n_rows] raw 8-byte values, col_is_null [n_cols][n_rows] bytes, out_match
  * [n_rows] bytes. */
 int32_t tsc_selftest_where(const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
