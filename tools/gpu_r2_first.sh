@@ -11,7 +11,7 @@ which dart flutter 2>&1 | tee -a $L      # a Dart SDK on the box would let the r
 echo "== pytest gpu (default)" | tee -a $L
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee -a $L
 echo "== pytest gpu (experimental paths)" | tee -a $L
-TSC_TEST_TF32=1 TSC_TEST_SPARSE_PF=1 timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py -m gpu -q -k "tf32 or sparse" 2>&1 | tail -12 | tee -a $L
+TSC_TEST_TF32=1 TSC_TEST_SPARSE_PF=1 TSC_TEST_PROPERTY=1 timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_parity.py tests/test_round1_late_gpu.py -m gpu -q -k "tf32 or sparse or property" 2>&1 | tail -12 | tee -a $L
 echo "== C example" | tee -a $L
 gcc -std=c99 -I include examples/minimal.c -L tostore_b200 -ltostore_cuda -Wl,-rpath,$PWD/tostore_b200 -lm -o /tmp/minimal && /tmp/minimal 2>&1 | tee -a $L
 echo "== C++ host layer demo" | tee -a $L
