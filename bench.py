@@ -12,7 +12,8 @@ A "step" is one single-query search over the whole corpus (one scan pass +
 select/re-rank). N>1 (torchrun, one rank per GPU): the same 10M-row corpus is
 row-range sharded across ranks (strong scaling); every step each rank scans its
 shard, the per-shard exact top-k are exchanged with one ncclAllGather inside the
-library and merged on every rank.
+library and merged on every rank. `--mode replicas` (not the default) instead gives every
+GPU a full copy of the corpus and its own stream of queries: no exchange, weak scaling.
 
 Prints ONE JSON line on rank 0.
 """
@@ -47,6 +48,10 @@ def parse_args():
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+                    help="N>1: row-range shards of ONE corpus with a top-k exchange per query (default, "
+                         "what BASELINE's north_star asks for) or N independent full replicas, each "
+                         "serving its own queries (no exchange; the corpus fits one GPU)")
     ap.add_argument("--exchange", default=os.environ.get("TSC_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
                     help="N>1: ncclAllGather + merge (default, measured) or the experimental "
                          "one-kernel exchange over NVLink peer memory")
@@ -212,12 +217,17 @@ def run_b200(args):
     n, d, k = args.rows, args.dims, args.k
     steps, warmup = args.steps, max(args.warmup, 3)
     # row-range sharding: contiguous node-id ranges, aligned to 32 rows
+    replicas = world > 1 and args.mode == "replicas"
     per = ((n + world - 1) // world + 31) // 32 * 32
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    if replicas:
+        lo, hi = 0, n
     ix = GpuVectorIndex(d, METRIC_L2, capacity_rows=max(hi - lo, 1), device_id=local,
                         first_node_id=lo, k_max=16, nq_max=8)
     ix.append_synthetic(SEED, hi - lo, first_node_id=lo)
-    if world > 1 and args.exchange == "p2p":
+    if replicas:
+        pass                                            # no exchange step at all
+    elif world > 1 and args.exchange == "p2p":
         ix.comm_init_p2p(dist, world, rank)
     elif world > 1:
         uid = [GpuVectorIndex.comm_unique_id() if rank == 0 else None]
@@ -225,7 +235,8 @@ def run_b200(args):
         ix.comm_init(uid[0], world, rank)
 
     nqs = steps + warmup
-    q_host = torch.from_numpy(oracle.synth_rows(SEED + 1, 0, nqs, d)).pin_memory()
+    # replicas serve different queries; shards of one corpus all see the same query
+    q_host = torch.from_numpy(oracle.synth_rows(SEED + 1, (rank * nqs) if replicas else 0, nqs, d)).pin_memory()
     q_dev = q_host.cuda()
     o_ids = torch.empty((nqs, k), dtype=torch.int64, device="cuda")
     o_dist = torch.empty((nqs, k), dtype=torch.float64, device="cuda")
@@ -240,7 +251,7 @@ def run_b200(args):
     def step_device(i):
         ix.search_device(q_dev.data_ptr() + i * esz, 1, k, o_ids.data_ptr() + i * k * 8,
                          o_dist.data_ptr() + i * k * 8, o_cnt.data_ptr() + i * 4,
-                         stream=sptr, sharded=world > 1)
+                         stream=sptr, sharded=world > 1 and not replicas)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -281,7 +292,7 @@ def run_b200(args):
     dq1 = torch.empty((d,), dtype=torch.float32, device="cuda")
 
     def step_e2e(i):
-        if world == 1:
+        if world == 1 or replicas:
             return ix.search(q_host[i].numpy(), k)          # tsc_search: H2D + kernels + D2H inside
         # sharded: pinned host query -> device, library search+all-gather+merge, results -> host
         dq1.copy_(q_host[i], non_blocking=True)
@@ -327,14 +338,19 @@ def run_b200(args):
         achieved = hot_bytes / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
         traffic, traffic_src = ncu_traffic(n, d, world)
         line = {
-            "metric": METRIC_NAME, "value": steps / (total_ms * 1e-3), "unit": "queries/s",
+            # replicas: every rank answers one query per step
+            "metric": METRIC_NAME, "value": steps * (world if replicas else 1) / (total_ms * 1e-3),
+            "unit": "queries/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
+            "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"single-query L2, N={n} d={d} fp32, k={k} (BASELINE config 2)",
                        "implementation": f"HBM-bound scan + in-kernel top-k + exact fp64 re-rank on {world}xB200",
-                       "rows_per_gpu": hi - lo, "sharding": "row-range" if world > 1 else "none",
-                       "exchange": ("none" if world == 1 else
+                       "rows_per_gpu": hi - lo,
+                       "sharding": "replicas (each GPU holds the whole corpus and serves its own queries)"
+                       if replicas else ("row-range" if world > 1 else "none"),
+                       "exchange": ("none" if world == 1 or replicas else
                                     "one-kernel push over NVLink peer memory (experimental)"
                                     if args.exchange == "p2p" else
                                     "ncclAllGather of per-shard top-k (in-library)"),
@@ -352,10 +368,10 @@ def run_b200(args):
                          "kernel": "scan_topk_kernel<L2,f32,QB=1>",
                          "kernel_ms": hot_ms, "algorithmic_bytes_per_launch": hot_bytes,
                          "kernel_share_of_step": hot_ms / (total_ms / steps) if total_ms else None},
-            "e2e": {"value": steps / (e2e_ms * 1e-3), "unit": "queries/s",
+            "e2e": {"value": steps * (world if replicas else 1) / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": k * 16 + 4,
                     "ms_per_step": e2e_ms / steps,
-                    "api": "tsc_search (host buffers)" if world == 1 else
+                    "api": "tsc_search (host buffers)" if world == 1 or replicas else
                            "pinned H2D + tsc_search_sharded + D2H"},
             "gpu_launches": int(launches),
             "clocks": clocks,
