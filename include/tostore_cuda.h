@@ -242,6 +242,14 @@ int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len,
                           uint32_t k, double distance_threshold, int64_t *out_ids,
                           double *out_dist, double *out_score, uint32_t *out_count);
 
+/* Batch form (additive; the reference's API is single-query): nq query vectors of `len`
+ * values each [nq][len], prepared like single queries and searched in one call (the
+ * tensor-core path for 16-bit columns and nq >= 9). out_ids / out_dist / out_score are
+ * [nq][k], out_counts [nq]. */
+int32_t tsc_vector_search_batch(uint64_t handle, const double *values, uint64_t len, uint32_t nq,
+                                uint32_t k, double distance_threshold, int64_t *out_ids,
+                                double *out_dist, double *out_score, uint32_t *out_counts);
+
 /* ---- nodeId -> primary key side table. Takes the place of the
  * `<index>__nid2pk` B+Tree lookups after the engine call
  * (core/vector_index_manager.dart:553-588; maintained at flush :1276-1293): a dense
@@ -317,6 +325,11 @@ int32_t tsc_selftest_where(const tsc_where_op *ops, uint32_t n_ops, const void *
                            const uint8_t *col_types, const uint64_t *col_values,
                            const uint8_t *col_is_null, uint64_t n_rows, uint8_t *out_match);
 
+/* self-test hooks (no GPU, not fallbacks): the host-side query preparation (_toFloat32 +
+ * _normalizeFloat32) and score mapping (_distanceToScore) of tsc_vector_search. */
+int32_t tsc_selftest_query_prep(uint32_t dims, int32_t metric, const double *values, uint64_t len,
+                                float *out_f32);
+double tsc_selftest_distance_to_score(int32_t metric, double distance);
 /* self-test hook (no GPU): the directory walk / chunking / double-buffered reader of
  * tsc_index_load_ngh with a host sink that records, per chunk, the first logical page, the
  * page count and the CRC-32 of the chunk's bytes. category 0 = rawvec, 1 = graph. */

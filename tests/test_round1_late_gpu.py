@@ -199,3 +199,34 @@ def test_property_random_shapes_equal_oracle(n, dims, k, metric, dt, seed, p_dea
         assert (bits(dist[0, : len(od)]) == bits(od)).all()
         uniq = np.r_[True, od[1:] != od[:-1]] & np.r_[od[:-1] != od[1:], True] if len(od) > 1 else np.ones(len(od), bool)
         assert (ids[0, : len(oi)][uniq] == oi[uniq]).all()
+
+
+@pytest.mark.parametrize("dt", [0, 1])
+def test_store_batch_search_equals_single_searches(dt):
+    """`vectorSearchBatch` (additive): every per-query list equals what `vectorSearch` returns
+    for that query — on an fp32 column (scan passes) and on a bf16 column (tcgen05 GEMM path
+    for the 40-query batch, scan for the single queries)."""
+    T = t()
+    n, d, k, nq = 5000, 64, 7, 40
+    rows = oracle.synth_rows(95, 0, n, d)
+    Q = oracle.synth_rows(96, 0, nq, d).astype(np.float64)
+    Q[3, 40:] = 0.0
+    st = T.GpuVectorStore(capacity_rows=8192, device_dtype=T.DeviceDType(dt))
+    try:
+        st.createVectorIndex("t", "e", T.VectorFieldConfig(d, T.VectorPrecision.float32),
+                             T.VectorIndexConfig(T.VectorDistanceMetric.cosine))
+        st.batchInsert("t", [{"id": f"k{i}", "e": T.VectorData.fromList(rows[i])} for i in range(n)])
+        st.delete("t", ["k17", "k4000"])
+        qvs = [T.VectorData.fromList(q) for q in Q]
+        qvs[5] = T.VectorData.fromList(Q[5][:30])               # short query: zero-padded
+        batch = st.vectorSearchBatch("t", fieldName="e", queryVectors=qvs, topK=k)
+        assert len(batch) == nq
+        for i in range(nq):
+            single = st.vectorSearch("t", fieldName="e", queryVector=qvs[i], topK=k)
+            assert [r.primaryKey for r in batch[i]] == [r.primaryKey for r in single], i
+            assert [r.distance for r in batch[i]] == [r.distance for r in single], i
+            assert [r.score for r in batch[i]] == [r.score for r in single], i
+            assert "k17" not in [r.primaryKey for r in batch[i]]
+        assert st.vectorSearchBatch("t", fieldName="nope", queryVectors=qvs[:2], topK=k) == [[], []]
+    finally:
+        st.close()

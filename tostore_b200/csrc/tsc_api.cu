@@ -885,22 +885,16 @@ int32_t tsc_search(uint64_t handle, const float *queries, uint32_t nq, uint32_t 
   return tsc_search_wait(t);
 }
 
-// VectorIndexManager.vectorSearch's arithmetic around the engine call.
-int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len, uint32_t k,
-                          double threshold, int64_t *out_ids, double *out_dist,
-                          double *out_score, uint32_t *out_count) {
-  Index *ix = lookup(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
-  if ((!values && len) || !out_ids || !out_dist || !out_score || !out_count) {
-    set_error("vector_search: NULL buffer");
-    return TSC_ERR_BAD_ARG;
-  }
-  const uint32_t dims = ix->desc.dims;
-  const int metric = ix->desc.metric;
-  std::vector<float> q(dims, 0.0f);  // _toFloat32, vector_index_manager.dart:1385-1392
-  uint64_t n = len < dims ? len : dims;
+// ---- VectorIndexManager.vectorSearch's arithmetic around the engine call --------------------
+// _toFloat32 (vector_index_manager.dart:1385-1392): truncate / zero-pad to dims, fp64 -> fp32
+// round to nearest even; cosine: _normalizeFloat32 (:1395-1408), magnitude in fp64 over the
+// fp32 values, zero vector unchanged.
+static void prep_query_f32(uint32_t dims, int metric, const double *values, uint64_t len,
+                           float *q) {
+  const uint64_t n = len < dims ? len : dims;
   for (uint64_t i = 0; i < n; i++) q[i] = (float)values[i];
-  if (metric == TSC_METRIC_COSINE) {  // _normalizeFloat32, :1395-1408
+  for (uint64_t i = n; i < dims; i++) q[i] = 0.0f;
+  if (metric == TSC_METRIC_COSINE) {
     double mag = 0;
     for (uint32_t i = 0; i < dims; i++) mag += (double)q[i] * (double)q[i];
     mag = sqrt(mag);
@@ -909,25 +903,65 @@ int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len, u
       for (uint32_t i = 0; i < dims; i++) q[i] = (float)((double)q[i] * inv);
     }
   }
-  int32_t rc = tsc_search(handle, q.data(), 1, k, threshold, out_ids, out_dist, out_count);
-  if (rc != TSC_OK) return rc;
-  for (uint32_t j = 0; j < k; j++) {  // _distanceToScore, :1411-1423
-    double d = out_dist[j], s;
-    if (j >= *out_count) {
-      out_score[j] = NAN;
-      continue;
-    }
-    if (metric == TSC_METRIC_L2) {
-      s = 1.0 / (1.0 + d);
-    } else if (metric == TSC_METRIC_INNER_PRODUCT) {
-      s = 1.0 / (1.0 + exp(-(-d)));
-    } else {
-      s = 1.0 - d;
-      if (s == s) s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
-    }
-    out_score[j] = s;
+}
+
+// _distanceToScore (:1411-1423)
+static double distance_to_score(int metric, double d) {
+  if (metric == TSC_METRIC_L2) return 1.0 / (1.0 + d);
+  if (metric == TSC_METRIC_INNER_PRODUCT) return 1.0 / (1.0 + exp(d));   // d = -dot
+  double s = 1.0 - d;
+  if (s == s) s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+  return s;
+}
+
+int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len, uint32_t k,
+                          double threshold, int64_t *out_ids, double *out_dist,
+                          double *out_score, uint32_t *out_count) {
+  return tsc_vector_search_batch(handle, values, len, 1, k, threshold, out_ids, out_dist, out_score,
+                                 out_count);
+}
+
+// Batch form (additive: the reference's API is single-query): nq query vectors of `len`
+// values each, prepared like single queries, searched in one call (the tcgen05 GEMM path for
+// 16-bit columns and nq >= 9), scored. out_* are [nq][k], out_counts [nq].
+int32_t tsc_vector_search_batch(uint64_t handle, const double *values, uint64_t len, uint32_t nq,
+                                uint32_t k, double threshold, int64_t *out_ids, double *out_dist,
+                                double *out_score, uint32_t *out_counts) {
+  Index *ix = lookup(handle);
+  if (!ix) return TSC_ERR_BAD_HANDLE;
+  if ((!values && len) || !out_ids || !out_dist || !out_score || !out_counts || nq == 0) {
+    set_error("vector_search: NULL buffer or nq == 0");
+    return TSC_ERR_BAD_ARG;
   }
+  const uint32_t dims = ix->desc.dims;
+  const int metric = ix->desc.metric;
+  std::vector<float> q((size_t)nq * dims);
+  for (uint32_t i = 0; i < nq; i++)
+    prep_query_f32(dims, metric, values ? values + (size_t)i * len : nullptr, len,
+                   q.data() + (size_t)i * dims);
+  int32_t rc = tsc_search(handle, q.data(), nq, k, threshold, out_ids, out_dist, out_counts);
+  if (rc != TSC_OK) return rc;
+  for (uint32_t i = 0; i < nq; i++)
+    for (uint32_t j = 0; j < k; j++) {
+      const size_t o = (size_t)i * k + j;
+      out_score[o] = j < out_counts[i] ? distance_to_score(metric, out_dist[o]) : NAN;
+    }
   return TSC_OK;
+}
+
+// Self-test hooks (no GPU, not fallbacks): the query preparation and the score mapping above,
+// so the CPU tier can pin them bit for bit against the oracle's restatement.
+int32_t tsc_selftest_query_prep(uint32_t dims, int32_t metric, const double *values, uint64_t len,
+                                float *out_f32) {
+  if (!out_f32 || dims == 0 || (!values && len)) {
+    set_error("selftest_query_prep: bad argument");
+    return TSC_ERR_BAD_ARG;
+  }
+  prep_query_f32(dims, metric, values, len, out_f32);
+  return TSC_OK;
+}
+double tsc_selftest_distance_to_score(int32_t metric, double distance) {
+  return distance_to_score(metric, distance);
 }
 
 // ---- sharding -------------------------------------------------------------------

@@ -234,6 +234,25 @@ class GpuVectorIndex:
         n = cnt.value
         return ids[:n], dist[:n], score[:n]
 
+    def vector_search_batch(self, values, k: int, threshold: Optional[float] = None):
+        """Batch form of `vector_search` (additive): values [nq, len] fp64, every query
+        prepared like a single one, one search call (tensor-core path for 16-bit columns and
+        nq >= 9). Returns (ids [nq,k], dist [nq,k], score [nq,k], counts [nq])."""
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        if v.ndim != 2:
+            raise ValueError("values must be [nq, len]")
+        nq = v.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        score = np.empty((nq, k), dtype=np.float64)
+        counts = np.empty(nq, dtype=np.uint32)
+        thr = math.nan if threshold is None else float(threshold)
+        N.check(self._lib.tsc_vector_search_batch(self.handle, v.ctypes.data, v.shape[1], nq, k, thr,
+                                                  ids.ctypes.data, dist.ctypes.data,
+                                                  score.ctypes.data, counts.ctypes.data),
+                "tsc_vector_search_batch")
+        return ids, dist, score, counts
+
     # -- nodeId -> primary key side table (role of `__nid2pk`) ------------------------
     def set_primary_keys(self, pks, first_node_id: Optional[int] = None) -> None:
         """pks: sequence of str (None / '' = tombstone mapping) for consecutive node ids."""

@@ -284,6 +284,36 @@ class GpuVectorStore:
         return [VectorSearchResult(primaryKey=pk, distance=d, score=s)
                 for pk, d, s in zip(pks, dist.tolist(), score.tolist())]   # ascending (:587)
 
+    def vectorSearchBatch(self, tableName: str, *, fieldName: str, queryVectors: Sequence[VectorData],
+                          topK: int = 10, distanceThreshold: Optional[float] = None
+                          ) -> List[List[VectorSearchResult]]:
+        """Batch form of `vectorSearch` (additive; the reference's API is single-query): one
+        result list per query vector, each exactly what `vectorSearch` would return. Queries
+        are truncated / zero-padded to the field's dimensions like single ones."""
+        ix = self._find(tableName, fieldName)
+        if ix is None or not ix.nid2pk or not queryVectors:
+            return [[] for _ in queryVectors]
+        dims = ix.field.dimensions
+        vals = np.zeros((len(queryVectors), dims), dtype=np.float64)
+        for i, qv in enumerate(queryVectors):
+            v = np.asarray(qv.values if isinstance(qv, VectorData) else qv, dtype=np.float64)[:dims]
+            vals[i, : v.size] = v
+        out: List[List[VectorSearchResult]] = []
+        step = ix.engine.nq_max
+        for b in range(0, len(queryVectors), step):
+            ids, dist, score, counts = ix.engine.vector_search_batch(vals[b: b + step], topK, distanceThreshold)
+            for i in range(ids.shape[0]):
+                res = []
+                for j in range(int(counts[i])):
+                    nid = int(ids[i, j])
+                    pk = ix.nid2pk[nid] if 0 <= nid < len(ix.nid2pk) else None
+                    if pk is None:                               # :578-579 (deleted / unmapped)
+                        continue
+                    res.append(VectorSearchResult(primaryKey=pk, distance=float(dist[i, j]),
+                                                  score=float(score[i, j])))
+                out.append(res)
+        return out
+
     def close(self) -> None:
         for lst in self._indexes.values():
             for ix in lst:
