@@ -113,6 +113,10 @@ typedef _SearchPkN = Int32 Function(
 typedef _SearchPkD = int Function(
     int, Pointer<Double>, int, int, double, Pointer<Int64>, Pointer<Double>,
     Pointer<Double>, Pointer<Uint8>, int, Pointer<Uint64>, Pointer<Uint32>);
+typedef _SearchBatchN = Int32 Function(Uint64, Pointer<Double>, Uint64, Uint32, Uint32, Double,
+    Pointer<Int64>, Pointer<Double>, Pointer<Double>, Pointer<Uint32>);
+typedef _SearchBatchD = int Function(int, Pointer<Double>, int, int, int, double,
+    Pointer<Int64>, Pointer<Double>, Pointer<Double>, Pointer<Uint32>);
 typedef _LoadNghN = Int32 Function(Uint64, Pointer<Utf8>, Uint32, Pointer<Void>);
 typedef _LoadNghD = int Function(int, Pointer<Utf8>, int, Pointer<Void>);
 typedef _LastErrorN = Pointer<Utf8> Function();
@@ -450,6 +454,42 @@ class TostoreCuda {
       return fn(handle, dir, tombstones ? 1 : 0, nullptr) == 0;
     } finally {
       calloc.free(dir);
+    }
+  }
+  /// Batch form of the search (additive; `ToStore.vectorSearch` stays single-query):
+  /// `queries` are equally long fp64 vectors; returns per query the (nodeId, distance, score)
+  /// triples in ascending distance order. [] on error.
+  static List<List<(int, double, double)>> vectorSearchBatch(
+      int handle, List<List<double>> queries, int topK,
+      {double? distanceThreshold}) {
+    final lib = _open();
+    if (lib == null || topK <= 0 || queries.isEmpty) return const [];
+    final fn = lib.lookupFunction<_SearchBatchN, _SearchBatchD>('tsc_vector_search_batch');
+    final nq = queries.length, len = queries.first.length;
+    final q = calloc<Double>(nq * (len == 0 ? 1 : len));
+    final ids = calloc<Int64>(nq * topK);
+    final dist = calloc<Double>(nq * topK);
+    final score = calloc<Double>(nq * topK);
+    final counts = calloc<Uint32>(nq);
+    try {
+      for (var i = 0; i < nq; i++) {
+        for (var c = 0; c < len && c < queries[i].length; c++) {
+          q[i * len + c] = queries[i][c];
+        }
+      }
+      if (fn(handle, q, len, nq, topK, distanceThreshold ?? double.nan, ids, dist, score, counts) != 0) {
+        return const [];
+      }
+      return [
+        for (var i = 0; i < nq; i++)
+          [for (var j = 0; j < counts[i]; j++) (ids[i * topK + j], dist[i * topK + j], score[i * topK + j])]
+      ];
+    } finally {
+      calloc.free(q);
+      calloc.free(ids);
+      calloc.free(dist);
+      calloc.free(score);
+      calloc.free(counts);
     }
   }
 }

@@ -21,6 +21,7 @@
 #ifndef TOSTORE_VECTOR_HPP
 #define TOSTORE_VECTOR_HPP
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -433,6 +434,43 @@ class GpuVectorStore {
     for (uint32_t j = 0; j < count; j++)
       out.push_back({std::string((const char *)pks.data() + offs[j], (size_t)(offs[j + 1] - offs[j])), dist[j], score[j]});
     return out;                                        // ascending distance (:587)
+  }
+
+  // Batch form (additive; the reference's API is single-query): one result list per query,
+  // each what vectorSearch would return; one library call (tensor-core path for 16-bit
+  // columns and >= 9 queries).
+  std::vector<std::vector<VectorSearchResult>> vectorSearchBatch(
+      const std::string &tableName, const std::string &fieldName, const std::vector<VectorData> &queryVectors,
+      int topK = 10, std::optional<double> distanceThreshold = std::nullopt) {
+    std::vector<std::vector<VectorSearchResult>> out(queryVectors.size());
+    Index *ix = find(tableName, fieldName);
+    if (!ix || ix->nextNodeId == 0 || topK <= 0 || queryVectors.empty()) return out;
+    const size_t dims = (size_t)ix->field.dimensions, k = (size_t)topK;
+    for (size_t b = 0; b < queryVectors.size(); b += 64) {          // nq_max of the index
+      const size_t nq = std::min<size_t>(64, queryVectors.size() - b);
+      std::vector<double> vals(nq * dims, 0.0);
+      for (size_t i = 0; i < nq; i++) {
+        const auto &v = queryVectors[b + i].values;
+        for (size_t c = 0; c < v.size() && c < dims; c++) vals[i * dims + c] = v[c];
+      }
+      std::vector<int64_t> ids(nq * k);
+      std::vector<double> dist(nq * k), score(nq * k);
+      std::vector<uint32_t> counts(nq);
+      check(tsc_vector_search_batch(ix->handle, vals.data(), dims, (uint32_t)nq, (uint32_t)k,
+                                    distanceThreshold ? *distanceThreshold : std::nan(""), ids.data(),
+                                    dist.data(), score.data(), counts.data()),
+            "tsc_vector_search_batch");
+      for (size_t i = 0; i < nq; i++)
+        for (uint32_t j = 0; j < counts[i]; j++) {
+          uint8_t pk[4096];
+          uint32_t len = 0;
+          check(tsc_index_get_primary_key(ix->handle, (uint64_t)ids[i * k + j], pk, sizeof pk, &len),
+                "tsc_index_get_primary_key");
+          if (len == 0) continue;                                    // unmapped / tombstoned (:578-579)
+          out[b + i].push_back({std::string((const char *)pk, len), dist[i * k + j], score[i * k + j]});
+        }
+    }
+    return out;
   }
 
   void close() {
