@@ -28,8 +28,28 @@
  * Conventions (mirroring lib/src/handler/system_ffi_helper.dart): every buffer
  * is caller-allocated and caller-freed; int32 status, 0 = success, negative =
  * tsc_status; handles are opaque uint64 (safe to pass between isolates).
- * Thread-safe per handle (internal mutex). There is NO CPU fallback: without a
- * usable CUDA device every compute entry point returns TSC_ERR_CUDA.
+ * Thread-safe per handle (internal mutex): searches on one handle are serialised —
+ * a second blocking search waits for the first, a second tsc_search_submit first
+ * retires the ticket in flight (its results are delivered to its buffers) — and
+ * device-buffer searches on different streams are ordered by an event, because a
+ * handle owns one set of search scratch. No exception crosses the boundary.
+ * There is NO CPU fallback: without a usable CUDA device every compute entry point
+ * returns TSC_ERR_CUDA.
+ *
+ * One process can own all GPUs of a box: tsc_index_create with n_devices = 2..8
+ * returns a GROUP handle — the embedding column is row-range sharded over the
+ * devices, every entry point that takes HOST buffers (append, load, filter, WHERE,
+ * tsc_search, tsc_vector_search*, primary keys, stats) works on it unchanged, and
+ * one tsc_search call scans all shards and merges their exact top-k on the first
+ * device through NVLink peer memory. That is the form the single-process Dart host
+ * binds (call site core/vector_index_manager.dart:538-548). The one-process-per-GPU
+ * form (tsc_comm_*, tsc_search_sharded) exists for torchrun-style launches.
+ *
+ * Exactness: candidates are chosen by an fp32 key and re-ranked in exact fp64; the
+ * library PROVES per query that no row outside the candidates can belong to the
+ * result (certificate) and otherwise re-runs the query in range mode,
+ * which collects every row the key error bound cannot exclude. tsc_stats reports
+ * certified / retried / uncertified query counts.
  */
 #ifndef TOSTORE_CUDA_H
 #define TOSTORE_CUDA_H
@@ -41,7 +61,7 @@
 extern "C" {
 #endif
 
-#define TSC_ABI_VERSION 1
+#define TSC_ABI_VERSION 2
 
 typedef enum tsc_status {
   TSC_OK = 0,
@@ -75,7 +95,10 @@ typedef struct tsc_index_desc {
   uint64_t first_node_id;  /* nodeId of shard row 0 (row-range sharding)         */
   uint32_t k_max;          /* largest topK that will be requested (<= 128)       */
   uint32_t nq_max;         /* largest query batch per call                       */
-} tsc_index_desc;
+  uint32_t n_devices;      /* 0 / 1: one shard on device_id. 2..8: a GROUP — the  */
+  int32_t device_ids[8];   /* column is row-range sharded over device_ids[0..n),  */
+  uint32_t reserved1;      /* capacity_rows / first_node_id describe the WHOLE    */
+} tsc_index_desc;          /* column; device_id is ignored                        */
 
 typedef struct tsc_stats {
   uint32_t struct_size;
@@ -96,6 +119,14 @@ typedef struct tsc_stats {
   double hot_ms_total;       /* sum of their device durations                  */
   double hot_bytes_total;    /* algorithmic bytes they covered (rows*dims*elem)*/
   double hot_flops_total;    /* algorithmic flops (GEMM path), else 0          */
+  /* exactness certificate (per query, since creation / tsc_stats_reset) */
+  uint64_t certified_queries;   /* first pass proven complete                  */
+  uint64_t retried_queries;     /* re-run in range mode, exact afterwards      */
+  uint64_t uncertified_queries; /* more near-ties than the range pass holds
+                                   (4096 rows): best-effort result            */
+  uint64_t range_rows;          /* rows the range passes re-ranked             */
+  uint32_t n_devices;           /* 1, or the shard count of a group            */
+  uint32_t reserved2;
 } tsc_stats;
 
 /* ---- library ---- */
@@ -218,6 +249,8 @@ int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_
  * distance_threshold: NaN = none; results with distance > threshold are dropped.
  * out_ids [nq*k] (-1 padded), out_dist [nq*k] ascending (NaN padded),
  * out_counts [nq]. HOST buffers; blocks until the results are written. */
+/* On a group handle, or on a shard whose exchange has been set up (tsc_comm_*), this
+ * is the SHARDED search: out_* receive the global result (on the consumer ranks). */
 int32_t tsc_search(uint64_t handle, const float *queries, uint32_t nq, uint32_t k,
                    double distance_threshold, int64_t *out_ids, double *out_dist,
                    uint32_t *out_counts);
@@ -270,6 +303,13 @@ int32_t tsc_vector_search_pk(uint64_t handle, const double *values, uint64_t len
                              double *out_score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
                              uint64_t *out_pk_offsets, uint32_t *out_count);
 
+/* Per-query verdict of the exactness certificate for the LAST search on the handle:
+ * 0 = exact (certified, possibly after a range pass), 1 = a range pass is still owed
+ * (device-buffer searches with more uncertified queries than the in-stream range
+ * launches cover; the host-buffer calls never return this), 2 = uncertified (more
+ * than 4096 rows tie with the k-th neighbour within the key error bound). */
+int32_t tsc_search_flags(uint64_t handle, uint32_t nq, uint32_t *out_flags);
+
 /* ---- row-range sharding across GPUs (one process per GPU) ---- */
 /* Merge n_parts per-shard results ([n_parts, nq, k] ids/dist as produced by
  * tsc_search_device on each shard and all-gathered by the caller or by
@@ -290,14 +330,17 @@ int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
                            int64_t *d_out_ids, double *d_out_dist,
                            uint32_t *d_out_counts, void *cuda_stream);
 
-/* Experimental alternative to tsc_comm_init (not yet measured): the
- * exchange + merge as ONE kernel over NVLink peer memory — every rank pushes its k pairs
- * straight into the peers' receive buffers and spins on release flags — instead of
- * ncclAllGather + merge. One process per GPU. export returns this rank's 64-byte CUDA IPC
- * handle; the caller all-gathers the n_ranks handles (any host transport) and hands the
- * [n_ranks][64] array to import; afterwards tsc_search_sharded takes this path. */
+/* The exchange over NVLink peer memory (preferred; tsc_comm_init remains as the NCCL form):
+ * every rank pushes its k pairs straight into the consumers' receive buffers and publishes
+ * release flags; for nq <= 8 this happens in the scan kernel's last CTA, so scan + select
+ * + re-rank + exchange + merge is ONE kernel launch. One process per GPU. export returns
+ * this rank's 64-byte CUDA IPC handle; the caller all-gathers the n_ranks handles (any
+ * host transport) and hands the [n_ranks][64] array to import; afterwards
+ * tsc_search_sharded / tsc_search take this path. root = -1: every rank receives the
+ * global result (all-gather semantics); root = r: only rank r does — the others never
+ * wait and out_* on them is left untouched. */
 int32_t tsc_comm_p2p_export(uint64_t handle, int32_t n_ranks, int32_t rank, uint8_t *out_ipc64);
-int32_t tsc_comm_p2p_import(uint64_t handle, const uint8_t *all_ipc);
+int32_t tsc_comm_p2p_import(uint64_t handle, const uint8_t *all_ipc, int32_t root);
 
 /* ---- observability ---- */
 int32_t tsc_stats_get(uint64_t handle, tsc_stats *out);

@@ -109,25 +109,16 @@ def test_full_size_c3_properties():
             assert better <= set(ids[qi].tolist()) | set(planted.values())
 
 
-# ---- opt-in: fp32 column multiplied as tf32 on the tensor cores (TSC_GEMM_TF32=1) ------------
-# Written without a GPU at hand (round 1 ran out of GPU budget): these tests only run when
-# TSC_TEST_TF32=1 is exported, until the path has been verified on a B200.
-import os  # noqa: E402
-
-_tf32 = pytest.mark.skipif(os.environ.get("TSC_TEST_TF32") != "1",
-                           reason="experimental tf32 path: set TSC_TEST_TF32=1 to run")
-
+# ---- fp32 column multiplied as tf32 on the tensor cores (batches of >= 9 queries) ------------
 
 def _tf32_trunc(a):
     """What kind::tf32 reads from an fp32 operand: the low 13 mantissa bits are ignored."""
     return (np.ascontiguousarray(a, dtype=np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
-@_tf32
 @pytest.mark.parametrize("dims,n,nq", [(32, 300, 5), (128, 1000, 130), (768, 777, 64), (100, 513, 257)])
-def test_tf32_keys_match_matmul(dims, n, nq, monkeypatch):
+def test_tf32_keys_match_matmul(dims, n, nq):
     import tostore_b200 as T
-    monkeypatch.setenv("TSC_GEMM_TF32", "1")
     rng = np.random.default_rng(dims + n)
     rows = rng.standard_normal((n, dims)).astype(np.float32)
     q = rng.standard_normal((nq, dims)).astype(np.float32)
@@ -143,11 +134,9 @@ def test_tf32_keys_match_matmul(dims, n, nq, monkeypatch):
             assert (np.abs(keys - ref) <= tol).all(), (metric, dims, np.abs(keys - ref).max())
 
 
-@_tf32
 @pytest.mark.parametrize("metric", [0, 1, 2])
-def test_tf32_path_parity_with_oracle(metric, monkeypatch):
+def test_tf32_path_parity_with_oracle(metric):
     import tostore_b200 as T
-    monkeypatch.setenv("TSC_GEMM_TF32", "1")
     n, dims, nq, k = 20000, 256, 200, 10
     rows = oracle.synth_rows(61, 0, n, dims)
     Q = oracle.synth_rows(62, 0, nq, dims)

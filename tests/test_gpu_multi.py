@@ -55,10 +55,9 @@ def _worker(rank, world, port, ret, exchange="nccl"):
         dist.destroy_process_group()
 
 
-# exchange="p2p": the one-kernel exchange over NVLink peer memory (tsc_exchange.cuh), written
-# without a GPU at hand — runs only with TSC_TEST_P2P=1 until verified on a multi-GPU box
-@pytest.mark.parametrize("exchange", ["nccl", pytest.param("p2p", marks=pytest.mark.skipif(
-    os.environ.get("TSC_TEST_P2P") != "1", reason="experimental: set TSC_TEST_P2P=1"))])
+# exchange="p2p": push over NVLink peer memory fused into the scan kernel's tail
+# (tsc_exchange.cuh); "nccl": ncclAllGather + merge kernel
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 def test_sharded_search_nccl_all_gather(exchange):
     import torch
     if torch.cuda.device_count() < 2:

@@ -343,16 +343,10 @@ def test_full_size_c2_properties():
         assert st.last_path == 1 and st.last_search_ms > 0
 
 
-# pf=True: the prefetching block cursor of K6 (TSC_SCAN_SPARSE_PF=1), written without a GPU
-# at hand — runs only with TSC_TEST_SPARSE_PF=1 until it has been verified on a B200
-@pytest.mark.parametrize("pf", [False, pytest.param(True, marks=pytest.mark.skipif(
-    os.environ.get("TSC_TEST_SPARSE_PF") != "1", reason="experimental: set TSC_TEST_SPARSE_PF=1"))])
 @pytest.mark.parametrize("dt,dims", [(0, 384), (1, 256), (0, 100)])
-def test_sparse_where_filter_uses_per_row_scan(dt, dims, pf, monkeypatch):
+def test_sparse_where_filter_uses_per_row_scan(dt, dims):
     """Low-selectivity WHERE bitmap -> per-live-row bulk copies (K6); same results as the oracle."""
     T = t()
-    if pf:
-        monkeypatch.setenv("TSC_SCAN_SPARSE_PF", "1")       # read at index creation
     n, k = 60000, 10
     rows = onp.round_dev(oracle.synth_rows(71, 0, n, dims), dt)
     Q = oracle.synth_rows(72, 0, 5, dims)

@@ -159,13 +159,10 @@ def test_native_loader_load_and_search(tmp_path, prec):
 
 
 # ---- property test of the whole search path ---------------------------
-# Random small shapes hit corners the fixed cases do not; gated until it has been run once on
-# a B200 (set TSC_TEST_PROPERTY=1), because a counter-example found at round end could not be
-# looked at.
+# Random small shapes hit corners the fixed cases do not.
 from hypothesis import HealthCheck, given, settings, strategies as st   # noqa: E402
 
 
-@pytest.mark.skipif(os.environ.get("TSC_TEST_PROPERTY") != "1", reason="set TSC_TEST_PROPERTY=1")
 @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
 @given(st.integers(1, 400), st.integers(1, 70), st.integers(1, 30), st.integers(0, 2), st.integers(0, 2),
        st.integers(0, 10 ** 6), st.floats(0.0, 1.0), st.floats(0.0, 1.0), st.booleans())

@@ -1,6 +1,6 @@
-"""Per-config measurements (BASELINE.json configs 1-5, one GPU's share of the
-sharded ones). Prints one JSON line per config. Usage:
-    python tools/bench_configs.py [c1 c2 c3 c4 c5]"""
+"""Per-config measurements (BASELINE.json configs 1-5, one GPU's share of the sharded ones).
+Importable (bench.py appends `measure_all()` to its JSON line as the `configs` block) and a
+command line:  python tools/bench_configs.py [c1 c2 c3 c4 c5 ...]  -> one JSON line per config."""
 import json
 import os
 import sys
@@ -9,10 +9,6 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
-import oracle  # noqa: E402
-from oracle import oracle_np as onp  # noqa: E402
-from tostore_b200 import GpuVectorIndex  # noqa: E402
-
 PEAKS = {"hbm_gbs": 6545.6, "bf16_tflops": 1622.2, "bf16_tflops_sustained": 1365.6}
 try:
     PEAKS.update(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))))
@@ -20,24 +16,19 @@ except Exception:
     pass
 
 
-def run(name, n, d, metric, dt, nq, k, reps, mask_frac=None, warm=3, env=None, where=False):
-    """env: library switches read at index creation (e.g. TSC_GEMM_TF32, TSC_SCAN_SPARSE_PF);
+def measure(name, n, d, metric, dt, nq, k, reps, mask_frac=None, warm=3, where=False, device_id=0):
+    """One config on one GPU: `reps` searches through tsc_search (host buffers), device time
+    from the library's CUDA events, dominant-kernel time from its per-launch event pairs.
     where: produce the mask on the GPU from two attribute columns (tsc_index_filter_where)
     instead of uploading a bitmap, and time that call."""
-    for key, val in (env or {}).items():
-        os.environ[key] = val
-    try:
-        _run(name, n, d, metric, dt, nq, k, reps, mask_frac, warm, where)
-    finally:
-        for key in (env or {}):
-            os.environ.pop(key, None)
-
-
-def _run(name, n, d, metric, dt, nq, k, reps, mask_frac, warm, where):
+    import oracle
+    from oracle import oracle_np as onp
+    from tostore_b200 import GpuVectorIndex
     Q = oracle.synth_rows(99, 0, nq * (reps + warm), d).reshape(reps + warm, nq, d)
     if metric == 2:
         Q = np.stack([np.stack([onp.normalize_f32(q) for q in b]) for b in Q])
-    with GpuVectorIndex(d, metric, capacity_rows=n, dev_dtype=dt, k_max=max(k, 16), nq_max=max(nq, 8)) as ix:
+    with GpuVectorIndex(d, metric, capacity_rows=n, dev_dtype=dt, k_max=max(k, 16), nq_max=max(nq, 8),
+                        device_id=device_id) as ix:
         ix.append_synthetic(7, n)
         where_ms = None
         if mask_frac is not None and where:
@@ -69,54 +60,54 @@ def _run(name, n, d, metric, dt, nq, k, reps, mask_frac, warm, where):
         wall = (time.perf_counter() - t0) / reps * 1e3
         st = ix.stats()
         hot_ms = st.hot_ms_total / st.hot_launches
-        per_search_launches = st.hot_launches / reps
         out = {"config": name, "n": n, "d": d, "metric": metric, "dev_dtype": dt, "nq": nq, "k": k,
-               "path": st.last_path, "device_ms_per_search": tot / reps, "e2e_ms_per_search": wall,
+               "path": "tensor" if st.last_path == 2 else "scan",
+               "device_ms_per_search": tot / reps, "e2e_ms_per_search": wall,
                "qps_device": nq / (tot / reps) * 1e3, "qps_e2e": nq / wall * 1e3,
-               "hot_kernel_ms": hot_ms, "hot_launches_per_search": per_search_launches,
+               "hot_kernel_ms": hot_ms, "hot_launches_per_search": st.hot_launches / reps,
                "hbm_gbs": st.hot_bytes_total / st.hot_launches / hot_ms / 1e6,
-               "hbm_frac_of_measured": st.hot_bytes_total / st.hot_launches / hot_ms / 1e6 / PEAKS["hbm_gbs"]}
+               "hbm_frac": st.hot_bytes_total / st.hot_launches / hot_ms / 1e6 / PEAKS["hbm_gbs"],
+               "certified": int(st.certified_queries), "retried": int(st.retried_queries),
+               "uncertified": int(st.uncertified_queries)}
         if st.hot_flops_total > 0:
             tf = st.hot_flops_total / st.hot_launches / hot_ms / 1e9
-            out.update(tflops=tf, tensor_frac_of_measured_burst=tf / PEAKS["bf16_tflops"],
-                       tensor_frac_of_measured_sustained=tf / PEAKS["bf16_tflops_sustained"])
+            out.update(tflops=tf, tensor_frac_burst=tf / PEAKS["bf16_tflops"],
+                       tensor_frac_sustained=tf / PEAKS["bf16_tflops_sustained"])
         if mask_frac is not None:
-            out["filtered_bytes_gbs"] = out["hbm_gbs"] * mask_frac
+            out["full_scan_equivalent_gbs"] = out["hbm_gbs"] / mask_frac
         if where_ms is not None:
             # two 8-byte columns read + one bit per row written (tsc_where.cuh)
             out.update(where_ms_incl_sync=where_ms, where_matched=int(matched),
                        where_gbs=n * 16.125 / where_ms / 1e6)
-        print(json.dumps(out), flush=True)
+        return out
 
 
-which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]
-if "c1" in which:
-    run("c1 brute-force L2 10k x 128 fp32 k=10", 10_000, 128, 0, 0, 1, 10, 200)
-if "c2" in which:
-    run("c2 single-query L2 10M x 768 fp32 k=10", 10_000_000, 768, 0, 0, 1, 10, 30)
-if "c2b" in which:
-    run("c2b 8-query L2 10M x 768 fp32 k=10", 10_000_000, 768, 0, 0, 8, 10, 10)
-if "c3" in which:
-    run("c3 batch-1024 cosine 10M x 768 bf16 k=10", 10_000_000, 768, 2, 1, 1024, 10, 10)
-if "c3s" in which:
-    run("c3s single-query cosine 10M x 768 bf16 k=10 (scan)", 10_000_000, 768, 2, 1, 1, 10, 20)
-if "c2t" in which:      # experimental: fp32 column, batch on the tensor cores as tf32
-    run("c2t batch-1024 L2 10M x 768 fp32 k=10 (tf32 tensor path, TSC_GEMM_TF32=1)", 10_000_000, 768, 0, 0,
-        1024, 10, 5, env={"TSC_GEMM_TF32": "1"})
-if "c2b1024" in which:  # what c2t replaces: the scan kernel looped 8 queries per pass
-    run("c2b1024 batch-1024 L2 10M x 768 fp32 k=10 (scan, 128 passes)", 10_000_000, 768, 0, 0, 1024, 10, 2, warm=1)
-if "c4" in which:
-    run("c4 shard: IP 12.5M x 1536 fp16 k=100 (1 of 8 GPUs)", 12_500_000, 1536, 1, 2, 1, 100, 20)
-if "c5" in which:
-    run("c5 shard: L2 12.5M x 384 fp32 k=10, 10% WHERE mask (1 of 4 GPUs)", 12_500_000, 384, 0, 0, 1, 10, 20,
-        mask_frac=0.10)
-    run("c5u shard unfiltered: L2 12.5M x 384 fp32 k=10", 12_500_000, 384, 0, 0, 1, 10, 20)
-if "c5pf" in which:     # experimental: prefetching block cursor in the sparse scan
-    run("c5pf shard: L2 12.5M x 384 fp32 k=10, 10% mask, TSC_SCAN_SPARSE_PF=1", 12_500_000, 384, 0, 0, 1, 10, 20,
-        mask_frac=0.10, env={"TSC_SCAN_SPARSE_PF": "1"})
-    run("c5pf1 shard: 1% mask, TSC_SCAN_SPARSE_PF=1", 12_500_000, 384, 0, 0, 1, 10, 20,
-        mask_frac=0.01, env={"TSC_SCAN_SPARSE_PF": "1"})
-    run("c5s1 shard: 1% mask, default cursor", 12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.01)
-if "c5w" in which:      # mask produced on the GPU by the WHERE kernel from two attribute columns
-    run("c5w shard: L2 12.5M x 384 fp32 k=10, WHERE price<316 AND rating<0.316 (~10%) evaluated on the GPU",
-        12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.10, where=True)
+CONFIGS = {
+    "c1": lambda: [measure("c1 brute-force L2 10k x 128 fp32 k=10", 10_000, 128, 0, 0, 1, 10, 200)],
+    "c2": lambda: [measure("c2 single-query L2 10M x 768 fp32 k=10", 10_000_000, 768, 0, 0, 1, 10, 30)],
+    "c2b": lambda: [measure("c2b 8-query L2 10M x 768 fp32 k=10 (scan, one pass)", 10_000_000, 768, 0, 0, 8, 10, 10)],
+    "c2t": lambda: [measure("c2t batch-1024 L2 10M x 768 fp32 k=10 (tf32 tensor path)", 10_000_000, 768, 0, 0,
+                            1024, 10, 5)],
+    "c3": lambda: [measure("c3 batch-1024 cosine 10M x 768 bf16 k=10", 10_000_000, 768, 2, 1, 1024, 10, 10)],
+    "c3s": lambda: [measure("c3s single-query cosine 10M x 768 bf16 k=10 (scan)", 10_000_000, 768, 2, 1, 1, 10, 20)],
+    "c4": lambda: [measure("c4 shard: IP 12.5M x 1536 fp16 k=100 (1 of 8 GPUs)", 12_500_000, 1536, 1, 2, 1, 100, 20)],
+    "c5": lambda: [measure("c5 shard: L2 12.5M x 384 fp32 k=10, 10% WHERE mask (1 of 4 GPUs)", 12_500_000, 384,
+                           0, 0, 1, 10, 20, mask_frac=0.10),
+                   measure("c5u shard unfiltered: L2 12.5M x 384 fp32 k=10", 12_500_000, 384, 0, 0, 1, 10, 20)],
+    "c5s1": lambda: [measure("c5s1 shard: 1% mask", 12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.01)],
+    "c5w": lambda: [measure("c5w shard: L2 12.5M x 384 fp32 k=10, WHERE price<316 AND rating<0.316 (~10%) "
+                            "evaluated on the GPU", 12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.10, where=True)],
+}
+
+
+def measure_all(which=("c1", "c3", "c4", "c5")):
+    out = []
+    for w in which:
+        out.extend(CONFIGS[w]())
+    return out
+
+
+if __name__ == "__main__":
+    for w in (sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]):
+        for line in CONFIGS[w]():
+            print(json.dumps(line), flush=True)

@@ -19,7 +19,7 @@ EXPORTS = (
     "tsc_index_create", "tsc_index_destroy", "tsc_index_clear",
     "tsc_index_append_rows", "tsc_index_append_pages", "tsc_index_append_synthetic",
     "tsc_index_set_deleted", "tsc_index_apply_graph_pages", "tsc_index_set_filter",
-    "tsc_search", "tsc_search_submit", "tsc_search_poll", "tsc_search_wait",
+    "tsc_search", "tsc_search_submit", "tsc_search_poll", "tsc_search_wait", "tsc_search_flags",
     "tsc_search_device", "tsc_vector_search", "tsc_vector_search_batch", "tsc_merge_shards",
     "tsc_selftest_query_prep", "tsc_selftest_distance_to_score",
     "tsc_comm_unique_id", "tsc_comm_init", "tsc_search_sharded",
@@ -51,6 +51,7 @@ class IndexDesc(C.Structure):
         ("device_id", C.c_int32),
         ("capacity_rows", C.c_uint64), ("first_node_id", C.c_uint64),
         ("k_max", C.c_uint32), ("nq_max", C.c_uint32),
+        ("n_devices", C.c_uint32), ("device_ids", C.c_int32 * 8), ("reserved1", C.c_uint32),
     ]
 
 
@@ -64,6 +65,9 @@ class Stats(C.Structure):
         ("last_path", C.c_uint32), ("reserved", C.c_uint32),
         ("hot_launches", C.c_uint64), ("hot_ms_total", C.c_double),
         ("hot_bytes_total", C.c_double), ("hot_flops_total", C.c_double),
+        ("certified_queries", C.c_uint64), ("retried_queries", C.c_uint64),
+        ("uncertified_queries", C.c_uint64), ("range_rows", C.c_uint64),
+        ("n_devices", C.c_uint32), ("reserved2", C.c_uint32),
     ]
 
 
@@ -120,7 +124,8 @@ def lib():
     L.tsc_comm_unique_id.argtypes = [vp]
     L.tsc_comm_init.argtypes = [u64, vp, i32, i32]
     L.tsc_comm_p2p_export.argtypes = [u64, i32, i32, vp]
-    L.tsc_comm_p2p_import.argtypes = [u64, vp]
+    L.tsc_comm_p2p_import.argtypes = [u64, vp, i32]
+    L.tsc_search_flags.argtypes = [u64, u32, vp]
     L.tsc_search_sharded.argtypes = [u64, vp, u32, u32, C.c_double, vp, vp, vp, vp]
     L.tsc_stats_get.argtypes = [u64, C.POINTER(Stats)]
     L.tsc_stats_reset.argtypes = [u64]

@@ -712,282 +712,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 }
 
-// ====================================================================================
-// TS variant: the query tile lives in TENSOR MEMORY for the whole kernel.
-//
-// Measured on B200 (profiles/r01_gemm_*): the SS kernel above saturates the shared
-// memory port, not the tensor pipe — every UMMA re-reads A (4 KB) and B (8 KB) from
-// smem while TMA writes the same 12 KB back in: 192 B/cycle wanted, ~100 delivered,
-// tensor pipe 52 % busy. Queries never change during a search, so this kernel parks
-// the 128 x dims query tile in TMEM once (tcgen05.st, 384 of the 512 columns for
-// dims <= 768) and issues tcgen05.mma with A from TMEM: shared memory then carries
-// only the corpus stream (64 B/cycle in + 64 B/cycle out).
-//   TMEM columns: [0,64) and [64,128) = two fp32 accumulators D[128 x 64],
-//                 [128,512) = A, row m on lane m, element k in column 128 + k/2
-//   stage = corpus rows [64] x K [128] = two 128B-swizzled TMA boxes (16 KB)
-// ====================================================================================
-constexpr int kTsBN = 64;         // corpus rows per tile (UMMA N)
-constexpr int kTsBK = 128;        // K elements per stage (two 64-wide swizzled boxes)
-constexpr int kTsMaxDims = 768;   // A must fit 384 TMEM columns
-constexpr uint32_t kTsStageBytes = kTsBN * kTsBK * 2;
-constexpr uint32_t kTsAcol = 128;
-
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc,
-                                        uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-      "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
-      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
-      "r"(v[30]), "r"(v[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() {
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// smem: [stages x 16 KB] [scale 2x64][bias 2x64] [lists kp x 256 x 8] [barriers] [tmem ptr]
-__host__ __device__ inline size_t gemm_ts_smem_bytes(uint32_t stages, uint32_t kprime) {
-  return 1024 + (size_t)stages * kTsStageBytes + 2 * 2 * kTsBN * 4 +
-         (size_t)kprime * kGemmEpiThreads * 8 + (2 * stages + 5) * 8 + 16;
-}
-
-template <bool DBG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_topk_ts_kernel(const __grid_constant__ CUtensorMap map_b, const GemmParams p,
-                    const uint16_t *__restrict__ q16, const uint32_t qld, const uint32_t idesc) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t *sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t S = p.stages;
-  float *s_scale = reinterpret_cast<float *>(sm + (size_t)S * kTsStageBytes);  // [2][64]
-  float *s_bias = s_scale + 2 * kTsBN;
-  float *l_keys = s_bias + 2 * kTsBN;                                           // [kp][256]
-  uint32_t *l_rows = reinterpret_cast<uint32_t *>(l_keys + (size_t)p.kprime * kGemmEpiThreads);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(l_rows + (size_t)p.kprime * kGemmEpiThreads);
-  uint64_t *full = bars, *empty = bars + S, *tfull = bars + 2 * S, *tempty = bars + 2 * S + 2;
-  uint64_t *a_ready = bars + 2 * S + 4;
-  uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * S + 5);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t qt = blockIdx.x % p.q_tiles;
-  const uint32_t slice = blockIdx.x / p.q_tiles;
-  const uint32_t n_tiles = p.n_tiles;  // tiles of kTsBN rows
-
-  if (warp == kWarpTma && lane == 0) {
-    tma_prefetch_desc(&map_b);
-    for (uint32_t s = 0; s < S; s++) {
-      mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), 1);
-    }
-    for (int a = 0; a < 2; a++) {
-      mbar_init(smem_u32(&tfull[a]), 1);
-      mbar_init(smem_u32(&tempty[a]), kGemmEpiThreads);
-    }
-    mbar_init(smem_u32(a_ready), 128);
-    mbar_fence_init();
-  }
-  if (warp == kWarpMma) tmem_alloc(smem_u32(s_tmem), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
-
-  if (warp == kWarpTma) {
-    // ===== TMA producer: corpus only =====
-    const uint64_t pol_b = policy_evict_normal();
-    uint32_t s = 0, ph = 0;
-    for (uint32_t ct = slice; ct < n_tiles; ct += p.n_slices) {
-      for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
-        if (p.exp_flags & 4u) continue;
-        mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
-        if (elect_one()) {
-          const uint32_t bar = smem_u32(&full[s]);
-          mbar_expect_tx(bar, kTsStageBytes);
-          const uint32_t dst = base + s * kTsStageBytes;
-          const uint32_t ctl = (p.exp_flags & 1u) ? slice : ct;
-          tma_load_2d(dst, &map_b, bar, (int32_t)(kb * kTsBK), (int32_t)(ctl * kTsBN), pol_b);
-          tma_load_2d(dst + kTsStageBytes / 2, &map_b, bar, (int32_t)(kb * kTsBK + 64),
-                      (int32_t)(ctl * kTsBN), pol_b);
-        }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
-      }
-    }
-  } else if (warp == kWarpMma) {
-    // ===== MMA issuer: A from TMEM, B from smem =====
-    mbar_wait(smem_u32(a_ready), 0);
-    tc_fence_after();
-    uint32_t s = 0, ph = 0, as = 0, aph = 0;
-    const uint64_t desc_hi = umma_desc_sw128(0) & 0xFFFFFFFF00000000ull;
-    for (uint32_t ct = slice; ct < n_tiles; ct += p.n_slices) {
-      mbar_wait(smem_u32(&tempty[as]), aph ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * kTsBN;
-      for (uint32_t kb = 0; kb < p.k_blocks; kb++) {
-        if (!(p.exp_flags & 4u)) mbar_wait(smem_u32(&full[s]), ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t b_lo = (uint32_t)umma_desc_sw128(base + s * kTsStageBytes);
-          const uint32_t a_col = tmem_base + kTsAcol + kb * (kTsBK / 2);
-#pragma unroll
-          for (int k = 0; k < kTsBK / kGemmUK; k++) {
-            const uint32_t b_k = b_lo + (k >> 2) * (kTsStageBytes / 2 / 16) + (k & 3) * 2;
-            umma_ts(d_tmem, a_col + k * (kGemmUK / 2), desc_hi | b_k, idesc, (kb | k) != 0);
-          }
-          umma_commit(smem_u32(&empty[s]));
-          if (kb + 1 == p.k_blocks) umma_commit(smem_u32(&tfull[as]));
-        }
-        __syncwarp();
-        if (++s == S) { s = 0; ph ^= 1u; }
-      }
-      if (++as == 2) { as = 0; aph ^= 1u; }
-    }
-  } else {
-    // ===== epilogue warps (8): first park A in TMEM, then run the top-K' epilogue =====
-    const int et = threadIdx.x;                      // 0..255
-    const int quad = warp & 3;
-    const int half = warp >> 2;                      // 0: columns [0,32) of a tile, 1: [32,64)
-    const int qlane = quad * 32 + lane;
-    const int lidx = half * 128 + qlane;
-    const uint32_t q = qt * kGemmBM + qlane;
-    const uint32_t kp = p.kprime;
-
-    if (half == 0) {
-      // thread (quad, lane) owns query row q: lane `qlane`, columns 128 + k/2
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + kTsAcol;
-      const uint4 *src = reinterpret_cast<const uint4 *>(q16 + (size_t)q * qld);
-      const uint32_t vec_per_row = qld / 8;          // 16-byte vectors in a padded query row
-      const uint32_t chunks = p.k_blocks * (kTsBK / 64);
-      for (uint32_t c = 0; c < chunks; c++) {        // 64 elements = 32 columns per chunk
-        uint32_t v[32];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          uint4 t = make_uint4(0, 0, 0, 0);
-          if (q < p.nq && c * 8 + j < vec_per_row) t = __ldg(src + c * 8 + j);
-          v[4 * j + 0] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
-        }
-        tmem_st32(lane_addr + c * 32, v);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(a_ready));
-    }
-
-    for (uint32_t j = 0; j < kp; j++) {
-      l_keys[j * kGemmEpiThreads + lidx] = __int_as_float(0x7F800000);
-      l_rows[j * kGemmEpiThreads + lidx] = kInvalidRow;
-    }
-    float thr = __int_as_float(0x7F800000);
-    uint32_t as = 0, aph = 0;
-
-    // threads 0..63 own one column of every tile and prefetch its coefficients
-    auto column_coeffs = [&](uint32_t ct, float &sc, float &bi) {
-      const uint64_t n = (uint64_t)ct * kTsBN + et;
-      sc = __int_as_float(0x7FC00000);
-      bi = 0.0f;
-      bool live = et < kTsBN && ct < n_tiles && n < p.n_rows;
-      if (live && p.live_mask) live = (p.live_mask[n >> 5] >> (n & 31)) & 1u;
-      if (live) {
-        if (p.metric == kIP) {
-          sc = -1.0f;
-        } else {
-          const float n2 = __ldg(p.norm2 + n);
-          if (p.metric == kL2) { sc = -2.0f; bi = n2; }
-          else { sc = n2 > 0.0f ? -rsqrtf(n2) : 0.0f; }
-        }
-      }
-    };
-    float sc_next, bi_next;
-    column_coeffs(slice, sc_next, bi_next);
-
-    for (uint32_t ct = slice; ct < n_tiles; ct += p.n_slices) {
-      const uint64_t row0 = (uint64_t)ct * kTsBN;
-      if (et < kTsBN) {
-        s_scale[as * kTsBN + et] = sc_next;
-        s_bias[as * kTsBN + et] = bi_next;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      column_coeffs(ct + p.n_slices, sc_next, bi_next);
-      mbar_wait(smem_u32(&tfull[as]), aph);
-      tc_fence_after();
-      const uint32_t col0 = (uint32_t)half * 32;
-      if (p.exp_flags & 2u) {
-        tc_fence_before();
-        mbar_arrive(smem_u32(&tempty[as]));
-        if (++as == 2) { as = 0; aph ^= 1u; }
-        continue;
-      }
-      uint32_t v[32];
-      tmem_ld32_nowait(tmem_base + ((uint32_t)(quad * 32) << 16) + as * kTsBN + col0, v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tempty[as]));            // registers hold the tile: free the buffer
-      float key[32];
-      const float4 *sc4 = reinterpret_cast<const float4 *>(s_scale + as * kTsBN + col0);
-      const float4 *bi4 = reinterpret_cast<const float4 *>(s_bias + as * kTsBN + col0);
-      float lo = __int_as_float(0x7F800000);
-#pragma unroll
-      for (int j4 = 0; j4 < 8; j4++) {
-        const float4 sc = sc4[j4], bi = bi4[j4];
-        key[4 * j4 + 0] = fmaf(__uint_as_float(v[4 * j4 + 0]), sc.x, bi.x);
-        key[4 * j4 + 1] = fmaf(__uint_as_float(v[4 * j4 + 1]), sc.y, bi.y);
-        key[4 * j4 + 2] = fmaf(__uint_as_float(v[4 * j4 + 2]), sc.z, bi.z);
-        key[4 * j4 + 3] = fmaf(__uint_as_float(v[4 * j4 + 3]), sc.w, bi.w);
-        lo = fminf(lo, fminf(fminf(key[4 * j4 + 0], key[4 * j4 + 1]),
-                             fminf(key[4 * j4 + 2], key[4 * j4 + 3])));
-      }
-      if (DBG) {
-        if (q < p.nq)
-#pragma unroll
-          for (int j = 0; j < 32; j++)
-            if (row0 + col0 + j < p.n_rows)
-              p.dbg_keys[(size_t)q * p.n_rows + row0 + col0 + j] = key[j] + 0.0f;
-      }
-      if (lo < thr) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          if (key[j] < thr)
-            thr = gemm_list_insert(l_keys, l_rows, kp, lidx, key[j] + 0.0f,
-                                   (uint32_t)(row0 + col0 + j));
-        }
-      }
-      if (++as == 2) { as = 0; aph ^= 1u; }
-    }
-    if (q < p.nq) {
-      uint64_t *out = p.cand + ((size_t)q * p.n_slices * 2 + slice * 2 + half) * kp;
-      for (uint32_t j = 0; j < kp; j++) {
-        uint32_t r = l_rows[j * kGemmEpiThreads + lidx];
-        out[j] = r == kInvalidRow
-                     ? ~0ull
-                     : (((uint64_t)ordered_key(l_keys[j * kGemmEpiThreads + lidx]) << 32) | r);
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
-}
-
-// ---- K4: per-row sum of squares of the stored values (fp32), one warp per row ------
+// K4: sum of squares of every stored row (fp32, lane-strided fma + butterfly: the scan
+// kernel's accumulation order, so the certificate's scan_eps covers it) and the running
+// maximum of the shard (bits of a non-negative float order like the float).
 template <int DTYPE>
 __global__ void row_norms_kernel(const uint8_t *rows, uint64_t first, uint64_t n, uint32_t ld,
-                                 uint32_t row_bytes, float *norm2) {
+                                 uint32_t row_bytes, float *norm2, uint32_t *maxnorm) {
   const int lane = threadIdx.x & 31;
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  float mx = 0.0f;
   for (uint64_t r = first + w; r < first + n; r += nw) {
     const uint8_t *row = rows + r * row_bytes;
     float s = 0.0f;
@@ -1001,20 +735,38 @@ __global__ void row_norms_kernel(const uint8_t *rows, uint64_t first, uint64_t n
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
     if (lane == 0) norm2[r] = s;
+    if (s == s) mx = fmaxf(mx, s); else mx = __int_as_float(0x7F800000);   // NaN row: no bound
   }
+  if (lane == 0 && mx > 0.0f) atomicMax(maxnorm, __float_as_uint(mx));
 }
 
-// fp32 queries [nq, qld] -> 16-bit [nq, qld] in the corpus storage type (RNE)
-__global__ void convert_queries_kernel(const float *src, uint32_t n, uint16_t *dst, int dtype) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// fp32 queries [nq, qld] -> 16-bit [nq, qld] in the corpus storage type (RNE), one warp per
+// query; enorm[q] = |q16 - q|_2 rounded up: what the rounding can move a dot product by
+// (Cauchy-Schwarz), the certificate's a_e term (tsc_tail.cuh).
+__global__ void convert_queries_kernel(const float *src, uint32_t nq, uint32_t qld, uint16_t *dst,
+                                       float *enorm, int dtype) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (q >= nq) return;
+  float s = 0.0f;
+  for (uint32_t i = lane; i < qld; i += 32) {
+    const float v = src[(size_t)q * qld + i];
+    float r;
     if (dtype == kBF16) {
-      __nv_bfloat16 b = __float2bfloat16_rn(src[i]);
-      dst[i] = *reinterpret_cast<uint16_t *>(&b);
+      __nv_bfloat16 b = __float2bfloat16_rn(v);
+      dst[(size_t)q * qld + i] = *reinterpret_cast<uint16_t *>(&b);
+      r = __bfloat162float(b);
     } else {
-      __half h = __float2half_rn(src[i]);
-      dst[i] = *reinterpret_cast<uint16_t *>(&h);
+      __half h = __float2half_rn(v);
+      dst[(size_t)q * qld + i] = *reinterpret_cast<uint16_t *>(&h);
+      r = __half2float(h);
     }
+    const float e = v - r;   // exact: r is v rounded to fewer bits (or inf / NaN)
+    s = fmaf(e, e, s);
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if (lane == 0) enorm[q] = sqrtf(s) * 1.0001f;
 }
 
 }  // namespace tsc

@@ -4,7 +4,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <condition_variable>
+#include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -31,7 +34,6 @@ struct ScanConfig {
   int stages = 0;      // S (0 = auto)
   int stage_target = 6144;  // bytes per stage aimed for when R is auto
   int inflight_target = 96 * 1024;  // bytes of bulk copies in flight per CTA when S is auto
-  bool sparse_pf = false;   // sparse scan with the prefetching block cursor (opt-in)
 };
 
 // numeric table field kept column-wise next to the embedding column (tsc_where.cuh)
@@ -76,11 +78,41 @@ struct Index {
   uint32_t k_max = 0, nq_max = 0, kprime_max = 0;
   float *d_queries = nullptr;      // [nq_max, qld]
   float *h_queries = nullptr;      // pinned
-  float *d_norm2 = nullptr;        // [capacity] sum of squares per stored row (16-bit dtypes)
-  int *d_progress = nullptr;       // lockstep counters of the tensor-core path
+  float *d_norm2 = nullptr;        // [capacity] sum of squares per stored row
+  uint32_t *d_maxnorm = nullptr;   // bits of the largest norm2 seen (atomicMax; norms are >= 0)
+  float max_norm2 = 0.0f;          // host copy: upper bound of |row|^2 (certificate, IP / L2)
+  int *d_progress = nullptr;       // diagnostics scratch of the tensor-core path
   uint16_t *d_q16 = nullptr;       // [nq_max, qld] queries in the storage dtype (GEMM path)
+  float *d_enorm = nullptr;        // [nq_max] |q16 - q| of the converted queries (certificate)
   uint32_t gemm_min_nq = 9;        // batches at least this large take the tensor-core path
-  bool tf32 = false;               // fp32 column with the opt-in tf32 tensor path (TSC_GEMM_TF32=1)
+  // TMA descriptors of the tensor path, encoded once per (pointer, extent) instead of per launch
+  struct TmapSlot {
+    alignas(64) unsigned char bytes[128];   // a CUtensorMap
+    const void *ptr = nullptr;
+    uint64_t rows = 0;
+    uint32_t box_rows = 0;
+  };
+  TmapSlot tmap_b[2], tmap_q;      // corpus (CTA / CTA pair boxes), queries
+  // certificate / range retry state (tsc_tail.cuh)
+  uint32_t *d_flags = nullptr;     // [nq_max] kFlag* of the last search
+  uint32_t *h_flags = nullptr;     // pinned mirror
+  uint32_t *d_range_thr = nullptr; // [nq_max]
+  uint32_t *d_retry_list = nullptr;// [nq_max]
+  uint32_t *d_retry_n = nullptr;   // zero between searches
+  uint32_t *d_range_count = nullptr; // [kRangeSlots], zero between launches
+  uint64_t *d_range_buf = nullptr; // [kRangeSlots][kRangeCap]
+  uint32_t *d_done = nullptr;      // [2] last-CTA tickets (scan, exchange), zero between launches
+  unsigned long long *d_cert_stat = nullptr;  // [kStatSlots]
+  uint32_t *d_loc_counts = nullptr;  // [nq_max] shard-local result counts of a sharded search
+  // host-buffer searches: at most one in flight; `host_done` follows its last D2H copy
+  cudaEvent_t host_done = nullptr;
+  std::shared_ptr<struct Ticket> inflight;
+  bool host_consumer = true;         // the search in flight delivers its result on this shard
+  double last_threshold = 0;         // of the host-buffer search in flight (owed range passes)
+  // one search at a time uses the scratch above: searches on other streams wait for this
+  cudaEvent_t scratch_ev = nullptr;
+  cudaStream_t scratch_stream = nullptr;
+  bool scratch_used = false;
   uint64_t *d_cand = nullptr;      // [nq_max][cand_lists][kprime_max]
   uint64_t cand_lists = 0;
   int64_t *d_out_ids = nullptr, *h_out_ids = nullptr;
@@ -107,15 +139,20 @@ struct Index {
   // sharding
   void *nccl_comm = nullptr;
   int n_ranks = 1, rank = 0;
+  int xroot = -1;                   // consumer rank of the exchange, -1 = every rank
   uint8_t *d_gather_send = nullptr, *d_gather_recv = nullptr;
-  // opt-in P2P exchange (tsc_exchange.cuh): receive buffer exported to the peers over CUDA IPC
+  // exchange over peer memory (tsc_exchange.cuh): receive buffer mapped by the peers (CUDA
+  // IPC between processes, peer access inside one process)
   uint8_t *d_xbuf = nullptr;
   uint64_t xbuf_bytes = 0, xslot_bytes = 0;
+  uint32_t xdepth = 0;
   uint8_t *x_peer[8] = {};          // receive buffers of all ranks (own entry = d_xbuf)
+  bool x_ipc = false;               // x_peer entries were opened with cudaIpcOpenMemHandle
   bool p2p_ready = false;
   uint32_t xepoch = 0;
   uint32_t *h_xstatus = nullptr;    // mapped host word, set by the kernel on timeout
   uint32_t *d_xstatus = nullptr;    // device alias of h_xstatus
+  long long x_timeout_cycles = 4000000000ll;
 
   // dominant-kernel timing: ring of event pairs, resolved lazily
   static constexpr int kTimers = 128;
@@ -132,22 +169,140 @@ struct Index {
   uint64_t device_bytes = 0;
 };
 
-Index *lookup_index(uint64_t handle);   // NULL + error string when unknown
-uint64_t register_index(Index *ix);
+typedef std::shared_ptr<Index> IndexRef;
+void free_index(Index *ix);               // deleter of IndexRef: releases the device memory
+IndexRef lookup_index(uint64_t handle);   // empty + error string when unknown (or a group)
+uint64_t register_index(IndexRef ix);
 int32_t ensure_stage_bytes(Index *ix, size_t bytes);
+int32_t refresh_live(Index *ix, cudaStream_t st);   // recombine deleted / filter -> live when stale
+int32_t launch_pad_queries(Index *ix, const float *d_queries, uint32_t nq, cudaStream_t st);
+
+// A group: one logical column row-range sharded over the GPUs of one process
+// (tsc_index_create with n_devices > 1). Shard s owns node ids
+// [first + s * per_shard, first + (s + 1) * per_shard) on device_ids[s]; shard 0 is the
+// root of the exchange: it merges the shards' exact top-k and the host reads from it.
+struct Group {
+  std::mutex mu;                    // serialises calls on the group handle
+  tsc_index_desc desc{};            // as given: capacity / first_node_id of the whole column
+  std::vector<IndexRef> shards;
+  uint64_t per_shard = 0;           // rows per shard (multiple of 64)
+  bool search_pending = false;      // grp_search_begin without grp_search_end
+  uint32_t pend_nq = 0, pend_k = 0;
+  std::shared_ptr<struct Ticket> inflight;
+};
+typedef std::shared_ptr<Group> GroupRef;
+GroupRef lookup_group(uint64_t handle);   // empty (no error set) when the handle is no group
+uint64_t register_group(GroupRef g);
+
+// ---- per-shard operations behind the C ABI (each locks ix->mu itself) ------------------
+int32_t ix_create(const tsc_index_desc *d, IndexRef *out);
+int32_t ix_clear(Index *ix);
+int32_t ix_append_rows(Index *ix, uint64_t first_node_id, const void *rows, uint64_t n_rows);
+int32_t ix_append_pages(Index *ix, uint64_t first_logical_page, const uint8_t *pages,
+                        uint64_t n_pages, uint32_t page_size, uint64_t live_rows);
+int32_t ix_append_synthetic(Index *ix, uint64_t seed, uint64_t first_node_id, uint64_t n_rows);
+int32_t ix_set_deleted(Index *ix, const uint64_t *node_ids, uint64_t n, uint8_t deleted);
+int32_t ix_apply_graph_pages(Index *ix, uint64_t first_logical_page, const uint8_t *pages,
+                             uint64_t n_pages, uint32_t page_size);
+int32_t ix_set_filter(Index *ix, const uint64_t *bitmap_words, uint64_t n_words);
+int32_t ix_stats_get(Index *ix, tsc_stats *out);
+int32_t ix_stats_reset(Index *ix);
+int32_t ix_column_create(Index *ix, uint32_t column_id, uint8_t col_type);
+int32_t ix_column_append(Index *ix, uint32_t column_id, uint64_t first_node_id, const void *values,
+                         const uint8_t *is_null, uint64_t n);
+int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                        uint32_t n_in_args, uint64_t *out_matched);
+int32_t ix_set_primary_keys(Index *ix, uint64_t first_node_id, const uint8_t *utf8,
+                            const uint64_t *offsets, uint64_t n);
+int32_t ix_get_primary_key(Index *ix, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
+                           uint32_t *out_len);
+int32_t ix_load_ngh(Index *ix, const char *index_dir, uint32_t flags, tsc_ngh_info *out);
+// host-buffer search in two halves: begin enqueues H2D + kernels (+ D2H where this shard
+// consumes the result) on the shard's stream, end waits, runs owed range passes and copies
+// out. `queries` are [nq, dims] fp32 in host memory. ix->mu is NOT taken: the caller holds
+// it (blocking search) or the group's lock.
+int32_t ix_search_begin(Index *ix, const float *queries, uint32_t nq, uint32_t k, double threshold);
+int32_t ix_search_end(Index *ix, uint32_t nq, uint32_t k, int64_t *out_ids, double *out_dist,
+                      uint32_t *out_counts);
+bool ix_is_consumer(const Index *ix);
+void drop_tickets_of(uint64_t handle);    // tsc_index_destroy: tickets die with their handle
+void comm_release(Index *ix);             // destroy the NCCL communicator, if any
+// peer-memory exchange between the shards of one process (tsc_group.cu)
+int32_t ix_xchg_alloc(Index *ix, int n_ranks, int rank, int root);
+
+// ---- group operations (tsc_group.cu) -----------------------------------------------------
+int32_t grp_create(const tsc_index_desc *d, uint64_t *out_handle);
+int32_t grp_clear(Group &g);
+int32_t grp_append_rows(Group &g, uint64_t first_node_id, const void *rows, uint64_t n_rows);
+int32_t grp_append_pages(Group &g, uint64_t first_logical_page, const uint8_t *pages,
+                         uint64_t n_pages, uint32_t page_size, uint64_t live_rows);
+int32_t grp_append_synthetic(Group &g, uint64_t seed, uint64_t first_node_id, uint64_t n_rows);
+int32_t grp_set_deleted(Group &g, const uint64_t *node_ids, uint64_t n, uint8_t deleted);
+int32_t grp_apply_graph_pages(Group &g, uint64_t first_logical_page, const uint8_t *pages,
+                              uint64_t n_pages, uint32_t page_size);
+int32_t grp_set_filter(Group &g, const uint64_t *bitmap_words, uint64_t n_words);
+int32_t grp_stats_get(Group &g, tsc_stats *out);
+int32_t grp_stats_reset(Group &g);
+int32_t grp_column_create(Group &g, uint32_t column_id, uint8_t col_type);
+int32_t grp_column_append(Group &g, uint32_t column_id, uint64_t first_node_id, const void *values,
+                          const uint8_t *is_null, uint64_t n);
+int32_t grp_filter_where(Group &g, const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                         uint32_t n_in_args, uint64_t *out_matched);
+int32_t grp_set_primary_keys(Group &g, uint64_t first_node_id, const uint8_t *utf8,
+                             const uint64_t *offsets, uint64_t n);
+int32_t grp_get_primary_key(Group &g, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
+                            uint32_t *out_len);
+int32_t grp_load_ngh(Group &g, const char *index_dir, uint32_t flags, tsc_ngh_info *out);
+int32_t grp_search_begin(Group &g, const float *queries, uint32_t nq, uint32_t k, double threshold);
+int32_t grp_search_end(Group &g, int64_t *out_ids, double *out_dist, uint32_t *out_counts);
+int32_t grp_search_flags(Group &g, uint32_t nq, uint32_t *out_flags);
+
+// every extern "C" body runs inside this: no exception crosses the C ABI
+#define TSC_API_TRY try {
+#define TSC_API_CATCH                                          \
+  }                                                            \
+  catch (const std::bad_alloc &) {                             \
+    tsc::set_error("out of host memory");                      \
+    return TSC_ERR_OOM;                                        \
+  }                                                            \
+  catch (...) {                                                \
+    tsc::set_error("internal error (C++ exception)");          \
+    return TSC_ERR_BAD_ARG;                                    \
+  }
+
+// One search as the launchers see it: the shard-local exact top-k goes to loc_*; for a
+// sharded index the exchange merges the shards' loc_* into x_* (on the consumer ranks).
+struct SearchCtx {
+  const float *d_q = nullptr;    // [nq, qld] fp32, padded
+  uint32_t nq = 0, k = 0, kprime = 0;
+  double threshold = 0;
+  int64_t *loc_ids = nullptr;
+  double *loc_dist = nullptr;
+  uint32_t *loc_counts = nullptr;
+  bool sharded = false;
+  int64_t *x_ids = nullptr;
+  double *x_dist = nullptr;
+  uint32_t *x_counts = nullptr;
+  cudaStream_t st = nullptr;
+};
+
+struct TailParams;
+struct XchgParams;
+// m candidates per query in ix->d_cand; gemm_keys: they come from the tensor path
+void fill_tail(const Index *ix, const SearchCtx &c, uint32_t m, bool gemm_keys, TailParams *out);
+void fill_xchg(const Index *ix, XchgParams *out);   // uses ix->xepoch as it stands
 
 // launchers implemented per translation unit
-int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
-                    uint32_t *out_lists, cudaStream_t st);
-int32_t launch_select(Index *ix, const float *d_q, uint32_t nq, uint32_t k, uint32_t kprime,
-                      const uint64_t *d_cand, uint32_t m, double threshold, int64_t *d_ids,
-                      double *d_dist, uint32_t *d_counts, cudaStream_t st);
+// mode 0: first pass over queries [q_base, q_base + n) (n <= 8); mode 1: range pass over
+// retry-list entries [q_base, q_base + qb). fused: the last CTA runs the tail (and, with
+// xchg, the shard exchange of the whole search).
+int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, uint32_t n, int qb,
+                    bool fused, bool xchg, bool last_retry, uint32_t *out_lists);
+int32_t launch_tail(Index *ix, const SearchCtx &c, uint32_t m, bool gemm_keys);
 int32_t launch_merge(Index *ix, const int64_t *d_part_ids, const double *d_part_dist,
                      uint64_t part_stride, uint32_t n_parts, uint32_t nq, uint32_t k,
                      int64_t *d_ids, double *d_dist, uint32_t *d_counts, cudaStream_t st);
-int32_t launch_exchange(Index *ix, const int64_t *d_src_ids, const double *d_src_dist, uint32_t nq,
-                        uint32_t k, int64_t *d_ids, double *d_dist, uint32_t *d_counts,
-                        cudaStream_t st);
+int32_t launch_exchange(Index *ix, const SearchCtx &c);
 int32_t scan_configure(Index *ix);
 bool gemm_supported(const Index *ix, uint32_t kprime);
 int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_t st);

@@ -84,7 +84,8 @@ __device__ __forceinline__ uint32_t ld_u16(const uint8_t *p) {
 // follow the slice by multiplying with x^(8n) mod P in GF(2)[x] (reflected
 // representation, bit 31 = x^0), and the 32 partial registers are XOR-ed: the
 // register update is affine, so raw(A||B, i) = shift(raw(A, i), |B|) ^ raw(B, 0).
-// status[page]: 0 ok, 1 bad magic/header, 2 bad length, 3 crc, 4 type, 5 payload, 6 dims
+// status[page]: 0 ok, 1 bad magic/header, 2 bad length, 3 crc, 4 type, 5 payload, 6 dims,
+// 7 precision
 __host__ __device__ __forceinline__ uint32_t crc_bytes(const uint32_t *tab, uint32_t c,
                                                        const uint8_t *p, uint32_t n) {
   for (uint32_t i = 0; i < n; i++) c = tab[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
@@ -114,8 +115,8 @@ __host__ __device__ __forceinline__ uint32_t crc_shift(uint32_t c, uint32_t nbyt
 }
 
 __global__ void page_check_kernel(const uint8_t *pages, uint64_t n_pages, uint32_t page_size,
-                                  uint32_t expect_type, uint32_t expect_dims, uint32_t *status,
-                                  uint32_t *bad_count) {
+                                  uint32_t expect_type, uint32_t expect_dims, uint32_t expect_prec,
+                                  uint32_t *status, uint32_t *bad_count) {
   __shared__ uint32_t tab[256];
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
     uint32_t c = i;
@@ -158,6 +159,8 @@ __global__ void page_check_kernel(const uint8_t *pages, uint64_t n_pages, uint32
             st = 5;
           else if (dims != expect_dims)
             st = 6;
+          else if (prec != expect_prec)   // the slot -> node mapping assumes the index's precision
+            st = 7;
         }
       } else {
         if (len < 4) {

@@ -305,8 +305,25 @@ int32_t tsc_ngh_read_meta(const char *index_dir, tsc_ngh_info *out) {
 
 int32_t tsc_index_load_ngh(uint64_t handle, const char *index_dir, uint32_t flags,
                            tsc_ngh_info *out) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+  TSC_API_TRY
+  if (GroupRef g = lookup_group(handle)) {
+    std::lock_guard<std::mutex> glk(g->mu);
+    return grp_load_ngh(*g, index_dir, flags, out);
+  }
+  IndexRef ref = lookup_index(handle);
+  if (!ref) return TSC_ERR_BAD_HANDLE;
+  if (ref->host_only) {
+    set_error("host-only self-test handle: no device entry point works on it");
+    return TSC_ERR_UNSUPPORTED;
+  }
+  return ix_load_ngh(ref.get(), index_dir, flags, out);
+  TSC_API_CATCH
+}
+
+}  // extern "C"
+
+namespace tsc {
+int32_t ix_load_ngh(Index *ix, const char *index_dir, uint32_t flags, tsc_ngh_info *out) {
   tsc_ngh_info m;
   memset(&m, 0, sizeof m);
   m.struct_size = sizeof m;
@@ -342,16 +359,14 @@ int32_t tsc_index_load_ngh(uint64_t handle, const char *index_dir, uint32_t flag
   rc = walk_pages(index_dir, m, "rawvec", rows_per_raw_page(m), lo, hi, chunk_pages, bufs[0],
                   bufs[1],
                   [&](const Chunk &c, const uint8_t *data) {
-                    return tsc_index_append_pages(handle, c.first_page, data, c.n_pages, page_size,
-                                                  live);
+                    return ix_append_pages(ix, c.first_page, data, c.n_pages, page_size, live);
                   },
                   &m);
   if (rc == TSC_OK && (flags & TSC_LOAD_TOMBSTONES))
     rc = walk_pages(index_dir, m, "graph", slots_per_graph_page(m), lo, hi, chunk_pages, bufs[0],
                     bufs[1],
                     [&](const Chunk &c, const uint8_t *data) {
-                      return tsc_index_apply_graph_pages(handle, c.first_page, data, c.n_pages,
-                                                         page_size);
+                      return ix_apply_graph_pages(ix, c.first_page, data, c.n_pages, page_size);
                     },
                     &m);
   cudaFreeHost(bufs[0]);
@@ -360,6 +375,9 @@ int32_t tsc_index_load_ngh(uint64_t handle, const char *index_dir, uint32_t flag
   if (out) *out = m;
   return rc;
 }
+}  // namespace tsc
+
+extern "C" {
 
 // Self-test hook (no GPU): the directory walk / chunking / double-buffered reader of
 // tsc_index_load_ngh with a host sink that records (first logical page, pages, CRC-32 of the

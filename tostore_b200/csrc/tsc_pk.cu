@@ -6,14 +6,10 @@
 
 #include "tsc_index.h"
 
-using namespace tsc;
+namespace tsc {
 
-extern "C" {
-
-int32_t tsc_index_set_primary_keys(uint64_t handle, uint64_t first_node_id, const uint8_t *utf8,
-                                   const uint64_t *offsets, uint64_t n) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+int32_t ix_set_primary_keys(Index *ix, uint64_t first_node_id, const uint8_t *utf8,
+                            const uint64_t *offsets, uint64_t n) {
   if (n == 0) return TSC_OK;
   if (!offsets || (!utf8 && offsets[n] != offsets[0])) {
     set_error("set_primary_keys: NULL buffer");
@@ -34,29 +30,22 @@ int32_t tsc_index_set_primary_keys(uint64_t handle, uint64_t first_node_id, cons
       return TSC_ERR_BAD_ARG;
     }
   const uint64_t row0 = first_node_id - base;
-  try {
-    if (ix->pk_off.size() < row0 + n) {
-      ix->pk_off.resize(row0 + n, 0);
-      ix->pk_len.resize(row0 + n, 0);
-    }
-    const uint64_t arena0 = ix->pk_arena.size();
-    ix->pk_arena.insert(ix->pk_arena.end(), (const char *)utf8 + offsets[0],
-                        (const char *)utf8 + offsets[n]);
-    for (uint64_t i = 0; i < n; i++) {
-      ix->pk_off[row0 + i] = arena0 + (offsets[i] - offsets[0]);
-      ix->pk_len[row0 + i] = (uint32_t)(offsets[i + 1] - offsets[i]);
-    }
-  } catch (const std::bad_alloc &) {
-    set_error("set_primary_keys: out of host memory");
-    return TSC_ERR_OOM;
+  if (ix->pk_off.size() < row0 + n) {
+    ix->pk_off.resize(row0 + n, 0);
+    ix->pk_len.resize(row0 + n, 0);
+  }
+  const uint64_t arena0 = ix->pk_arena.size();
+  ix->pk_arena.insert(ix->pk_arena.end(), (const char *)utf8 + offsets[0],
+                      (const char *)utf8 + offsets[n]);
+  for (uint64_t i = 0; i < n; i++) {
+    ix->pk_off[row0 + i] = arena0 + (offsets[i] - offsets[0]);
+    ix->pk_len[row0 + i] = (uint32_t)(offsets[i + 1] - offsets[i]);
   }
   return TSC_OK;
 }
 
-int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *out_utf8,
-                                  uint32_t capacity, uint32_t *out_len) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+int32_t ix_get_primary_key(Index *ix, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
+                           uint32_t *out_len) {
   if (!out_len || (!out_utf8 && capacity)) {
     set_error("get_primary_key: NULL buffer");
     return TSC_ERR_BAD_ARG;
@@ -77,26 +66,27 @@ int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *ou
 
 // Result assembly after the engine call (vector_index_manager.dart:576-587): drop hits
 // whose node has no primary-key mapping, keep ascending distance order, compact in place.
-static int32_t pk_assemble(Index *ix, uint32_t k, int64_t *out_ids, double *out_dist,
+// `get` reads the key of one node id (one shard's table, or the group's routing).
+template <typename GetKey>
+static int32_t pk_assemble(GetKey get, uint32_t k, int64_t *out_ids, double *out_dist,
                            double *out_score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
                            uint64_t *out_pk_offsets, uint32_t *out_count) {
-  std::lock_guard<std::mutex> lk(ix->mu);
-  const uint64_t base = ix->desc.first_node_id;
   uint32_t kept = 0;
   uint64_t used = 0;
   out_pk_offsets[0] = 0;
   for (uint32_t j = 0; j < *out_count && j < k; j++) {
-    const uint64_t nid = (uint64_t)out_ids[j];
-    const uint64_t r = nid - base;
-    // `if (pk == null) continue;` vector_index_manager.dart:578-579
-    if (out_ids[j] < 0 || nid < base || r >= ix->pk_len.size() || ix->pk_len[r] == 0) continue;
-    if (used + ix->pk_len[r] > pk_capacity) {
+    if (out_ids[j] < 0) continue;
+    uint32_t len = 0;
+    const uint64_t room = pk_capacity - used;
+    int32_t rc = get((uint64_t)out_ids[j], out_pk_utf8 ? out_pk_utf8 + used : nullptr,
+                     room > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)room, &len);
+    if (rc != TSC_OK) {
       set_error("vector_search_pk: keys need more than %llu bytes",
                 (unsigned long long)pk_capacity);
       return TSC_ERR_BAD_ARG;
     }
-    memcpy(out_pk_utf8 + used, ix->pk_arena.data() + ix->pk_off[r], ix->pk_len[r]);
-    used += ix->pk_len[r];
+    if (len == 0) continue;   // `if (pk == null) continue;` vector_index_manager.dart:578-579
+    used += len;
     out_ids[kept] = out_ids[j];
     out_dist[kept] = out_dist[j];
     out_score[kept] = out_score[j];
@@ -111,12 +101,44 @@ static int32_t pk_assemble(Index *ix, uint32_t k, int64_t *out_ids, double *out_
   return TSC_OK;
 }
 
+}  // namespace tsc
+
+using namespace tsc;
+
+extern "C" {
+
+int32_t tsc_index_set_primary_keys(uint64_t handle, uint64_t first_node_id, const uint8_t *utf8,
+                                   const uint64_t *offsets, uint64_t n) {
+  TSC_API_TRY
+  if (GroupRef g = lookup_group(handle)) {
+    std::lock_guard<std::mutex> glk(g->mu);
+    return grp_set_primary_keys(*g, first_node_id, utf8, offsets, n);
+  }
+  IndexRef ref = lookup_index(handle);
+  if (!ref) return TSC_ERR_BAD_HANDLE;
+  return ix_set_primary_keys(ref.get(), first_node_id, utf8, offsets, n);
+  TSC_API_CATCH
+}
+
+int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *out_utf8,
+                                  uint32_t capacity, uint32_t *out_len) {
+  TSC_API_TRY
+  if (GroupRef g = lookup_group(handle)) {
+    std::lock_guard<std::mutex> glk(g->mu);
+    return grp_get_primary_key(*g, node_id, out_utf8, capacity, out_len);
+  }
+  IndexRef ref = lookup_index(handle);
+  if (!ref) return TSC_ERR_BAD_HANDLE;
+  return ix_get_primary_key(ref.get(), node_id, out_utf8, capacity, out_len);
+  TSC_API_CATCH
+}
+
 int32_t tsc_vector_search_pk(uint64_t handle, const double *values, uint64_t len, uint32_t k,
                              double threshold, int64_t *out_ids, double *out_dist,
                              double *out_score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
                              uint64_t *out_pk_offsets, uint32_t *out_count) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+  TSC_API_TRY
+  if (!lookup_group(handle) && !lookup_index(handle)) return TSC_ERR_BAD_HANDLE;
   if (!out_pk_offsets || (!out_pk_utf8 && pk_capacity)) {
     set_error("vector_search_pk: NULL buffer");
     return TSC_ERR_BAD_ARG;
@@ -124,8 +146,12 @@ int32_t tsc_vector_search_pk(uint64_t handle, const double *values, uint64_t len
   int32_t rc = tsc_vector_search(handle, values, len, k, threshold, out_ids, out_dist, out_score,
                                  out_count);
   if (rc != TSC_OK) return rc;
-  return pk_assemble(ix, k, out_ids, out_dist, out_score, out_pk_utf8, pk_capacity, out_pk_offsets,
+  auto get = [&](uint64_t node, uint8_t *dst, uint32_t cap, uint32_t *out_len) {
+    return tsc_index_get_primary_key(handle, node, dst, cap, out_len);
+  };
+  return pk_assemble(get, k, out_ids, out_dist, out_score, out_pk_utf8, pk_capacity, out_pk_offsets,
                      out_count);
+  TSC_API_CATCH
 }
 
 // Self-test hooks (no GPU): a host-only index object that carries nothing but the
@@ -134,6 +160,7 @@ int32_t tsc_vector_search_pk(uint64_t handle, const double *values, uint64_t len
 // memory behind it); release it with tsc_index_destroy.
 int32_t tsc_selftest_host_index(uint64_t capacity_rows, uint64_t first_node_id,
                                 uint64_t *out_handle) {
+  TSC_API_TRY
   if (!out_handle || capacity_rows == 0) {
     set_error("selftest_host_index: bad argument");
     return TSC_ERR_BAD_ARG;
@@ -144,20 +171,26 @@ int32_t tsc_selftest_host_index(uint64_t capacity_rows, uint64_t first_node_id,
   ix->desc.capacity_rows = capacity_rows;
   ix->capacity = capacity_rows;
   ix->host_only = true;
-  *out_handle = register_index(ix);
+  *out_handle = register_index(IndexRef(ix, free_index));
   return TSC_OK;
+  TSC_API_CATCH
 }
 
 int32_t tsc_selftest_pk_assemble(uint64_t handle, uint32_t k, int64_t *ids, double *dist,
                                  double *score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
                                  uint64_t *out_pk_offsets, uint32_t *inout_count) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+  TSC_API_TRY
+  if (!lookup_group(handle) && !lookup_index(handle)) return TSC_ERR_BAD_HANDLE;
   if (!ids || !dist || !score || !out_pk_offsets || !inout_count) {
     set_error("selftest_pk_assemble: NULL buffer");
     return TSC_ERR_BAD_ARG;
   }
-  return pk_assemble(ix, k, ids, dist, score, out_pk_utf8, pk_capacity, out_pk_offsets, inout_count);
+  auto get = [&](uint64_t node, uint8_t *dst, uint32_t cap, uint32_t *out_len) {
+    return tsc_index_get_primary_key(handle, node, dst, cap, out_len);
+  };
+  return pk_assemble(get, k, ids, dist, score, out_pk_utf8, pk_capacity, out_pk_offsets,
+                     inout_count);
+  TSC_API_CATCH
 }
 
 }  // extern "C"

@@ -1,4 +1,4 @@
-// tsc_scan.cu — host launcher for K1 (tsc_scan.cuh): stage geometry + dispatch.
+// tsc_scan.cu — host launcher for K1 / K6 (tsc_scan.cuh): stage geometry + dispatch.
 #include <stdlib.h>
 
 #include "tsc_index.h"
@@ -6,11 +6,16 @@
 
 namespace tsc {
 
+#ifdef TSC_DIAG
 static int env_int(const char *name, int dflt) {
   const char *v = getenv(name);
   if (!v || !*v) return dflt;
   return atoi(v);
 }
+#else
+// the shipping library reads no tuning switches from the environment
+static int env_int(const char *, int dflt) { return dflt; }
+#endif
 
 int32_t scan_configure(Index *ix) {
   ix->scan.grid = env_int("TSC_SCAN_CTAS", 1) * ix->sm_count;
@@ -19,7 +24,6 @@ int32_t scan_configure(Index *ix) {
   ix->scan.stages = env_int("TSC_SCAN_STAGES", 0);
   ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 6144);
   ix->scan.inflight_target = env_int("TSC_SCAN_INFLIGHT_BYTES", 96 * 1024);
-  ix->scan.sparse_pf = env_int("TSC_SCAN_SPARSE_PF", 0) == 1;   // experimental, see tsc_scan.cuh
   if (ix->scan.warps < 1 || ix->scan.warps > 16 || ix->scan.grid < 1) {
     set_error("bad TSC_SCAN_* override");
     return TSC_ERR_BAD_ARG;
@@ -86,11 +90,13 @@ static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cuda
     attr_done[ix->device & 63] = true;
   }
   int slot = 0;
-  int32_t rc = hot_timer_begin(ix, st, &slot);
+  int32_t rc = TSC_OK;
+  if (p.mode == 0) rc = hot_timer_begin(ix, st, &slot);
   if (rc != TSC_OK) return rc;
   kern<<<ix->scan.grid, pl.warps * 32, pl.smem, st>>>(p);
   TSC_CUDA(cudaGetLastError());
   ix->launches++;
+  if (p.mode != 0) return TSC_OK;   // range launches are not part of the roofline accounting
   // algorithmic bytes of one pass: live rows x dims x sizeof(elem)
   return hot_timer_end(ix, st, slot, (double)p.n_rows * ix->desc.dims * ix->elem_bytes, 0.0);
 }
@@ -98,21 +104,20 @@ static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cuda
 template <int METRIC, int DTYPE, int QB>
 static int32_t run_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
   static bool attr_done[64] = {false};
-  auto kern = ix->scan.sparse_pf ? scan_topk_sparse_kernel<METRIC, DTYPE, QB, true>
-                                 : scan_topk_sparse_kernel<METRIC, DTYPE, QB, false>;
+  auto kern = scan_topk_sparse_kernel<METRIC, DTYPE, QB>;
   if (!attr_done[ix->device & 63]) {
-    TSC_CUDA(cudaFuncSetAttribute(scan_topk_sparse_kernel<METRIC, DTYPE, QB, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
-    TSC_CUDA(cudaFuncSetAttribute(scan_topk_sparse_kernel<METRIC, DTYPE, QB, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_optin));
+    TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)ix->smem_optin));
     attr_done[ix->device & 63] = true;
   }
   int slot = 0;
-  int32_t rc = hot_timer_begin(ix, st, &slot);
+  int32_t rc = TSC_OK;
+  if (p.mode == 0) rc = hot_timer_begin(ix, st, &slot);
   if (rc != TSC_OK) return rc;
   kern<<<ix->scan.grid, pl.warps * 32, pl.smem, st>>>(p);
   TSC_CUDA(cudaGetLastError());
   ix->launches++;
+  if (p.mode != 0) return TSC_OK;
   // algorithmic bytes: only live rows are read (+ the bitmap)
   return hot_timer_end(ix, st, slot,
                        (double)ix->live_rows * ix->desc.dims * ix->elem_bytes + p.n_rows / 8.0, 0.0);
@@ -158,59 +163,78 @@ static int32_t dispatch_dtype(Index *ix, const ScanParams &p, const ScanPlan &pl
   }
 }
 
-// Scan the shard once per group of up to 8 queries. d_cand receives
-// [nq][grid][kprime] composites; *out_lists = grid.
-int32_t launch_scan(Index *ix, const float *d_q, uint32_t nq, uint32_t kprime, uint64_t *d_cand,
-                    uint32_t *out_lists, cudaStream_t st) {
-  *out_lists = (uint32_t)ix->scan.grid;
-  for (uint32_t q0 = 0; q0 < nq;) {
-    uint32_t left = nq - q0;
-    int qb = left >= 5 ? 8 : (left >= 2 ? 4 : 1);
-    ScanPlan pl;
-    // sparse liveness (WHERE prefilter): move only the live rows, one bulk copy each
-    const bool masked = ix->has_deleted || ix->has_filter;
-    const bool sparse = masked && ix->row_bytes >= 256 &&
-                        (double)ix->live_rows < ix->sparse_frac * (double)ix->rows;
-    if (!plan_scan(ix, qb, kprime, &pl, sparse)) {
-      set_error("scan: dims=%u (row %u B) with k'=%u does not fit shared memory", ix->desc.dims,
-                ix->row_bytes, kprime);
+// One scan launch over the shard. mode 0: first pass for queries [q_base, q_base + n), the
+// kernel variant `qb` (1 / 4 / 8 queries per pass); d_cand receives [nq][grid][kprime]
+// composites, *out_lists = grid. mode 1: range pass over retry-list entries
+// [q_base, q_base + qb); exits at once on the device when there are none.
+int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, uint32_t n, int qb,
+                    bool fused, bool xchg, bool last_retry, uint32_t *out_lists) {
+  if (out_lists) *out_lists = (uint32_t)ix->scan.grid;
+  ScanPlan pl;
+  // sparse liveness (WHERE prefilter): move only the live rows, one bulk copy each
+  const bool masked = ix->has_deleted || ix->has_filter;
+  const bool sparse = masked && ix->row_bytes >= 256 &&
+                      (double)ix->live_rows < ix->sparse_frac * (double)ix->rows;
+  if (!plan_scan(ix, qb, c.kprime, &pl, sparse)) {
+    set_error("scan: dims=%u (row %u B) with k'=%u does not fit shared memory", ix->desc.dims,
+              ix->row_bytes, c.kprime);
+    return TSC_ERR_BAD_DIMS;
+  }
+  ScanParams p{};
+  p.rows = ix->d_rows;
+  p.n_rows = ix->rows;
+  p.row_bytes = ix->row_bytes;
+  p.chunks_per_row = ix->row_bytes / 16;
+  p.queries = c.d_q;
+  p.qld = ix->qld;
+  p.q_base = q_base;
+  p.nq = n;
+  p.live_mask = masked ? ix->d_live : nullptr;
+  p.kprime = c.kprime;
+  p.stages = (uint32_t)pl.stages;
+  p.stage_bytes = pl.stage_bytes;
+  p.cand = ix->d_cand;
+  p.sort_cap = pl.sort_cap;
+  p.mode = mode;
+  p.fused_tail = (fused || mode == 1) ? 1 : 0;
+  p.xchg_in_tail = xchg ? 1 : 0;
+  p.last_retry = last_retry ? 1 : 0;
+  p.nq_total = c.nq;
+  p.done_counter = ix->d_done;
+  const uint32_t m = (uint32_t)ix->scan.grid * c.kprime;
+  fill_tail(ix, c, m, false, &p.tail);
+  p.tail_sort_cap = tail_sort_cap(m, c.kprime, mode == 1);
+  if (xchg) {
+    fill_xchg(ix, &p.xchg);
+    p.x_out_ids = c.x_ids;
+    p.x_out_dist = c.x_dist;
+    p.x_out_counts = c.x_counts;
+    uint32_t xcap = next_pow2((uint32_t)ix->n_ranks * c.k);
+    if (xcap > p.tail_sort_cap) p.tail_sort_cap = xcap;
+  }
+  if (p.fused_tail) {
+    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld);
+    if (need > ix->smem_optin) {
+      set_error("scan: the tail needs %zu bytes of shared memory", need);
       return TSC_ERR_BAD_DIMS;
     }
-    uint32_t n = left < (uint32_t)qb ? left : (uint32_t)qb;
-    ScanParams p{};
-    p.rows = ix->d_rows;
-    p.n_rows = ix->rows;
-    p.row_bytes = ix->row_bytes;
-    p.chunks_per_row = ix->row_bytes / 16;
-    p.queries = d_q + (size_t)q0 * ix->qld;
-    p.qld = ix->qld;
-    p.nq = n;
-    p.live_mask = (ix->has_deleted || ix->has_filter) ? ix->d_live : nullptr;
-    p.kprime = kprime;
-    p.stages = (uint32_t)pl.stages;
-    p.stage_bytes = pl.stage_bytes;
-    p.cand = d_cand + (size_t)q0 * ix->scan.grid * kprime;
-    p.sort_cap = pl.sort_cap;
-    int32_t rc;
-    if (sparse) {
-      switch (ix->desc.metric) {
-        case TSC_METRIC_L2: rc = dispatch_sparse_dtype<kL2>(ix, p, pl, st); break;
-        case TSC_METRIC_INNER_PRODUCT: rc = dispatch_sparse_dtype<kIP>(ix, p, pl, st); break;
-        default: rc = dispatch_sparse_dtype<kCos>(ix, p, pl, st); break;
-      }
-      if (rc != TSC_OK) return rc;
-      q0 += n;
-      continue;
-    }
-    switch (ix->desc.metric) {
-      case TSC_METRIC_L2: rc = dispatch_dtype<kL2>(ix, p, pl, st); break;
-      case TSC_METRIC_INNER_PRODUCT: rc = dispatch_dtype<kIP>(ix, p, pl, st); break;
-      default: rc = dispatch_dtype<kCos>(ix, p, pl, st); break;
-    }
-    if (rc != TSC_OK) return rc;
-    q0 += n;
+    if (need > pl.smem) pl.smem = need;
   }
-  return TSC_OK;
+  int32_t rc;
+  if (sparse) {
+    switch (ix->desc.metric) {
+      case TSC_METRIC_L2: rc = dispatch_sparse_dtype<kL2>(ix, p, pl, c.st); break;
+      case TSC_METRIC_INNER_PRODUCT: rc = dispatch_sparse_dtype<kIP>(ix, p, pl, c.st); break;
+      default: rc = dispatch_sparse_dtype<kCos>(ix, p, pl, c.st); break;
+    }
+    return rc;
+  }
+  switch (ix->desc.metric) {
+    case TSC_METRIC_L2: rc = dispatch_dtype<kL2>(ix, p, pl, c.st); break;
+    case TSC_METRIC_INNER_PRODUCT: rc = dispatch_dtype<kIP>(ix, p, pl, c.st); break;
+    default: rc = dispatch_dtype<kCos>(ix, p, pl, c.st); break;
+  }
+  return rc;
 }
 
 }  // namespace tsc

@@ -1,11 +1,14 @@
-// tsc_scan.cuh — K1: HBM-bound exact scan with in-kernel top-K' selection.
+// tsc_scan.cuh — K1 / K6: HBM-bound exact scan with in-kernel top-K' selection and a fused
+// tail (selection, exact re-rank, certificate, shard exchange) in the last CTA.
 //
 // Replaces the candidate-generation half of NghGraphEngine.search
 // (core/ngh_graph_engine.dart:98-113: ADC beam search) with an exhaustive pass
 // over the row-major embedding block. The fp32 ranking key computed here plays
 // the role the PQ/ADC distance plays in the reference: it only has to put the
 // true top-k inside the K' = max(2k, 20) candidates (ngh_graph_engine.dart:115)
-// that tsc_select.cu then re-ranks with the reference's exact fp64 arithmetic.
+// that the tail (tsc_tail.cuh) then re-ranks with the reference's exact fp64
+// arithmetic — and the tail PROVES that it did (certificate), re-running the query
+// in range mode when it cannot.
 //
 // Data movement: every warp owns a private ring of S stages in shared memory and
 // keeps it full with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP, the TMA
@@ -13,9 +16,16 @@
 // CTA-wide barrier exists in the main loop. Lanes read 16-byte chunks of the
 // staged rows (conflict-free LDS.128), accumulate in fp32, butterfly-reduce with
 // warp shuffles, and insert into a per-warp sorted candidate list in shared memory.
+//
+// mode 0 (first pass): per-warp top-K' lists -> block merge -> one list per CTA.
+// mode 1 (range pass): every row with key <= T[q] is appended to a global buffer; the
+//   launch exits at once when no query of its group needs it (the common case).
+// Tail: the last CTA to finish (atomic ticket) runs tsc_tail.cuh for the launch's queries
+// and, for a sharded index, pushes the shard's exact top-k to the consumers over NVLink
+// and merges (tsc_exchange.cuh) — scan, select, re-rank, exchange and merge are one kernel.
 #pragma once
 
-#include "tsc_common.cuh"
+#include "tsc_exchange.cuh"
 
 namespace tsc {
 
@@ -24,15 +34,28 @@ struct ScanParams {
   uint64_t n_rows;
   uint32_t row_bytes;        // row stride in bytes (multiple of 16)
   uint32_t chunks_per_row;   // row_bytes / 16
-  const float *queries;      // [QB, qld] fp32, zero padded to qld
+  const float *queries;      // [nq_total, qld] fp32, zero padded to qld
   uint32_t qld;              // padded dims = chunks_per_row * elems_per_chunk
-  uint32_t nq;               // valid queries in this launch (<= QB)
+  uint32_t q_base;           // mode 0: first query of this launch; mode 1: first retry_list entry
+  uint32_t nq;               // mode 0: valid queries in this launch (<= QB)
   const uint32_t *live_mask; // optional: bit r = row r may be returned; NULL = all live
   uint32_t kprime;           // candidates kept per list
   uint32_t stages;           // S
   uint32_t stage_bytes;      // R * row_bytes
-  uint64_t *cand;            // [QB][gridDim.x][kprime] (ordered key << 32 | shard row)
+  uint64_t *cand;            // [nq_total][gridDim.x][kprime] (ordered key << 32 | shard row)
   uint32_t sort_cap;         // pow2 >= warps * kprime (block-level merge buffer)
+  int mode;                  // 0 = top-K' lists, 1 = range collect
+  int fused_tail;            // the last CTA runs the tail (always in mode 1)
+  int xchg_in_tail;          // ... and the shard exchange
+  int last_retry;            // mode 1: the last range launch of the search resets retry_n
+  uint32_t nq_total;         // queries of the whole search (exchange loop)
+  uint32_t tail_sort_cap;    // Pair128 slots of the tail's sort buffer
+  uint32_t *done_counter;    // zero between launches
+  TailParams tail;
+  XchgParams xchg;
+  int64_t *x_out_ids;        // exchange output (global top-k), [nq_total, k]
+  double *x_out_dist;
+  uint32_t *x_out_counts;
 };
 
 // Insert (key,id) into a sorted (ascending) list of kp entries held in shared
@@ -71,39 +94,33 @@ __device__ __forceinline__ uint32_t list_insert(uint32_t *keys, uint32_t *ids, i
   return keys[kp - 1];
 }
 
-template <int DTYPE>
-struct Chunk;  // 16 bytes of a stored row -> fp32 lanes
+// A row passed the threshold test: keep it. mode 0: sorted insertion into the warp's list
+// (returns the new threshold); mode 1: append to the query slot's global range buffer
+// (threshold unchanged). Warp-uniform.
+__device__ __forceinline__ uint32_t scan_keep(const ScanParams &p, uint32_t *lkeys, uint32_t *lids,
+                                              uint32_t slot, uint32_t thr, uint32_t uk,
+                                              uint32_t row, int lane) {
+  if (p.mode == 0) return list_insert(lkeys, lids, (int)p.kprime, uk, row, lane);
+  if (lane == 0) {
+    const uint32_t s = atomicAdd(p.tail.range_count + slot, 1u);
+    if (s < kRangeCap) p.tail.range_buf[(size_t)slot * kRangeCap + s] = ((uint64_t)uk << 32) | row;
+  }
+  return thr;
+}
 
-template <>
-struct Chunk<kF32> {
-  static constexpr int kElems = 4;
-  __device__ static __forceinline__ void unpack(const uint4 &v, float (&f)[4]) {
-    f[0] = __uint_as_float(v.x);
-    f[1] = __uint_as_float(v.y);
-    f[2] = __uint_as_float(v.z);
-    f[3] = __uint_as_float(v.w);
+template <int METRIC>
+__device__ __forceinline__ uint32_t scan_key(float acc, float bb) {
+  float key;
+  if (METRIC == kL2) {
+    key = acc;
+  } else if (METRIC == kIP) {
+    key = -acc;
+  } else {
+    key = (bb > 0.0f) ? -acc * rsqrtf(bb) : 0.0f;
   }
-};
-template <>
-struct Chunk<kBF16> {
-  static constexpr int kElems = 8;
-  __device__ static __forceinline__ void unpack(const uint4 &v, float (&f)[8]) {
-    unpack_bf16x2(v.x, f[0], f[1]);
-    unpack_bf16x2(v.y, f[2], f[3]);
-    unpack_bf16x2(v.z, f[4], f[5]);
-    unpack_bf16x2(v.w, f[6], f[7]);
-  }
-};
-template <>
-struct Chunk<kF16> {
-  static constexpr int kElems = 8;
-  __device__ static __forceinline__ void unpack(const uint4 &v, float (&f)[8]) {
-    unpack_f16x2(v.x, f[0], f[1]);
-    unpack_f16x2(v.y, f[2], f[3]);
-    unpack_f16x2(v.z, f[4], f[5]);
-    unpack_f16x2(v.w, f[6], f[7]);
-  }
-};
+  key += 0.0f;  // -0.0 -> +0.0 so exact ties order by id only
+  return ordered_key(key);
+}
 
 // Shared-memory footprint (must match the carve-up in the kernel).
 __host__ __device__ inline size_t scan_smem_query_bytes(int qb, uint32_t qld) {
@@ -123,10 +140,11 @@ __host__ __device__ inline size_t scan_smem_warp_bytes(int qb, uint32_t kprime, 
 // ---- block-level merge: W sorted lists -> one list of kp per query -------------
 // (bitonic sort of the composites in shared memory; every bulk copy this CTA
 // issued has been waited on, so no async write is outstanding)
-__device__ __forceinline__ void scan_block_merge(const ScanParams &p, uint64_t *sortbuf,
+__device__ __forceinline__ void scan_block_merge(const ScanParams &p, const uint32_t *qi,
+                                                 uint32_t nq, uint64_t *sortbuf,
                                                  const uint32_t *lkeys, const uint32_t *lids,
                                                  uint32_t kp, int warp, int warps, int lane) {
-  for (uint32_t q = 0; q < p.nq; q++) {
+  for (uint32_t q = 0; q < nq; q++) {
     __syncthreads();
     for (uint32_t i = lane; i < kp; i += 32)
       sortbuf[(size_t)warp * kp + i] =
@@ -150,9 +168,75 @@ __device__ __forceinline__ void scan_block_merge(const ScanParams &p, uint64_t *
         __syncthreads();
       }
     }
-    uint64_t *out = p.cand + ((size_t)q * gridDim.x + blockIdx.x) * kp;
+    uint64_t *out = p.cand + ((size_t)qi[q] * gridDim.x + blockIdx.x) * kp;
     for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) out[i] = sortbuf[i];
   }
+}
+
+// Which queries does this launch work on? mode 0: q_base .. q_base + nq. mode 1: the
+// entries [q_base, q_base + QB) of the retry list; returns 0 when there are none (the
+// launch exits at once). Uniform over the grid.
+template <int QB>
+__device__ __forceinline__ uint32_t scan_queries(const ScanParams &p, uint32_t (&qi)[QB]) {
+  uint32_t nq = p.nq;
+  if (p.mode == 1) {
+    const uint32_t n_retry = __ldcg(p.tail.retry_n);
+    if (n_retry <= p.q_base) {
+      if (p.last_retry && blockIdx.x == 0 && threadIdx.x == 0 && n_retry != 0) *p.tail.retry_n = 0;
+      return 0;
+    }
+    nq = n_retry - p.q_base < (uint32_t)QB ? n_retry - p.q_base : (uint32_t)QB;
+  }
+#pragma unroll
+  for (int q = 0; q < QB; q++) {
+    const uint32_t j = (uint32_t)q < nq ? (uint32_t)q : 0u;
+    qi[q] = p.mode == 1 ? __ldcg(p.tail.retry_list + p.q_base + j) : p.q_base + j;
+  }
+  return nq;
+}
+
+// Everything after the main loop: publish the CTA's candidates, then the LAST CTA of the
+// grid runs the tail for the launch's queries and the exchange of the search.
+template <int METRIC, int DTYPE, int QB>
+__device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t (&qi)[QB],
+                                            uint32_t nq, uint8_t *smem, uint64_t *sortbuf,
+                                            const uint32_t *lkeys, const uint32_t *lids, int warp,
+                                            int warps, int lane) {
+  __shared__ uint32_t s_ticket;
+  if (p.mode == 0) scan_block_merge(p, qi, nq, sortbuf, lkeys, lids, p.kprime, warp, warps, lane);
+  if (!p.fused_tail) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(p.done_counter, 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.x - 1) return;
+  if (threadIdx.x == 0) *p.done_counter = 0;   // stream order: the next launch sees zero
+  __threadfence();
+  for (uint32_t q = 0; q < nq; q++)
+    tail_query<METRIC, DTYPE>(p.tail, qi[q], p.mode, q, smem, p.tail_sort_cap);
+  // the last range launch of a search leaves the retry list empty for the next search
+  // (queries beyond the in-stream range launches keep kFlagRetry: the host API re-runs them)
+  if (p.mode == 1 && p.last_retry && threadIdx.x == 0) *p.tail.retry_n = 0;
+  if (!p.xchg_in_tail) return;
+  // a first pass with uncertified queries leaves the exchange to the range launch
+  __syncthreads();
+  if (p.mode == 0 && __ldcg(p.tail.retry_n) != 0) return;
+  for (uint32_t q = 0; q < p.nq_total; q++) {
+    __syncthreads();
+    xchg_push(p.xchg, q, p.tail.k, p.tail.out_ids + (size_t)q * p.tail.k,
+              p.tail.out_dist + (size_t)q * p.tail.k);
+  }
+  if (!xchg_is_consumer(p.xchg, p.xchg.rank)) return;
+  uint32_t xcap = 2;
+  while (xcap < p.xchg.n_ranks * p.tail.k) xcap <<= 1;
+  for (uint32_t q = 0; q < p.nq_total; q++) {
+    __syncthreads();
+    xchg_wait_merge(p.xchg, q, p.tail.k, reinterpret_cast<Pair128 *>(smem), xcap,
+                    p.x_out_ids + (size_t)q * p.tail.k, p.x_out_dist + (size_t)q * p.tail.k,
+                    p.x_out_counts + q);
+  }
+  __syncthreads();
+  xchg_ack(p.xchg);
 }
 
 template <int METRIC, int DTYPE, int QB, int R>
@@ -164,6 +248,10 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   const int warps = blockDim.x >> 5;
   const uint32_t kp = p.kprime;
   const uint32_t S = p.stages;
+
+  uint32_t qi[QB];
+  const uint32_t nq = scan_queries<QB>(p, qi);
+  if (nq == 0) return;
 
   // ---- carve shared memory -------------------------------------------------
   float *qs = reinterpret_cast<float *>(smem);
@@ -181,7 +269,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   // ---- queries -> smem (zero rows for q >= nq), lists -> empty --------------
   for (uint32_t i = threadIdx.x; i < (uint32_t)QB * p.qld; i += blockDim.x) {
     uint32_t q = i / p.qld;
-    qs[i] = (q < p.nq) ? p.queries[i] : 0.0f;
+    qs[i] = (q < nq) ? p.queries[(size_t)qi[q] * p.qld + (i - q * p.qld)] : 0.0f;
   }
   for (uint32_t i = lane; i < (uint32_t)QB * kp; i += 32) {
     lkeys[i] = kEmptyKey;
@@ -215,9 +303,11 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     }
   }
 
+  // mode 0: threshold = the list's largest key; mode 1: fixed T + 1 (key <= T passes)
   uint32_t thr[QB];
 #pragma unroll
-  for (int q = 0; q < QB; q++) thr[q] = kEmptyKey;
+  for (int q = 0; q < QB; q++)
+    thr[q] = (p.mode == 1 && (uint32_t)q < nq) ? __ldcg(p.tail.range_thr + qi[q]) + 1u : kEmptyKey;
 
   uint32_t s = 0, parity = 0;
   const uint32_t cpr = p.chunks_per_row;
@@ -302,19 +392,10 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
       if (row >= p.n_rows || !((live >> r) & 1u)) continue;
 #pragma unroll
       for (int q = 0; q < QB; q++) {
-        float key;
-        if (METRIC == kL2) {
-          key = acc[q][r];
-        } else if (METRIC == kIP) {
-          key = -acc[q][r];
-        } else {
-          key = (bb[r] > 0.0f) ? -acc[q][r] * rsqrtf(bb[r]) : 0.0f;
-        }
-        key += 0.0f;  // -0.0 -> +0.0 so exact ties order by id only
-        uint32_t uk = ordered_key(key);
-        if (uk < thr[q] && (uint32_t)q < p.nq)
-          thr[q] = list_insert(lkeys + (size_t)q * kp, lids + (size_t)q * kp, (int)kp, uk,
-                               (uint32_t)row, lane);
+        const uint32_t uk = scan_key<METRIC>(acc[q][r], bb[r]);
+        if (uk < thr[q] && (uint32_t)q < nq)
+          thr[q] = scan_keep(p, lkeys + (size_t)q * kp, lids + (size_t)q * kp, (uint32_t)q, thr[q],
+                             uk, (uint32_t)row, lane);
       }
     }
 
@@ -324,33 +405,38 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     }
   }
 
-  scan_block_merge(p, sortbuf, lkeys, lids, kp, warp, warps, lane);
+  scan_finish<METRIC, DTYPE, QB>(p, qi, nq, smem, sortbuf, lkeys, lids, warp, warps, lane);
 }
 
 // K6: scan of a sparsely live column (WHERE prefilter / heavy tombstoning).
-// Same arithmetic and candidate lists as scan_topk_kernel, but the unit of data
-// movement is ONE LIVE ROW: a warp walks its share of the liveness bitmap (one
+// Same arithmetic, candidate lists, modes and tail as scan_topk_kernel, but the unit of
+// data movement is ONE LIVE ROW: a warp walks its share of the liveness bitmap (one
 // 32-bit word = 32 consecutive rows at a time) and issues a bulk copy only for rows
 // whose bit is set, so dead rows cost no HBM bytes (rows are whole 16-byte-aligned
 // byte ranges; at d=384 fp32 a row is exactly twelve 128-byte lines). The ring is a
-// queue of S one-row stages; rows are consumed in issue (= increasing id) order.
-//
-// PF = false: a warp takes single bitmap words (32 rows) round-robin and loads each word
-// when the previous one is exhausted — a dependent global load on the issue path.
-// PF = true (opt-in, TSC_SCAN_SPARSE_PF=1; written after the round's GPU budget was spent,
-// not yet measured): a warp takes BLOCKS of 32 consecutive words (1024 rows) round-robin;
-// lane l holds word l of the block (one coalesced 128-byte load), the next block is
-// prefetched while the current one is consumed, and all-zero words are skipped with a
-// ballot — no load latency on the issue path and cheap skipping at low selectivity.
-template <int METRIC, int DTYPE, int QB, bool PF = false>
+// queue of S one-row stages; rows are consumed in issue (= increasing id) order, G at a
+// time: one row per step left the warp latency-bound (ncu, profiles/r02_sparse_*: 168
+// dependent instructions per row at 6.7 cycles each, 48 % of HBM) — G rows' LDS / FMA /
+// shuffle chains are independent and interleave.
+template <int QB>
+struct SparseGroup {
+  static constexpr int kRows = QB == 1 ? 4 : (QB == 4 ? 2 : 1);
+};
+
+template <int METRIC, int DTYPE, int QB>
 __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int E = Chunk<DTYPE>::kElems;
+  constexpr int G = SparseGroup<QB>::kRows;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps = blockDim.x >> 5;
   const uint32_t kp = p.kprime;
   const uint32_t S = p.stages;
+
+  uint32_t qi[QB];
+  const uint32_t nq = scan_queries<QB>(p, qi);
+  if (nq == 0) return;
 
   float *qs = reinterpret_cast<float *>(smem);
   uint64_t *sortbuf = reinterpret_cast<uint64_t *>(smem + scan_smem_query_bytes(QB, p.qld));
@@ -366,7 +452,7 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
 
   for (uint32_t i = threadIdx.x; i < (uint32_t)QB * p.qld; i += blockDim.x) {
     uint32_t q = i / p.qld;
-    qs[i] = (q < p.nq) ? p.queries[i] : 0.0f;
+    qs[i] = (q < nq) ? p.queries[(size_t)qi[q] * p.qld + (i - q * p.qld)] : 0.0f;
   }
   for (uint32_t i = lane; i < (uint32_t)QB * kp; i += 32) {
     lkeys[i] = kEmptyKey;
@@ -386,7 +472,8 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
 
   uint32_t thr[QB];
 #pragma unroll
-  for (int q = 0; q < QB; q++) thr[q] = kEmptyKey;
+  for (int q = 0; q < QB; q++)
+    thr[q] = (p.mode == 1 && (uint32_t)q < nq) ? __ldcg(p.tail.range_thr + qi[q]) + 1u : kEmptyKey;
 
   // issue side: (word, remaining bits) cursor over this warp's bitmap words
   uint64_t word = gw;
@@ -401,47 +488,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
       word += GW;
     }
   };
-  // PF: block cursor. `cur` / `nxt` = this lane's word of the current / next block,
-  // `nz` = lanes of the current block whose word is non-zero and not yet consumed.
-  const uint64_t n_blocks = (n_words + 31) / 32;
-  uint64_t blk = gw;
-  uint32_t cur = 0, nxt = 0;
-  unsigned nz = 0;
-  auto load_block = [&](uint64_t b) -> uint32_t {
-    const uint64_t w = b * 32 + (uint64_t)lane;
-    uint32_t v = 0;
-    if (b < n_blocks && w < n_words) {
-      v = p.live_mask[w];
-      const uint64_t base_row = w * 32;
-      if (base_row + 32 > p.n_rows) v &= (uint32_t)((1ull << (p.n_rows - base_row)) - 1ull);
-    }
-    return v;
-  };
-  auto next_word = [&]() {   // warp-uniform: advance to the next non-zero word of this warp
-    bits = 0;
-    for (;;) {
-      if (nz) {
-        const int l = __ffs(nz) - 1;
-        nz &= nz - 1;
-        bits = __shfl_sync(0xFFFFFFFFu, cur, l);
-        word = blk * 32 + (uint64_t)l;
-        return;
-      }
-      blk += GW;
-      if (blk >= n_blocks) return;
-      cur = nxt;
-      nxt = load_block(blk + GW);
-      nz = __ballot_sync(0xFFFFFFFFu, cur != 0);
-    }
-  };
-  if (PF) {
-    cur = load_block(blk);
-    nxt = load_block(blk + GW);
-    nz = __ballot_sync(0xFFFFFFFFu, cur != 0);
-    if (blk < n_blocks) next_word();
-  } else {
-    load_word();
-  }
+  load_word();
+  // ring state: stages [head, head + inflight) mod S are in flight; the barrier of stage s
+  // completes its phase number (uses of s so far) & 1
   uint32_t head = 0, tail = 0, inflight = 0, hpar = 0;
   // row ids of the stages in flight (uniform per warp): kept in registers of lane s
   uint32_t my_row = kInvalidRow;
@@ -461,82 +510,106 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
       if (++tail == S) tail = 0;
       inflight++;
       if (!bits) {
-        if (PF) {
-          next_word();
-        } else {
-          word += GW;
-          load_word();
-        }
+        word += GW;
+        load_word();
       }
     }
     if (inflight == 0) break;
 
-    mbar_wait(smem_u32(&bars[head]), hpar);
-    const uint32_t row = __shfl_sync(0xFFFFFFFFu, my_row, head);
-    float acc[QB];
-    float bb = 0.0f;
+    // ---- consume up to G rows at once (warp-uniform n) -------------------------------
+    const uint32_t n = inflight < (uint32_t)G ? inflight : (uint32_t)G;
+    uint32_t st_idx[G], rows_g[G];
 #pragma unroll
-    for (int q = 0; q < QB; q++) acc[q] = 0.0f;
-    const uint4 *stage = reinterpret_cast<const uint4 *>(ring + (size_t)head * p.stage_bytes);
+    for (int g = 0; g < G; g++) {
+      uint32_t h = head + ((uint32_t)g < n ? (uint32_t)g : 0u);
+      uint32_t par = hpar;
+      if (h >= S) {
+        h -= S;
+        par ^= 1u;
+      }
+      st_idx[g] = h;
+      if ((uint32_t)g < n) mbar_wait(smem_u32(&bars[h]), par);
+      rows_g[g] = __shfl_sync(0xFFFFFFFFu, my_row, (int)h);
+    }
+    float acc[QB][G];
+    float bb[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+      bb[g] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < QB; q++) acc[q][g] = 0.0f;
+    }
 #pragma unroll 2
     for (uint32_t c = lane; c < cpr; c += 32) {
-      float b[E];
-      uint4 v = stage[c];
-      Chunk<DTYPE>::unpack(v, b);
+      float b[G][E];
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const uint4 v =
+            reinterpret_cast<const uint4 *>(ring + (size_t)st_idx[g] * p.stage_bytes)[c];
+        Chunk<DTYPE>::unpack(v, b[g]);
+      }
       if (METRIC == kCos) {
 #pragma unroll
-        for (int e = 0; e < E; e++) bb = fmaf(b[e], b[e], bb);
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int e = 0; e < E; e++) bb[g] = fmaf(b[g][e], b[g][e], bb[g]);
       }
 #pragma unroll
       for (int q = 0; q < QB; q++) {
+        float a[E];
         const float4 *qp = reinterpret_cast<const float4 *>(qs + (size_t)q * p.qld + (size_t)c * E);
 #pragma unroll
         for (int h = 0; h < E / 4; h++) {
           float4 t = qp[h];
-          const float a[4] = {t.x, t.y, t.z, t.w};
+          a[4 * h + 0] = t.x;
+          a[4 * h + 1] = t.y;
+          a[4 * h + 2] = t.z;
+          a[4 * h + 3] = t.w;
+        }
 #pragma unroll
-          for (int e = 0; e < 4; e++) {
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int e = 0; e < E; e++) {
             if (METRIC == kL2) {
-              float d = a[e] - b[4 * h + e];
-              acc[q] = fmaf(d, d, acc[q]);
+              float d = a[e] - b[g][e];
+              acc[q][g] = fmaf(d, d, acc[q][g]);
             } else {
-              acc[q] = fmaf(a[e], b[4 * h + e], acc[q]);
+              acc[q][g] = fmaf(a[e], b[g][e], acc[q][g]);
             }
           }
-        }
       }
     }
-    __syncwarp();  // stage `head` is free again
-    if (++head == S) {
-      head = 0;
+    __syncwarp();  // the n stages are free again
+    head += n;
+    if (head >= S) {
+      head -= S;
       hpar ^= 1u;
     }
-    inflight--;
+    inflight -= n;
 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      if (METRIC == kCos) bb += __shfl_xor_sync(0xFFFFFFFFu, bb, o);
 #pragma unroll
-      for (int q = 0; q < QB; q++) acc[q] += __shfl_xor_sync(0xFFFFFFFFu, acc[q], o);
+      for (int g = 0; g < G; g++) {
+        if (METRIC == kCos) bb[g] += __shfl_xor_sync(0xFFFFFFFFu, bb[g], o);
+#pragma unroll
+        for (int q = 0; q < QB; q++) acc[q][g] += __shfl_xor_sync(0xFFFFFFFFu, acc[q][g], o);
+      }
     }
 #pragma unroll
-    for (int q = 0; q < QB; q++) {
-      float key;
-      if (METRIC == kL2) {
-        key = acc[q];
-      } else if (METRIC == kIP) {
-        key = -acc[q];
-      } else {
-        key = (bb > 0.0f) ? -acc[q] * rsqrtf(bb) : 0.0f;
+    for (int g = 0; g < G; g++) {
+      if ((uint32_t)g >= n) continue;
+#pragma unroll
+      for (int q = 0; q < QB; q++) {
+        const uint32_t uk = scan_key<METRIC>(acc[q][g], bb[g]);
+        if (uk < thr[q] && (uint32_t)q < nq)
+          thr[q] = scan_keep(p, lkeys + (size_t)q * kp, lids + (size_t)q * kp, (uint32_t)q, thr[q],
+                             uk, rows_g[g], lane);
       }
-      key += 0.0f;
-      uint32_t uk = ordered_key(key);
-      if (uk < thr[q] && (uint32_t)q < p.nq)
-        thr[q] = list_insert(lkeys + (size_t)q * kp, lids + (size_t)q * kp, (int)kp, uk, row, lane);
     }
   }
   __syncwarp();
-  scan_block_merge(p, sortbuf, lkeys, lids, kp, warp, warps, lane);
+  scan_finish<METRIC, DTYPE, QB>(p, qi, nq, smem, sortbuf, lkeys, lids, warp, warps, lane);
 }
 
 }  // namespace tsc

@@ -1,0 +1,515 @@
+// tsc_tail.cuh — K5: the tail of every search — candidate selection, exact fp64 re-rank,
+// exactness certificate, final ordering.
+//
+// One CTA works on one query (as a standalone kernel: one CTA per query; fused into the
+// scan kernel: the last CTA to finish, tsc_scan.cuh):
+//   1. pick the K' best (fp32 key, row) composites out of the M the scan / GEMM kernels
+//      published (shared-memory bitonic sort when M is small, 11-bit radix select
+//      otherwise);
+//   2. re-rank them with the reference's exact arithmetic — `_exactDistance`
+//      core/ngh_graph_engine.dart:908-946: fp32 inputs widened to fp64, sequential index
+//      order, every multiply and add a separate IEEE double operation (no FMA:
+//      __dmul_rn/__dadd_rn), sqrt / divide correctly rounded — so the distances returned
+//      are bit-identical to the Dart code. ONE LANE owns one candidate: the add chain is
+//      sequential by definition, so a warp re-ranks 32 candidates in the time of one;
+//   3. drop `distance > threshold` (:127), sort ascending with Dart's double.compareTo
+//      order (-0.0 < 0.0, NaN last; ties by node id), cut at k (:133-134);
+//   4. CERTIFY the candidate stage. The reference re-ranks everything it kept (:115-134);
+//      this path keeps K' rows chosen by an approximate fp32 key, so it has to prove it
+//      kept enough: with kappa_piv the K'-th smallest key (every row that is not a
+//      candidate has key >= kappa_piv), D_adm the largest distance that could still enter
+//      the result, K*(D) the key an error-free candidate stage would give a row at
+//      distance D and |key - K*| <= c_rel |K*| + A the proven error of the stage
+//      (CertModel, filled by the host per metric / dtype / path):
+//          certified  <=>  K*(D_adm) < (kappa_piv - A) / (1 + c_rel)
+//      Uncertified queries get a threshold T >= every key a row at distance <= D_adm can
+//      have and are re-run by the RANGE pass (scan kernel, mode 1): it collects every row
+//      with key <= T, this tail re-ranks all of them, and the result is exact regardless
+//      of how many near-ties surround the k-th neighbour (up to kRangeCap rows).
+#pragma once
+
+#include "tsc_common.cuh"
+
+namespace tsc {
+
+constexpr uint32_t kSelectSortMax = 1024;  // M above this goes through radix select
+constexpr uint32_t kMaxRerank = 512;
+constexpr int kRadixBins = 2048;           // 11-bit digits
+constexpr uint32_t kRangeCap = 4096;       // rows the range pass can hold per query
+constexpr uint32_t kRangeSlots = 8;        // queries per range pass (= the scan kernel's QB max)
+constexpr uint32_t kRetryLaunches = 4;     // in-stream range passes per search
+
+// per-query flag values (TailParams::flags)
+enum : uint32_t { kFlagExact = 0, kFlagRetry = 1, kFlagUncertified = 2 };
+// TailParams::stat slots
+enum : int { kStatCertified = 0, kStatRetried = 1, kStatUncertified = 2, kStatRangeRows = 3,
+             kStatRetryAsked = 4, kStatSlots = 8 };
+
+struct Pair128 {
+  uint64_t hi, lo;
+};
+__device__ __forceinline__ bool pair_gt(const Pair128 &a, const Pair128 &b) {
+  return a.hi > b.hi || (a.hi == b.hi && a.lo > b.lo);
+}
+
+// block-wide bitonic sort of n (power of two) pairs in shared memory, ascending
+__device__ __forceinline__ void bitonic_sort_pairs(Pair128 *v, uint32_t n) {
+  for (uint32_t k = 2; k <= n; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        uint32_t x = i ^ j;
+        if (x > i) {
+          Pair128 a = v[i], b = v[x];
+          bool up = (i & k) == 0;
+          if (pair_gt(a, b) == up) {
+            v[i] = b;
+            v[x] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ double key64_to_double(uint64_t kk) {
+  if (kk == ~0ull) return __longlong_as_double(0x7FF8000000000000ll);
+  uint64_t b = (kk & 0x8000000000000000ull) ? (kk & 0x7FFFFFFFFFFFFFFFull) : ~kk;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ float key32_to_float(uint32_t uk) {
+  uint32_t b = (uk & 0x80000000u) ? (uk & 0x7FFFFFFFu) : ~uk;
+  return __uint_as_float(b);
+}
+
+template <int DTYPE>
+__device__ __forceinline__ float load_elem(const uint8_t *row, uint32_t i) {
+  if (DTYPE == kF32) return reinterpret_cast<const float *>(row)[i];
+  if (DTYPE == kBF16)
+    return __uint_as_float((uint32_t)reinterpret_cast<const uint16_t *>(row)[i] << 16);
+  return __half2float(reinterpret_cast<const __half *>(row)[i]);
+}
+
+// Error model of a candidate stage in key space: |key - K*| <= c_rel * |K*| + A(q),
+// A(q) = a_q * ||q|| + a_e * ||q16 - q|| + a_0. K*(D) = D^2 (L2; minus ||q||^2 when
+// l2_shift: the tensor path's keys omit that constant), D (inner product: D = -dot),
+// (D - 1) * ||q|| (cosine: the stages never divide by ||q||).
+struct CertModel {
+  float c_rel, a_q, a_e, a_0;
+  int l2_shift;
+};
+
+struct TailParams {
+  const uint64_t *cand;     // [nq][m] composites (ordered key << 32 | shard row), first pass
+  uint32_t m;               // candidates per query
+  uint32_t kprime;          // candidates re-ranked by the first pass (<= kMaxRerank)
+  uint32_t k;               // results per query
+  const uint8_t *rows;      // shard rows, device storage dtype
+  uint32_t row_bytes;
+  uint32_t dims;
+  const float *queries;     // [nq, qld] fp32
+  uint32_t qld;
+  double threshold;         // NaN = none
+  int64_t first_node_id;
+  int64_t *out_ids;         // [nq, k]
+  double *out_dist;         // [nq, k]
+  uint32_t *out_counts;     // [nq]
+  CertModel cert;           // error model of the stage that produced `cand`
+  CertModel cert_range;     // error model of the range pass (scan kernel, exact fp32 query)
+  const float *enorm;       // [nq] ||q16 - q||_2 (tensor path) or NULL
+  uint32_t *flags;          // [nq] kFlag*
+  uint32_t *range_thr;      // [nq] ordered fp32 key T: the range pass collects key <= T
+  uint32_t *retry_list;     // compacted indices of the queries that need the range pass
+  uint32_t *retry_n;
+  uint32_t *range_count;    // [kRangeSlots] rows collected per slot of the running range pass
+  uint64_t *range_buf;      // [kRangeSlots][kRangeCap] composites
+  unsigned long long *stat; // [kStatSlots] kStat*
+};
+
+// shared memory the tail needs (dynamic): Pair128[sort_cap] | hist[kRadixBins] | q[qld]
+__host__ __device__ inline size_t tail_smem_bytes(uint32_t sort_cap, uint32_t qld) {
+  return (size_t)sort_cap * sizeof(Pair128) + (size_t)kRadixBins * 4 + (size_t)qld * 4 + 64;
+}
+__host__ __device__ inline uint32_t tail_sort_cap(uint32_t m, uint32_t kprime, bool range) {
+  uint32_t need = range ? kRangeCap : (m <= kSelectSortMax ? m : kprime);
+  uint32_t p = 2;
+  while (p < need) p <<= 1;
+  return p;
+}
+
+// 16 bytes of a stored row -> fp32 lanes (shared with tsc_scan.cuh)
+template <int DTYPE>
+struct Chunk;
+template <>
+struct Chunk<kF32> {
+  static constexpr int kElems = 4;
+  __device__ static __forceinline__ void unpack(const uint4 &v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z);
+    f[3] = __uint_as_float(v.w);
+  }
+};
+template <>
+struct Chunk<kBF16> {
+  static constexpr int kElems = 8;
+  __device__ static __forceinline__ void unpack(const uint4 &v, float (&f)[8]) {
+    unpack_bf16x2(v.x, f[0], f[1]);
+    unpack_bf16x2(v.y, f[2], f[3]);
+    unpack_bf16x2(v.z, f[4], f[5]);
+    unpack_bf16x2(v.w, f[6], f[7]);
+  }
+};
+template <>
+struct Chunk<kF16> {
+  static constexpr int kElems = 8;
+  __device__ static __forceinline__ void unpack(const uint4 &v, float (&f)[8]) {
+    unpack_f16x2(v.x, f[0], f[1]);
+    unpack_f16x2(v.y, f[2], f[3]);
+    unpack_f16x2(v.z, f[4], f[5]);
+    unpack_f16x2(v.w, f[6], f[7]);
+  }
+};
+
+// `_exactDistance` (core/ngh_graph_engine.dart:908-946) for one stored row by ONE lane:
+// the loop of the Dart code as written — i = 0..d-1, sums start at +0.0, one rounded
+// multiply and one rounded add per element — which is what makes the result bit-identical.
+// The loads of the next chunks do not depend on the add chain, so they are issued ahead
+// (unroll 4) and the lane runs at the latency of the dependent DADD chain.
+// s0 = dot / l2 sum, s1 = magB (cosine only); exact_finish() turns them into the distance.
+template <int METRIC, int DTYPE>
+__device__ __forceinline__ void lane_exact_sums(const float *qs, const uint8_t *row, uint32_t d,
+                                                double &s0, double &s1) {
+  constexpr int E = Chunk<DTYPE>::kElems;
+  s0 = 0.0;
+  s1 = 0.0;
+  const uint4 *rp = reinterpret_cast<const uint4 *>(row);
+  const uint32_t full = d / E;
+#pragma unroll 4
+  for (uint32_t c = 0; c < full; c++) {
+    const uint4 v = __ldg(rp + c);
+    float b[E];
+    Chunk<DTYPE>::unpack(v, b);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const double a = (double)qs[c * E + e], bb = (double)b[e];
+      if (METRIC == kL2) {
+        const double diff = __dsub_rn(a, bb);
+        s0 = __dadd_rn(s0, __dmul_rn(diff, diff));
+      } else {
+        s0 = __dadd_rn(s0, __dmul_rn(a, bb));
+        if (METRIC == kCos) s1 = __dadd_rn(s1, __dmul_rn(bb, bb));
+      }
+    }
+  }
+  for (uint32_t i = full * E; i < d; i++) {  // ragged tail of the last 16-byte chunk
+    const double a = (double)qs[i], bb = (double)load_elem<DTYPE>(row, i);
+    if (METRIC == kL2) {
+      const double diff = __dsub_rn(a, bb);
+      s0 = __dadd_rn(s0, __dmul_rn(diff, diff));
+    } else {
+      s0 = __dadd_rn(s0, __dmul_rn(a, bb));
+      if (METRIC == kCos) s1 = __dadd_rn(s1, __dmul_rn(bb, bb));
+    }
+  }
+}
+//   mag_a: sum of q[i]^2 (cosine only; the same for every candidate of a query)
+template <int METRIC>
+__device__ __forceinline__ double exact_finish(double s0, double s1, double mag_a) {
+  if (METRIC == kL2) return sqrt(s0);                      // :920-927
+  if (METRIC == kIP) return -s0;                           // :929-935, negated at :914
+  const double denom = __dmul_rn(sqrt(mag_a), sqrt(s1));   // :937-946
+  const double sim = denom > 0.0 ? __ddiv_rn(s0, denom) : 0.0;
+  return __dsub_rn(1.0, sim);
+}
+// sum of q[i]^2, sequential from +0.0 (magA of _cosineSimlarity); also ||q||^2 of the certificate
+__device__ __forceinline__ double lane_mag_a(const float *qs, uint32_t d) {
+  double m = 0.0;
+#pragma unroll 4
+  for (uint32_t e = 0; e < d; e++) {
+    const double a = (double)qs[e];
+    m = __dadd_rn(m, __dmul_rn(a, a));
+  }
+  return m;
+}
+
+// One radix-select digit pass over the composites: histogram the `bits`-wide digit
+// at `shift` of every entry matching (prefix, mask); warp 0 finds the bucket where
+// the running count crosses s_remaining and narrows the prefix.
+__device__ __forceinline__ void radix_pass(const uint64_t *cand, uint32_t m, int shift, int bits,
+                                           uint64_t mask, uint32_t *hist, uint64_t *s_prefix,
+                                           uint32_t *s_remaining, uint32_t *s_bucket_count) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t nb = 1u << bits;
+  for (uint32_t i = tid; i < nb; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const uint64_t prefix = *s_prefix;
+  for (uint32_t i = tid; i < m; i += blockDim.x) {
+    uint64_t v = __ldcg(cand + i);
+    if ((v & mask) == prefix) atomicAdd(&hist[(uint32_t)(v >> shift) & (nb - 1)], 1u);
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const uint32_t per = nb / 32;  // buckets per lane (nb >= 32)
+    uint32_t sum = 0;
+    for (uint32_t i = 0; i < per; i++) sum += hist[tid * per + i];
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if ((int)tid >= o) inc += t;
+    }
+    const uint32_t exc = inc - sum, rem = *s_remaining;
+    if (exc < rem && rem <= inc) {  // exactly one lane: m >= remaining entries match
+      uint32_t cum = exc, b = tid * per;
+      for (uint32_t i = 0; i < per; i++) {
+        uint32_t h = hist[tid * per + i];
+        if (cum + h >= rem) {
+          b = tid * per + i;
+          *s_bucket_count = h;
+          break;
+        }
+        cum += h;
+      }
+      *s_remaining = rem - cum;
+      *s_prefix = prefix | ((uint64_t)b << shift);
+    }
+  }
+  __syncthreads();
+}
+
+// K*(D): the key an error-free candidate stage would give a row at exact distance D
+__device__ __forceinline__ double key_star(int metric, double D, double qn, double q2,
+                                           int l2_shift) {
+  if (metric == kL2) return l2_shift ? D * D - q2 : D * D;
+  if (metric == kIP) return D;
+  return (D - 1.0) * qn;
+}
+
+// The tail for query `qi`, executed by every thread of the CTA (any blockDim that is a
+// multiple of 32). mode 0: first pass over cand[qi][0..m); mode 1: range pass over
+// range_buf[slot][0..range_count[slot]). `sm` = tail_smem_bytes(sort_cap, qld) bytes.
+template <int METRIC, int DTYPE>
+__device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t slot, uint8_t *sm,
+                           uint32_t sort_cap) {
+  Pair128 *buf = reinterpret_cast<Pair128 *>(sm);
+  uint32_t *hist = reinterpret_cast<uint32_t *>(sm + (size_t)sort_cap * sizeof(Pair128));
+  float *qs = reinterpret_cast<float *>(hist + kRadixBins);
+  __shared__ uint64_t s_prefix;
+  __shared__ uint32_t s_remaining, s_count, s_bucket, s_valid;
+  __shared__ double s_mag_a;
+
+  const uint32_t tid = threadIdx.x;
+  __syncthreads();   // the caller's use of `sm` is over
+  for (uint32_t i = tid; i < p.qld; i += blockDim.x) qs[i] = p.queries[(size_t)qi * p.qld + i];
+  if (tid == 0) {
+    s_prefix = 0;
+    s_remaining = p.kprime;
+    s_count = 0;
+    s_bucket = 0;
+    s_valid = 0;
+  }
+  __syncthreads();
+
+  // ---- 1. candidates -> buf[0 .. ncand).hi (unordered), pivot, all_in ------------------
+  uint32_t ncand;
+  uint64_t pivot = ~0ull;   // K'-th smallest composite of the first pass
+  bool all_in = false;      // every live row of the shard is a candidate
+  bool overflow = false;    // range pass: more rows than kRangeCap
+  if (mode == 1) {
+    const uint32_t cnt = __ldcg(p.range_count + slot);
+    overflow = cnt > kRangeCap;
+    ncand = overflow ? 0u : cnt;
+    const uint64_t *src = p.range_buf + (size_t)slot * kRangeCap;
+    for (uint32_t i = tid; i < sort_cap; i += blockDim.x) {
+      buf[i].hi = i < ncand ? __ldcg(src + i) : ~0ull;
+      buf[i].lo = 0;
+    }
+    all_in = true;   // by construction: every row that can matter was collected
+  } else if (p.m <= kSelectSortMax) {
+    const uint64_t *cand = p.cand + (size_t)qi * p.m;
+    uint32_t valid = 0;
+    for (uint32_t i = tid; i < sort_cap; i += blockDim.x) {
+      const uint64_t v = (i < p.m) ? __ldcg(cand + i) : ~0ull;
+      buf[i].hi = v;
+      buf[i].lo = 0;
+      valid += (uint32_t)v != kInvalidRow;
+    }
+    if (valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    bitonic_sort_pairs(buf, sort_cap);
+    const uint32_t nv = s_valid;
+    ncand = p.kprime < nv ? p.kprime : nv;
+    all_in = nv < p.kprime;
+    if (!all_in) pivot = buf[p.kprime - 1].hi;
+  } else {
+    // radix select of the K'-th smallest composite: three 11/11/10-bit passes over
+    // the key half; the id half is only walked when the pivot key is shared by
+    // more entries than are still needed (ties at the cut).
+    const uint64_t *cand = p.cand + (size_t)qi * p.m;
+    radix_pass(cand, p.m, 53, 11, 0ull, hist, &s_prefix, &s_remaining, &s_bucket);
+    radix_pass(cand, p.m, 42, 11, ~0ull << 53, hist, &s_prefix, &s_remaining, &s_bucket);
+    radix_pass(cand, p.m, 32, 10, ~0ull << 42, hist, &s_prefix, &s_remaining, &s_bucket);
+    if (s_bucket == s_remaining) {
+      pivot = s_prefix | 0xFFFFFFFFull;
+    } else {
+      radix_pass(cand, p.m, 21, 11, ~0ull << 32, hist, &s_prefix, &s_remaining, &s_bucket);
+      radix_pass(cand, p.m, 10, 11, ~0ull << 21, hist, &s_prefix, &s_remaining, &s_bucket);
+      radix_pass(cand, p.m, 0, 10, ~0ull << 10, hist, &s_prefix, &s_remaining, &s_bucket);
+      pivot = s_prefix;
+    }
+    for (uint32_t i = tid; i < sort_cap; i += blockDim.x) {
+      buf[i].hi = ~0ull;
+      buf[i].lo = 0;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < p.m; i += blockDim.x) {
+      const uint64_t v = __ldcg(cand + i);
+      if (v <= pivot && (uint32_t)v != kInvalidRow) {
+        const uint32_t s = atomicAdd(&s_count, 1u);
+        if (s < sort_cap) buf[s].hi = v;
+      }
+    }
+    __syncthreads();
+    ncand = s_count < p.kprime ? s_count : p.kprime;
+    // fewer than K' valid composites: the K'-th smallest is an empty slot (key 0xFFFFFFFF)
+    all_in = (uint32_t)(pivot >> 32) == kEmptyKey;
+  }
+  __syncthreads();
+
+  // ---- 2. exact fp64 re-rank, one lane per candidate -----------------------------------
+  // |q|^2 (magA of _cosineSimlarity; also the certificate's ||q||^2) is one more sequential
+  // chain: a spare lane computes it while the others stream their rows. Only when every
+  // thread has a candidate (K' >= blockDim, range pass) does it cost a chain of its own.
+  const bool mag_inline = ncand < blockDim.x;   // block-uniform
+  if (!mag_inline) {
+    if (tid == 0) s_mag_a = lane_mag_a(qs, p.dims);
+    __syncthreads();
+  }
+  for (uint32_t base = 0; base < ncand || (mag_inline && base == 0); base += blockDim.x) {
+    const uint32_t i = base + tid;
+    double s0 = 0.0, s1 = 0.0;
+    uint32_t row = kInvalidRow;
+    if (i < ncand) {
+      row = (uint32_t)buf[i].hi;
+      if (row != kInvalidRow)
+        lane_exact_sums<METRIC, DTYPE>(qs, p.rows + (size_t)row * p.row_bytes, p.dims, s0, s1);
+    } else if (mag_inline && i == ncand) {
+      s_mag_a = lane_mag_a(qs, p.dims);
+    }
+    if (mag_inline) __syncthreads();   // the loop body runs exactly once in this case
+    if (i < ncand) {
+      uint64_t hi = ~0ull, lo = ~0ull;
+      if (row != kInvalidRow) {
+        const double d = exact_finish<METRIC>(s0, s1, s_mag_a);
+        const bool drop = (p.threshold == p.threshold) && (d > p.threshold);  // :127
+        if (!drop) {
+          hi = ordered_key64(d);
+          lo = (uint64_t)row;
+        }
+      }
+      buf[i].hi = hi;
+      buf[i].lo = lo;
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. final order -------------------------------------------------------------------
+  uint32_t n2 = 2;
+  while (n2 < ncand) n2 <<= 1;
+  if (n2 > sort_cap) n2 = sort_cap;
+  for (uint32_t i = ncand + tid; i < n2; i += blockDim.x) {
+    buf[i].hi = ~0ull;
+    buf[i].lo = ~0ull;
+  }
+  __syncthreads();
+  bitonic_sort_pairs(buf, n2);
+
+  // ---- 4. certificate (first pass) / verdict (range pass), by one thread ---------------------
+  if (tid == 0) {
+    uint32_t kept = 0;   // results that survive the threshold, up to k
+    while (kept < p.k && kept < n2 && buf[kept].lo != ~0ull) kept++;
+    s_count = kept;
+    uint32_t flag = kFlagExact;
+    if (mode == 1) {
+      if (overflow) flag = kFlagUncertified;
+      atomicAdd(p.stat + (overflow ? kStatUncertified : kStatRetried), 1ull);
+      atomicAdd(p.stat + kStatRangeRows, (unsigned long long)__ldcg(p.range_count + slot));
+      p.range_count[slot] = 0;
+    } else if (!all_in) {
+      const double q2 = s_mag_a, qn = sqrt(q2);
+      const double en = p.enorm ? (double)p.enorm[qi] : 0.0;
+      // D_adm: a row at a smaller distance would enter the result
+      double d_adm;
+      if (kept == p.k) {
+        d_adm = key64_to_double(buf[p.k - 1].hi);
+      } else {
+        d_adm = (p.threshold == p.threshold) ? p.threshold
+                                             : __longlong_as_double(0x7FF0000000000000ll);
+      }
+      const double inf = __longlong_as_double(0x7FF0000000000000ll);
+      if (!(d_adm == d_adm)) d_adm = inf;   // NaN ranks last: anything would enter before it
+      const bool zero_q = METRIC != kL2 && q2 == 0.0;   // every key and distance is the same
+      bool ok = zero_q;
+      uint32_t thr_key = kEmptyKey - 1u;
+      if (!zero_q) {
+        const double A = (double)p.cert.a_q * qn + (double)p.cert.a_e * en + (double)p.cert.a_0;
+        double ks = key_star(METRIC, d_adm, qn, q2, p.cert.l2_shift);
+        ks += fabs(ks) * 1e-12;
+        const double kpiv = (double)key32_to_float((uint32_t)(pivot >> 32));
+        const double lower = (kpiv - A) / (1.0 + (double)p.cert.c_rel);
+        ok = ks < lower;   // false for NaN / inf on either side
+        if (!ok) {
+          // T: no row at distance <= D_adm can have a scan key above it
+          const double Ar = (double)p.cert_range.a_q * qn + (double)p.cert_range.a_0;
+          double ksr = key_star(METRIC, d_adm, qn, q2, p.cert_range.l2_shift);
+          ksr += fabs(ksr) * 1e-12;
+          const double t = ksr + fabs(ksr) * (double)p.cert_range.c_rel + Ar;
+          float tf = (t == t) ? __double2float_ru(t) : __int_as_float(0x7F800000);
+          tf += 0.0f;
+          thr_key = ordered_key(tf);
+        }
+      }
+      if (ok) {
+        atomicAdd(p.stat + kStatCertified, 1ull);
+      } else {
+        flag = kFlagRetry;
+        atomicAdd(p.stat + kStatRetryAsked, 1ull);
+        p.range_thr[qi] = thr_key;
+        const uint32_t s = atomicAdd(p.retry_n, 1u);
+        p.retry_list[s] = qi;
+      }
+    } else {
+      atomicAdd(p.stat + kStatCertified, 1ull);
+    }
+    p.flags[qi] = flag;
+  }
+  __syncthreads();
+
+  // ---- 5. emit (an overflowed range pass keeps the first pass's best-effort result) --------
+  if (!(mode == 1 && overflow)) {
+    const uint32_t kept = s_count;
+    for (uint32_t j = tid; j < p.k; j += blockDim.x) {
+      int64_t id = -1;
+      double d = __longlong_as_double(0x7FF8000000000000ll);
+      if (j < kept) {
+        id = p.first_node_id + (int64_t)buf[j].lo;
+        d = key64_to_double(buf[j].hi);
+      }
+      p.out_ids[(size_t)qi * p.k + j] = id;
+      p.out_dist[(size_t)qi * p.k + j] = d;
+    }
+    if (tid == 0) p.out_counts[qi] = kept;
+  }
+  __syncthreads();
+}
+
+// standalone form: one CTA per query (tensor path, multi-pass scans)
+constexpr int kTailThreads = 256;
+template <int METRIC, int DTYPE>
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailParams p, uint32_t sort_cap) {
+  extern __shared__ __align__(16) uint8_t tail_smem[];
+  tail_query<METRIC, DTYPE>(p, blockIdx.x, 0, 0, tail_smem, sort_cap);
+}
+
+}  // namespace tsc

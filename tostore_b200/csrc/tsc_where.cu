@@ -104,11 +104,9 @@ static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *
   return TSC_OK;
 }
 
-extern "C" {
+namespace tsc {
 
-int32_t tsc_index_column_create(uint64_t handle, uint32_t column_id, uint8_t col_type) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+int32_t ix_column_create(Index *ix, uint32_t column_id, uint8_t col_type) {
   if (col_type > TSC_COL_F64) {
     set_error("column_create: unknown column type %u", col_type);
     return TSC_ERR_BAD_ARG;
@@ -143,10 +141,8 @@ int32_t tsc_index_column_create(uint64_t handle, uint32_t column_id, uint8_t col
   return TSC_OK;
 }
 
-int32_t tsc_index_column_append(uint64_t handle, uint32_t column_id, uint64_t first_node_id,
-                                const void *values, const uint8_t *is_null, uint64_t n) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+int32_t ix_column_append(Index *ix, uint32_t column_id, uint64_t first_node_id, const void *values,
+                         const uint8_t *is_null, uint64_t n) {
   if (n == 0) return TSC_OK;
   if (!values) {
     set_error("column_append: NULL values");
@@ -194,10 +190,8 @@ int32_t tsc_index_column_append(uint64_t handle, uint32_t column_id, uint64_t fi
   return TSC_OK;
 }
 
-int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_t n_ops,
-                               const void *in_args, uint32_t n_in_args, uint64_t *out_matched) {
-  Index *ix = lookup_index(handle);
-  if (!ix) return TSC_ERR_BAD_HANDLE;
+int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                        uint32_t n_in_args, uint64_t *out_matched) {
   if ((n_ops && !ops) || n_ops > (uint32_t)kWhereMaxOps || (n_in_args && !in_args) ||
       n_in_args > 4096) {
     set_error("filter_where: bad program (n_ops=%u <= %d, n_in_args=%u <= 4096)", n_ops,
@@ -251,6 +245,43 @@ int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_
   ix->live_dirty = true;
   if (out_matched) *out_matched = matched;
   return TSC_OK;
+}
+
+}  // namespace tsc
+
+extern "C" {
+
+#define TSC_WHERE_DISPATCH(handle, grp_call, ix_call)                                   \
+  TSC_API_TRY                                                                           \
+  if (GroupRef g = lookup_group(handle)) {                                              \
+    std::lock_guard<std::mutex> glk(g->mu);                                             \
+    return grp_call;                                                                    \
+  }                                                                                     \
+  IndexRef ref = lookup_index(handle);                                                  \
+  if (!ref) return TSC_ERR_BAD_HANDLE;                                                  \
+  Index *ix = ref.get();                                                                \
+  if (ix->host_only) {                                                                  \
+    set_error("host-only self-test handle: no device entry point works on it");         \
+    return TSC_ERR_UNSUPPORTED;                                                         \
+  }                                                                                     \
+  return ix_call;                                                                       \
+  TSC_API_CATCH
+
+int32_t tsc_index_column_create(uint64_t handle, uint32_t column_id, uint8_t col_type) {
+  TSC_WHERE_DISPATCH(handle, grp_column_create(*g, column_id, col_type),
+                     ix_column_create(ix, column_id, col_type))
+}
+
+int32_t tsc_index_column_append(uint64_t handle, uint32_t column_id, uint64_t first_node_id,
+                                const void *values, const uint8_t *is_null, uint64_t n) {
+  TSC_WHERE_DISPATCH(handle, grp_column_append(*g, column_id, first_node_id, values, is_null, n),
+                     ix_column_append(ix, column_id, first_node_id, values, is_null, n))
+}
+
+int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_t n_ops,
+                               const void *in_args, uint32_t n_in_args, uint64_t *out_matched) {
+  TSC_WHERE_DISPATCH(handle, grp_filter_where(*g, ops, n_ops, in_args, n_in_args, out_matched),
+                     ix_filter_where(ix, ops, n_ops, in_args, n_in_args, out_matched))
 }
 
 // Self-test hook (no GPU): the same program translation (where_build) and the same

@@ -23,18 +23,29 @@ _SRC_NP = {SRC_F64: np.float64, SRC_F32: np.float32, SRC_I8: np.int8}
 
 
 class GpuVectorIndex:
+    """One shard on one GPU, or — with `device_ids=[...]` (2..8 devices) — a GROUP: the column
+    row-range sharded over the GPUs of this process behind one handle; every method that takes
+    host buffers works on it unchanged and `search` merges the shards over NVLink."""
+
     def __init__(self, dims: int, metric: int = METRIC_COSINE, *, capacity_rows: int,
                  src_precision: int = SRC_F32, dev_dtype: int = DEV_F32, device_id: int = 0,
-                 first_node_id: int = 0, k_max: int = 32, nq_max: int = 64):
+                 first_node_id: int = 0, k_max: int = 32, nq_max: int = 64, device_ids=None):
         self._lib = N.lib()
         self.dims, self.metric = int(dims), int(metric)
         self.src_precision, self.dev_dtype = int(src_precision), int(dev_dtype)
         self.device_id, self.first_node_id = int(device_id), int(first_node_id)
         self.k_max, self.nq_max = int(k_max), int(nq_max)
+        self.device_ids = [int(d) for d in device_ids] if device_ids else None
         desc = N.IndexDesc(struct_size=C.sizeof(N.IndexDesc), dims=self.dims, metric=self.metric,
                            src_precision=self.src_precision, dev_dtype=self.dev_dtype,
                            device_id=self.device_id, capacity_rows=int(capacity_rows),
                            first_node_id=self.first_node_id, k_max=self.k_max, nq_max=self.nq_max)
+        if self.device_ids:
+            if len(self.device_ids) > 8:
+                raise ValueError("at most 8 devices per group")
+            desc.n_devices = len(self.device_ids)
+            for i, dv in enumerate(self.device_ids):
+                desc.device_ids[i] = dv
         h = C.c_uint64(0)
         N.check(self._lib.tsc_index_create(C.byref(desc), C.byref(h)), "tsc_index_create")
         self.handle = h.value
@@ -306,16 +317,17 @@ class GpuVectorIndex:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         N.check(self._lib.tsc_comm_init(self.handle, buf, n_ranks, rank), "tsc_comm_init")
 
-    def comm_init_p2p(self, dist, n_ranks: int, rank: int) -> None:
-        """Experimental: peer-memory exchange instead of NCCL (tsc_exchange.cuh). `dist` is an
-        initialised torch.distributed module (any backend) used only to all-gather the
+    def comm_init_p2p(self, dist, n_ranks: int, rank: int, root: int = -1) -> None:
+        """Peer-memory exchange (tsc_exchange.cuh): every shard pushes its top-k over NVLink;
+        root = -1: every rank receives the global result, root = r: only rank r does. `dist` is
+        an initialised torch.distributed module (any backend) used only to all-gather the
         64-byte CUDA IPC handles of the receive buffers."""
         buf = (C.c_uint8 * 64)()
         N.check(self._lib.tsc_comm_p2p_export(self.handle, n_ranks, rank, buf), "tsc_comm_p2p_export")
         handles = [None] * n_ranks
         dist.all_gather_object(handles, bytes(buf))
         blob = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(b"".join(handles))
-        N.check(self._lib.tsc_comm_p2p_import(self.handle, blob), "tsc_comm_p2p_import")
+        N.check(self._lib.tsc_comm_p2p_import(self.handle, blob, int(root)), "tsc_comm_p2p_import")
         dist.barrier()          # every rank has mapped every buffer before the first search
 
     def merge_shards(self, d_part_ids: int, d_part_dist: int, n_parts: int, nq: int, k: int,
@@ -323,6 +335,13 @@ class GpuVectorIndex:
         N.check(self._lib.tsc_merge_shards(self.handle, d_part_ids, d_part_dist, n_parts, nq, k,
                                            d_ids, d_dist, d_counts, stream or None),
                 "tsc_merge_shards")
+
+    def search_flags(self, nq: int):
+        """Per-query verdict of the exactness certificate for the last search:
+        0 exact, 1 range pass owed (device-buffer searches only), 2 uncertified."""
+        f = np.zeros(nq, dtype=np.uint32)
+        N.check(self._lib.tsc_search_flags(self.handle, int(nq), f.ctypes.data), "tsc_search_flags")
+        return f
 
     # -- observability -----------------------------------------------------------------
     def stats(self) -> N.Stats:
