@@ -48,13 +48,17 @@ def parse_args():
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the `configs` block (BASELINE configs 1/3/4/5 measured after the headline)")
+    ap.add_argument("--recall-queries", type=int, default=3,
+                    help="full oracle searches (all N rows, every host core) run after the timed regions")
     ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
                     help="N>1: row-range shards of ONE corpus with a top-k exchange per query (default, "
                          "what BASELINE's north_star asks for) or N independent full replicas, each "
                          "serving its own queries (no exchange; the corpus fits one GPU)")
-    ap.add_argument("--exchange", default=os.environ.get("TSC_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
-                    help="N>1: ncclAllGather + merge (default, measured) or the experimental "
-                         "one-kernel exchange over NVLink peer memory")
+    ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
+                    help="N>1: push over NVLink peer memory fused into the scan kernel (default) or "
+                         "ncclAllGather + merge kernel")
     return ap.parse_args()
 
 
@@ -62,7 +66,7 @@ def ncu_traffic(n, d, world):
     """dram__bytes_read+write of the dominant kernel from the committed `ncu --set full`
     capture (profiles/), valid only for the exact workload it was taken on."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01c_scan_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_scan_traffic.json")) as f:
             t = json.load(f)
         if world == 1 and n == 10_000_000 and d == 768:
             return float(t["traffic"]), t["source"]
@@ -202,7 +206,7 @@ def run_b200(args):
     import numpy as np
     import torch
 
-    import oracle  # only for the cpu_baseline leg and the recall spot-check
+    import oracle  # only for the cpu_baseline leg and the recall check (after the timed regions)
     from tostore_b200 import METRIC_L2, GpuVectorIndex
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -218,6 +222,7 @@ def run_b200(args):
     steps, warmup = args.steps, max(args.warmup, 3)
     # row-range sharding: contiguous node-id ranges, aligned to 32 rows
     replicas = world > 1 and args.mode == "replicas"
+    sharded = world > 1 and not replicas
     per = ((n + world - 1) // world + 31) // 32 * 32
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
     if replicas:
@@ -225,22 +230,23 @@ def run_b200(args):
     ix = GpuVectorIndex(d, METRIC_L2, capacity_rows=max(hi - lo, 1), device_id=local,
                         first_node_id=lo, k_max=16, nq_max=8)
     ix.append_synthetic(SEED, hi - lo, first_node_id=lo)
-    if replicas:
-        pass                                            # no exchange step at all
-    elif world > 1 and args.exchange == "p2p":
-        ix.comm_init_p2p(dist, world, rank)
-    elif world > 1:
+    if sharded and args.exchange == "p2p":
+        # push exchange over NVLink peer memory, fused into the scan kernel's last CTA; the
+        # merged result is needed where the host reads it: rank 0 (the other ranks only push)
+        ix.comm_init_p2p(dist, world, rank, root=0)
+    elif sharded:
         uid = [GpuVectorIndex.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ix.comm_init(uid[0], world, rank)
 
     nqs = steps + warmup
     # replicas serve different queries; shards of one corpus all see the same query
-    q_host = torch.from_numpy(oracle.synth_rows(SEED + 1, (rank * nqs) if replicas else 0, nqs, d)).pin_memory()
+    q_np = oracle.synth_rows(SEED + 1, (rank * nqs) if replicas else 0, nqs, d)
+    q_host = torch.from_numpy(q_np).pin_memory()
     q_dev = q_host.cuda()
-    o_ids = torch.empty((nqs, k), dtype=torch.int64, device="cuda")
+    o_ids = torch.full((nqs, k), -1, dtype=torch.int64, device="cuda")
     o_dist = torch.empty((nqs, k), dtype=torch.float64, device="cuda")
-    o_cnt = torch.empty((nqs,), dtype=torch.int32, device="cuda")
+    o_cnt = torch.zeros((nqs,), dtype=torch.int32, device="cuda")
     # a real (non-default) stream: every kernel of the timed region is launched on
     # it and the CUDA events that time the region are recorded on it
     stream = torch.cuda.Stream()
@@ -251,7 +257,7 @@ def run_b200(args):
     def step_device(i):
         ix.search_device(q_dev.data_ptr() + i * esz, 1, k, o_ids.data_ptr() + i * k * 8,
                          o_dist.data_ptr() + i * k * 8, o_cnt.data_ptr() + i * 4,
-                         stream=sptr, sharded=world > 1 and not replicas)
+                         stream=sptr, sharded=sharded)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -284,107 +290,130 @@ def run_b200(args):
     launches = st.kernel_launches - launches0
     hot_ms = st.hot_ms_total / max(st.hot_launches, 1)
     hot_bytes = st.hot_bytes_total / max(st.hot_launches, 1)
+    dev_ids = o_ids.cpu().numpy()
+    dev_dist = o_dist.cpu().numpy()
 
-    # ---- end to end through the host-buffer API (`e2e`) -----------------------------
-    h_ids = torch.empty((k,), dtype=torch.int64).pin_memory()
-    h_dist = torch.empty((k,), dtype=torch.float64).pin_memory()
-    h_cnt = torch.empty((1,), dtype=torch.int32).pin_memory()
-    dq1 = torch.empty((d,), dtype=torch.float32, device="cuda")
+    # ---- end to end through the host-buffer plugin call (`e2e`) ----------------------
+    # tsc_search with HOST buffers on every rank: H2D of the query, the kernels (for a
+    # sharded index: + the exchange over NVLink), D2H of the result, all inside the call.
+    e2e_out = [None]
 
     def step_e2e(i):
-        if world == 1 or replicas:
-            return ix.search(q_host[i].numpy(), k)          # tsc_search: H2D + kernels + D2H inside
-        # sharded: pinned host query -> device, library search+all-gather+merge, results -> host
-        dq1.copy_(q_host[i], non_blocking=True)
-        ix.search_device(dq1.data_ptr(), 1, k, o_ids.data_ptr(), o_dist.data_ptr(),
-                         o_cnt.data_ptr(), stream=sptr, sharded=True)
-        h_ids.copy_(o_ids[0], non_blocking=True)
-        h_dist.copy_(o_dist[0], non_blocking=True)
-        h_cnt.copy_(o_cnt[:1], non_blocking=True)
-        stream.synchronize()
-        return h_ids, h_dist, h_cnt
+        e2e_out[0] = ix.search(q_np[i], k)
 
     for i in range(warmup):
         step_e2e(i)
     sync_all()
     t0 = time.perf_counter()
-    e0.record(stream)
     for i in range(warmup, warmup + steps):
         step_e2e(i)
-    e1.record(stream)
-    sync_all()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall_ms)], dtype=torch.float64, device="cuda")
+    sync_all()
+    ms2 = torch.tensor([wall_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms = float(ms2.item())
+    e2e_last = e2e_out[0]
+    cert = ix.stats()
+    flags_bad = int((ix.search_flags(1) != 0).sum())
 
-    # ---- recall spot check on rank 0 (bounded): ids/dists of the last query vs the oracle
-    recall = None
-    if rank == 0:
-        i = warmup + steps - 1
-        ids = o_ids[i].cpu().numpy() if world == 1 else None
-        if ids is not None:
-            dd = o_dist[i].cpu().numpy()
-            lib = oracle.c_oracle()
-            q = q_host[i].numpy()
-            ok = all(np.float64(lib.tso_l2_distance(q, oracle.synth_rows(SEED, int(r), 1, d)[0], d))
-                     .view(np.int64) == np.float64(x).view(np.int64) for r, x in zip(ids, dd))
-            recall = {"checked": "fp64 distances of the returned ids of the last query recomputed "
-                                 "by the oracle", "bit_exact": bool(ok)}
-
-    if rank == 0:
-        peak, which = peaks()
-        achieved = hot_bytes / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
-        traffic, traffic_src = ncu_traffic(n, d, world)
-        line = {
-            # replicas: every rank answers one query per step
-            "metric": METRIC_NAME, "value": steps * (world if replicas else 1) / (total_ms * 1e-3),
-            "unit": "queries/s",
-            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
-            "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
-            "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": f"single-query L2, N={n} d={d} fp32, k={k} (BASELINE config 2)",
-                       "implementation": f"HBM-bound scan + in-kernel top-k + exact fp64 re-rank on {world}xB200",
-                       "rows_per_gpu": hi - lo,
-                       "sharding": "replicas (each GPU holds the whole corpus and serves its own queries)"
-                       if replicas else ("row-range" if world > 1 else "none"),
-                       "exchange": ("none" if world == 1 or replicas else
-                                    "one-kernel push over NVLink peer memory (experimental)"
-                                    if args.exchange == "p2p" else
-                                    "ncclAllGather of per-shard top-k (in-library)"),
-                       "l2_flush": "inputs larger than L2 (each pass streams the whole shard; "
-                                   f"{(hi - lo) * d * 4 / 1e9:.2f} GB per GPU vs 126 MB L2)",
-                       "queries": "distinct synthetic query per step"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "traffic_source": traffic_src,
-                         "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)" if which == "measured"
-                         else "fallback 6650 GB/s (B200_PROFILING.md)",
-                         "peak_note": "MEASURED_PEAKS hbm_gbs is a torch copy (read + write) figure; a "
-                                      "read-only stream pays no write turnarounds, so frac can exceed 1 "
-                                      "(DESIGN.md K1: 90 % of the 8.18 TB/s ncu reports as DRAM peak)",
-                         "kernel": "scan_topk_kernel<L2,f32,QB=1>",
-                         "kernel_ms": hot_ms, "algorithmic_bytes_per_launch": hot_bytes,
-                         "kernel_share_of_step": hot_ms / (total_ms / steps) if total_ms else None},
-            "e2e": {"value": steps * (world if replicas else 1) / (e2e_ms * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": d * 4, "d2h_bytes_per_step": k * 16 + 4,
-                    "ms_per_step": e2e_ms / steps,
-                    "api": "tsc_search (host buffers)" if world == 1 or replicas else
-                           "pinned H2D + tsc_search_sharded + D2H"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-        }
-        if recall is not None:
-            line["recall_check"] = recall
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_arm(n, d, k, args.cpu_sample_rows, 8, 1)
-        print(json.dumps(line), flush=True)
+    # every rank's certificate counters (a query is exact when every shard certified it)
+    cert_t = torch.tensor([cert.certified_queries, cert.retried_queries, cert.uncertified_queries],
+                          dtype=torch.int64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(cert_t, op=dist.ReduceOp.SUM)
+    cert_sum = [int(x) for x in cert_t.cpu()]
     ix.close()
+    del q_dev, o_ids, o_dist, o_cnt
+    torch.cuda.empty_cache()
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
+        dist.destroy_process_group()   # nothing CPU-heavy happens inside a live process group
+    if rank != 0:
+        return
+
+    # ---- recall check on rank 0, after the timed regions, with every host core ------------
+    # FULL oracle searches (the C restatement of the reference arithmetic streams all N
+    # synthetic rows, ~5 s per query on 16 cores) for the last timed queries of both loops:
+    # ids identical, fp64 distances bit-identical = recall 1.0 for those queries, at any N.
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    checked, ok_ids, ok_bits = [], True, True
+    last = warmup + steps - 1
+    for which, qi, got_ids, got_dist in (("device loop", last, dev_ids[last], dev_dist[last]),
+                                         ("host-buffer loop", last, e2e_last[0][0], e2e_last[1][0]),
+                                         ("device loop", last - 1, dev_ids[last - 1],
+                                          dev_dist[last - 1]))[:max(args.recall_queries, 0)]:
+        oi, od = oracle.search_synth(SEED, n, d, 0, q_np[qi], 0, k, threads=threads)
+        ok_ids &= bool((np.asarray(got_ids) == oi).all())
+        ok_bits &= bool((np.asarray(got_dist, dtype=np.float64).view(np.int64) == od.view(np.int64)).all())
+        checked.append(f"{which} query {qi}")
+    recall = {"checked": f"full oracle search over all {n} rows for: " + ", ".join(checked),
+              "ids_identical": ok_ids, "bit_exact": ok_bits, "recall": 1.0 if ok_ids else None,
+              "certificate": {"certified": cert_sum[0], "range_pass": cert_sum[1],
+                              "uncertified": cert_sum[2],
+                              "note": "per shard and query over both timed loops + warm-up of the "
+                                      "second; uncertified must be 0 for recall=1.0 to be proven"},
+              "flags_nonzero_last_search": flags_bad}
+
+    peak, which = peaks()
+    achieved = hot_bytes / (hot_ms * 1e-3) / 1e9 if hot_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(n, d, world)
+    xname = ("none" if not sharded else
+             "push over NVLink peer memory to rank 0, fused into the scan kernel's last CTA"
+             if args.exchange == "p2p" else "ncclAllGather of per-shard top-k + merge kernel (in-library)")
+    line = {
+        # replicas: every rank answers one query per step
+        "metric": METRIC_NAME, "value": steps * (world if replicas else 1) / (total_ms * 1e-3),
+        "unit": "queries/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": total_ms / steps,
+        "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"single-query L2, N={n} d={d} fp32, k={k} (BASELINE config 2)",
+                   "implementation": "one kernel per query: HBM-bound scan + in-kernel top-k + exact fp64 "
+                                     f"re-rank + exactness certificate (+ shard exchange) on {world}xB200",
+                   "rows_per_gpu": hi - lo,
+                   "sharding": "replicas (each GPU holds the whole corpus and serves its own queries)"
+                   if replicas else ("row-range" if world > 1 else "none"),
+                   "exchange": xname,
+                   "l2_flush": "inputs larger than L2 (each pass streams the whole shard; "
+                               f"{(hi - lo) * d * 4 / 1e9:.2f} GB per GPU vs 126 MB L2)",
+                   "queries": "distinct synthetic query per step"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "traffic_source": traffic_src,
+                     "peak_source": f"{which} (MEASURED_PEAKS.json hbm_gbs)" if which == "measured"
+                     else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "peak_note": "MEASURED_PEAKS hbm_gbs is a torch copy (read + write) figure; a "
+                                  "read-only stream pays no write turnarounds, so frac can exceed 1 "
+                                  "(DESIGN.md K1: 90 % of the 8.18 TB/s ncu reports as DRAM peak)",
+                     "kernel": "scan_topk_kernel<L2,f32,QB=1> (scan + fused tail)",
+                     "kernel_ms": hot_ms, "algorithmic_bytes_per_launch": hot_bytes,
+                     "kernel_share_of_step": hot_ms / (total_ms / steps) if total_ms else None},
+        "e2e": {"value": steps * (world if replicas else 1) / (e2e_ms * 1e-3), "unit": "queries/s",
+                "h2d_bytes_per_step": d * 4 * world,            # every rank copies its query in
+                "d2h_bytes_per_step": (k * 16 + 8) * (world if replicas else 1),
+                "ms_per_step": e2e_ms / steps,
+                "api": "tsc_search (host buffers)" + (", called on every rank; rank 0 receives the "
+                                                      "merged result" if sharded else "")},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "recall_check": recall,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_arm(n, d, k, args.cpu_sample_rows, 8, 1)
+    if world == 1 and not args.no_configs:
+        # the other BASELINE configs (one GPU's share of the sharded ones), measured after the
+        # headline region: device ms, achieved GB/s or TFLOP/s and fraction of the measured peak
+        try:
+            from tools.bench_configs import measure_all
+            line["configs"] = measure_all(("c1", "c3", "c4", "c5", "c5w"))
+        except Exception as e:  # noqa: BLE001
+            line["configs"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -23,11 +23,13 @@ MOCK = textwrap.dedent('''
 
     class FakeStats:
         kernel_launches = 0; hot_launches = 100; hot_ms_total = 418.0; hot_bytes_total = 100 * 30.72e9
+        certified_queries = 1; retried_queries = 0; uncertified_queries = 0
     class FakeIndex:
         def __init__(self, *a, **k): pass
         def append_synthetic(self, *a, **k): pass
         def comm_init(self, *a): pass
-        def comm_init_p2p(self, d, n, r): d.barrier()
+        def comm_init_p2p(self, d, n, r, root=-1): d.barrier()
+        def search_flags(self, nq): return np.zeros(nq, dtype=np.uint32)
         @staticmethod
         def comm_unique_id(): return b"x" * 128
         def search_device(self, *a, **k): FakeStats.kernel_launches += 2
@@ -49,6 +51,10 @@ MOCK = textwrap.dedent('''
     torch.Tensor.pin_memory = lambda self: self
     torch.Tensor.cuda = lambda self, *a, **k: self
     _empty, _tensor, _init = torch.empty, torch.tensor, dist.init_process_group
+    _full, _zeros = torch.full, torch.zeros
+    torch.cuda.empty_cache = lambda: None
+    torch.full = lambda *a, **k: _full(*a, **{x: v for x, v in k.items() if x != "device"})
+    torch.zeros = lambda *a, **k: _zeros(*a, **{x: v for x, v in k.items() if x != "device"})
     torch.empty = lambda *a, **k: _empty(*a, **{x: v for x, v in k.items() if x != "device"})
     torch.tensor = lambda *a, **k: _tensor(*a, **{x: v for x, v in k.items() if x != "device"})
     dist.init_process_group = lambda backend, **k: _init("gloo")
@@ -70,6 +76,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 def _run(tmp_path, args, nproc=1):
     script = tmp_path / "mock_bench.py"
     script.write_text(f"ROOT = {ROOT!r}\n" + MOCK)
+    args = args + ["--no-configs", "--recall-queries", "1"]   # one full oracle search (~10 s here)
     cmd = [sys.executable, str(script)] + args
     if nproc > 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
@@ -89,7 +96,10 @@ def _check_common(line, n_gpus):
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert line["roofline"]["bound"] == "hbm" and line["roofline"]["unit"] == "GB/s"
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
-    assert line["e2e"]["h2d_bytes_per_step"] == 768 * 4 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 768 * 4 * n_gpus and line["e2e"]["d2h_bytes_per_step"] > 0
+    rc = line["recall_check"]
+    assert {"checked", "ids_identical", "bit_exact", "certificate"} <= set(rc)
+    assert rc["certificate"]["uncertified"] == 0
     assert line["gpu_launches"] > 0 and {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
     assert line["warmup"] >= 3
 

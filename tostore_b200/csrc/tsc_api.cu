@@ -111,6 +111,7 @@ void free_index(Index *ix) {
   cudaFree(ix->d_done);
   cudaFree(ix->d_cert_stat);
   cudaFree(ix->d_loc_counts);
+  cudaFree(ix->d_trace);
   if (ix->host_done) cudaEventDestroy(ix->host_done);
   cudaFree(ix->d_stage);
   cudaFree(ix->d_page_status);
@@ -274,7 +275,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
   ix->capacity = d->capacity_rows;
   ix->k_max = d->k_max;
   ix->nq_max = d->nq_max;
-  ix->kprime_max = kprime_for(d->k_max);
+  ix->kprime_max = kprime_for(d->k_max) > 32 ? kprime_for(d->k_max) : 32;   // tensor path: K' >= 32
   int32_t rc = scan_configure(ix);
   if (rc != TSC_OK) {
     delete ix;
@@ -322,6 +323,9 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
   ok(dev_alloc(ix, &ix->d_done, 2));
   ok(dev_alloc(ix, &ix->d_cert_stat, (size_t)kStatSlots));
   ok(dev_alloc(ix, &ix->d_loc_counts, (size_t)ix->nq_max));
+#ifdef TSC_DIAG
+  ok(dev_alloc(ix, &ix->d_trace, (size_t)4096));
+#endif
   ok(cudaEventCreateWithFlags(&ix->host_done, cudaEventDisableTiming));
   ok(cudaMallocHost((void **)&ix->h_queries, (size_t)ix->nq_max * ix->qld * 4));
   ok(cudaMallocHost((void **)&ix->h_out_ids, (size_t)ix->nq_max * ix->k_max * 8));
@@ -802,9 +806,13 @@ int32_t tsc_index_destroy(uint64_t handle) {
   drop_tickets_of(handle);
   if (ix) {
     std::lock_guard<std::mutex> lk(ix->mu);   // wait for a call in progress
+    ix->inflight.reset();                     // the ticket holds a reference to the index
     comm_release(ix.get());
   }
-  if (g) std::lock_guard<std::mutex> lk(g->mu);
+  if (g) {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->inflight.reset();
+  }
   return TSC_OK;
   TSC_API_CATCH
 }
@@ -896,6 +904,22 @@ int32_t tsc_index_device_rows(uint64_t handle, void **out_ptr, uint64_t *out_row
   return TSC_OK;
   TSC_API_CATCH
 }
+
+#ifdef TSC_DIAG
+// diagnostics build only: phase timestamps of the last scan launch (tsc_tail.cuh trace slots);
+// reset = 1 arms the next launch (slot 0 is taken with atomicMin)
+int32_t tsc_diag_scan_trace(uint64_t handle, unsigned long long *out, uint32_t n, int32_t reset) {
+  IndexRef ref = lookup_index(handle);
+  if (!ref || !out || n > 4096) return TSC_ERR_BAD_ARG;
+  Index *ix = ref.get();
+  std::lock_guard<std::mutex> lk(ix->mu);
+  TSC_CUDA(cudaSetDevice(ix->device));
+  TSC_CUDA(cudaStreamSynchronize(ix->stream));
+  TSC_CUDA(cudaMemcpy(out, ix->d_trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
+  if (reset) TSC_CUDA(cudaMemset(ix->d_trace, 0xFF, 4096 * 8));
+  return TSC_OK;
+}
+#endif
 
 // Host re-enactment of page_check_kernel's warp-sliced CRC-32 (same helpers, 32
 // simulated lanes) so the CPU test-suite can pin the slicing algebra without a GPU.

@@ -103,6 +103,7 @@ struct Index {
   uint64_t *d_range_buf = nullptr; // [kRangeSlots][kRangeCap]
   uint32_t *d_done = nullptr;      // [2] last-CTA tickets (scan, exchange), zero between launches
   unsigned long long *d_cert_stat = nullptr;  // [kStatSlots]
+  unsigned long long *d_trace = nullptr;      // diagnostics build: phase timestamps (tsc_tail.cuh)
   uint32_t *d_loc_counts = nullptr;  // [nq_max] shard-local result counts of a sharded search
   // host-buffer searches: at most one in flight; `host_done` follows its last D2H copy
   cudaEvent_t host_done = nullptr;

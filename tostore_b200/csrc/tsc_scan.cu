@@ -85,8 +85,9 @@ static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cuda
   static bool attr_done[64] = {false};
   auto kern = scan_topk_kernel<METRIC, DTYPE, QB, R>;
   if (!attr_done[ix->device & 63]) {
+    // the fused tail has a few static __shared__ words: the dynamic part stops 1 KB short
     TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ix->smem_optin));
+                                  (int)ix->smem_optin - 1024));
     attr_done[ix->device & 63] = true;
   }
   int slot = 0;
@@ -106,8 +107,9 @@ static int32_t run_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl, cu
   static bool attr_done[64] = {false};
   auto kern = scan_topk_sparse_kernel<METRIC, DTYPE, QB>;
   if (!attr_done[ix->device & 63]) {
+    // the fused tail has a few static __shared__ words: the dynamic part stops 1 KB short
     TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ix->smem_optin));
+                                  (int)ix->smem_optin - 1024));
     attr_done[ix->device & 63] = true;
   }
   int slot = 0;
@@ -213,13 +215,20 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
     if (xcap > p.tail_sort_cap) p.tail_sort_cap = xcap;
   }
   if (p.fused_tail) {
-    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld);
-    if (need > ix->smem_optin) {
+    // room to stage the candidates' rows for the re-rank: all of them when that fits
+    const size_t lim = ix->smem_optin - 1024;
+    uint32_t rows_staged = mode == 1 ? 64 : c.kprime;
+    while (rows_staged > 1 &&
+           tail_smem_bytes(p.tail_sort_cap, ix->qld, ix->row_bytes, rows_staged) > lim)
+      rows_staged >>= 1;
+    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld, ix->row_bytes, rows_staged);
+    if (need > ix->smem_optin - 1024) {
       set_error("scan: the tail needs %zu bytes of shared memory", need);
       return TSC_ERR_BAD_DIMS;
     }
     if (need > pl.smem) pl.smem = need;
   }
+  p.smem_bytes = (uint32_t)pl.smem;
   int32_t rc;
   if (sparse) {
     switch (ix->desc.metric) {

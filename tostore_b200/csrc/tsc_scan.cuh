@@ -50,6 +50,7 @@ struct ScanParams {
   int last_retry;            // mode 1: the last range launch of the search resets retry_n
   uint32_t nq_total;         // queries of the whole search (exchange loop)
   uint32_t tail_sort_cap;    // Pair128 slots of the tail's sort buffer
+  uint32_t smem_bytes;       // dynamic shared memory of this launch (the tail stages rows in it)
   uint32_t *done_counter;    // zero between launches
   TailParams tail;
   XchgParams xchg;
@@ -203,7 +204,9 @@ __device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t 
                                             const uint32_t *lkeys, const uint32_t *lids, int warp,
                                             int warps, int lane) {
   __shared__ uint32_t s_ticket;
+  TSC_TRACE(p.tail.diag, kTraceCta + blockIdx.x);
   if (p.mode == 0) scan_block_merge(p, qi, nq, sortbuf, lkeys, lids, p.kprime, warp, warps, lane);
+  TSC_TRACE(p.tail.diag, kTraceCta + gridDim.x + blockIdx.x);
   if (!p.fused_tail) return;
   __threadfence();
   __syncthreads();
@@ -212,8 +215,9 @@ __device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t 
   if (s_ticket != gridDim.x - 1) return;
   if (threadIdx.x == 0) *p.done_counter = 0;   // stream order: the next launch sees zero
   __threadfence();
+  TSC_TRACE(p.tail.diag, 1);
   for (uint32_t q = 0; q < nq; q++)
-    tail_query<METRIC, DTYPE>(p.tail, qi[q], p.mode, q, smem, p.tail_sort_cap);
+    tail_query<METRIC, DTYPE>(p.tail, qi[q], p.mode, q, smem, p.smem_bytes, p.tail_sort_cap);
   // the last range launch of a search leaves the retry list empty for the next search
   // (queries beyond the in-stream range launches keep kFlagRetry: the host API re-runs them)
   if (p.mode == 1 && p.last_retry && threadIdx.x == 0) *p.tail.retry_n = 0;
@@ -237,6 +241,7 @@ __device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t 
   }
   __syncthreads();
   xchg_ack(p.xchg);
+  TSC_TRACE(p.tail.diag, 7);
 }
 
 template <int METRIC, int DTYPE, int QB, int R>
@@ -252,6 +257,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   uint32_t qi[QB];
   const uint32_t nq = scan_queries<QB>(p, qi);
   if (nq == 0) return;
+#ifdef TSC_DIAG
+  if (p.tail.diag && threadIdx.x == 0) atomicMin(p.tail.diag, trace_now());
+#endif
 
   // ---- carve shared memory -------------------------------------------------
   float *qs = reinterpret_cast<float *>(smem);

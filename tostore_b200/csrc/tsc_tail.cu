@@ -87,6 +87,10 @@ void fill_tail(const Index *ix, const SearchCtx &c, uint32_t m, bool gemm_keys, 
   t->range_count = ix->d_range_count;
   t->range_buf = ix->d_range_buf;
   t->stat = ix->d_cert_stat;
+  t->diag = nullptr;
+#ifdef TSC_DIAG
+  t->diag = ix->d_trace;   // tools/scan_trace.py
+#endif
 }
 
 void fill_xchg(const Index *ix, XchgParams *x) {
@@ -110,7 +114,12 @@ static int32_t run_tail(Index *ix, const TailParams &p, uint32_t nq, uint32_t so
                         cudaStream_t st) {
   static bool attr_done[64] = {false};
   auto kern = tail_kernel<METRIC, DTYPE>;
-  const size_t smem = tail_smem_bytes(sort_cap, p.qld);
+  // stage up to 32 candidate rows per batch, within ~100 KB so that two CTAs share an SM
+  uint32_t rows_staged = p.kprime < 32 ? p.kprime : 32;
+  while (rows_staged > 1 &&
+         tail_smem_bytes(sort_cap, p.qld, p.row_bytes, rows_staged) > 100 * 1024)
+    rows_staged >>= 1;
+  const size_t smem = tail_smem_bytes(sort_cap, p.qld, p.row_bytes, rows_staged);
   if (!attr_done[ix->device & 63]) {
     TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)ix->smem_optin - 4 * 1024));
@@ -120,7 +129,7 @@ static int32_t run_tail(Index *ix, const TailParams &p, uint32_t nq, uint32_t so
     set_error("tail: dims too large for the re-rank staging (%zu B)", smem);
     return TSC_ERR_BAD_DIMS;
   }
-  kern<<<nq, kTailThreads, smem, st>>>(p, sort_cap);
+  kern<<<nq, kTailThreads, smem, st>>>(p, sort_cap, (uint32_t)smem);
   TSC_CUDA(cudaGetLastError());
   ix->launches++;
   return TSC_OK;

@@ -45,6 +45,28 @@ enum : uint32_t { kFlagExact = 0, kFlagRetry = 1, kFlagUncertified = 2 };
 enum : int { kStatCertified = 0, kStatRetried = 1, kStatUncertified = 2, kStatRangeRows = 3,
              kStatRetryAsked = 4, kStatSlots = 8 };
 
+// Diagnostics build only (-DTSC_DIAG, libtostore_cuda_diag.so): phase timestamps of the scan
+// kernel and its tail (globaltimer ns) for tools/scan_trace.py. Compiles to nothing otherwise.
+#ifdef TSC_DIAG
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TSC_TRACE(ptr, slot)                                            \
+  do {                                                                  \
+    if ((ptr) != nullptr && threadIdx.x == 0) (ptr)[slot] = trace_now(); \
+  } while (0)
+#else
+#define TSC_TRACE(ptr, slot) \
+  do {                       \
+  } while (0)
+#endif
+// trace slots: 0 first CTA start (atomicMin), 1 tail begin, 2 candidates selected, 3 rows
+// staged + chains done, 4 sorted, 5 certificate done, 6 emitted, 7 exchange done;
+// 16 + cta: main loop end, 16 + grid + cta: candidates published
+constexpr int kTraceCta = 16;
+
 struct Pair128 {
   uint64_t hi, lo;
 };
@@ -124,11 +146,18 @@ struct TailParams {
   uint32_t *range_count;    // [kRangeSlots] rows collected per slot of the running range pass
   uint64_t *range_buf;      // [kRangeSlots][kRangeCap] composites
   unsigned long long *stat; // [kStatSlots] kStat*
+  unsigned long long *diag; // phase timestamps (diagnostics build), else NULL
 };
 
-// shared memory the tail needs (dynamic): Pair128[sort_cap] | hist[kRadixBins] | q[qld]
-__host__ __device__ inline size_t tail_smem_bytes(uint32_t sort_cap, uint32_t qld) {
-  return (size_t)sort_cap * sizeof(Pair128) + (size_t)kRadixBins * 4 + (size_t)qld * 4 + 64;
+// shared memory of the tail (dynamic): Pair128[sort_cap] | hist[kRadixBins] | q[qld] | staged
+// candidate rows (as many as fit: the re-rank works through the candidates in such batches)
+__host__ __device__ inline size_t tail_fixed_bytes(uint32_t sort_cap, uint32_t qld) {
+  return (size_t)sort_cap * sizeof(Pair128) + (size_t)kRadixBins * 4 + (size_t)qld * 4;
+}
+__host__ __device__ inline size_t tail_smem_bytes(uint32_t sort_cap, uint32_t qld, uint32_t row_bytes,
+                                                  uint32_t stage_rows) {
+  return ((tail_fixed_bytes(sort_cap, qld) + 15) & ~(size_t)15) +
+         (size_t)stage_rows * (row_bytes + 16) + 64;
 }
 __host__ __device__ inline uint32_t tail_sort_cap(uint32_t m, uint32_t kprime, bool range) {
   uint32_t need = range ? kRangeCap : (m <= kSelectSortMax ? m : kprime);
@@ -187,7 +216,7 @@ __device__ __forceinline__ void lane_exact_sums(const float *qs, const uint8_t *
   const uint32_t full = d / E;
 #pragma unroll 4
   for (uint32_t c = 0; c < full; c++) {
-    const uint4 v = __ldg(rp + c);
+    const uint4 v = rp[c];
     float b[E];
     Chunk<DTYPE>::unpack(v, b);
 #pragma unroll
@@ -288,10 +317,11 @@ __device__ __forceinline__ double key_star(int metric, double D, double qn, doub
 
 // The tail for query `qi`, executed by every thread of the CTA (any blockDim that is a
 // multiple of 32). mode 0: first pass over cand[qi][0..m); mode 1: range pass over
-// range_buf[slot][0..range_count[slot]). `sm` = tail_smem_bytes(sort_cap, qld) bytes.
+// range_buf[slot][0..range_count[slot]). `sm` = the CTA's dynamic shared memory, sm_bytes of
+// it (>= tail_smem_bytes(sort_cap, qld, row_bytes, 1) for the staged re-rank).
 template <int METRIC, int DTYPE>
 __device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t slot, uint8_t *sm,
-                           uint32_t sort_cap) {
+                           size_t sm_bytes, uint32_t sort_cap) {
   Pair128 *buf = reinterpret_cast<Pair128 *>(sm);
   uint32_t *hist = reinterpret_cast<uint32_t *>(sm + (size_t)sort_cap * sizeof(Pair128));
   float *qs = reinterpret_cast<float *>(hist + kRadixBins);
@@ -376,29 +406,54 @@ __device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t 
     all_in = (uint32_t)(pivot >> 32) == kEmptyKey;
   }
   __syncthreads();
+  TSC_TRACE(p.diag, 2);
 
   // ---- 2. exact fp64 re-rank, one lane per candidate -----------------------------------
-  // |q|^2 (magA of _cosineSimlarity; also the certificate's ||q||^2) is one more sequential
-  // chain: a spare lane computes it while the others stream their rows. Only when every
-  // thread has a candidate (K' >= blockDim, range pass) does it cost a chain of its own.
-  const bool mag_inline = ncand < blockDim.x;   // block-uniform
+  // The candidates' rows are first staged in shared memory by the whole CTA (coalesced,
+  // every load in flight at once): a lane walking its row straight from HBM paid a DRAM
+  // round trip per 16 bytes (measured: 110 us for 20 rows of 3 KB). Row stride + 16 bytes
+  // keeps the lanes' 16-byte reads on different banks. |q|^2 (magA of _cosineSimlarity;
+  // also the certificate's ||q||^2) is one more sequential chain: a spare lane computes it
+  // while the others walk their rows; it costs a chain of its own only when no lane is spare.
+  uint8_t *stage = sm + ((tail_fixed_bytes(sort_cap, p.qld) + 15) & ~(size_t)15);
+  const uint32_t rstride = p.row_bytes + 16;
+  const uint32_t cpr = p.row_bytes / 16;
+  uint32_t cap_rows = sm_bytes > (size_t)(stage - sm) ? (uint32_t)((sm_bytes - (stage - sm)) / rstride) : 0u;
+  if (cap_rows > blockDim.x) cap_rows = blockDim.x;
+  if (cap_rows == 0) cap_rows = blockDim.x;   // no room to stage: lanes read global memory
+  const bool staged = sm_bytes >= (size_t)(stage - sm) + rstride;
+  const uint32_t first = ncand < cap_rows ? ncand : cap_rows;
+  const bool mag_inline = ncand > 0 && first < blockDim.x;   // block-uniform
   if (!mag_inline) {
     if (tid == 0) s_mag_a = lane_mag_a(qs, p.dims);
     __syncthreads();
   }
-  for (uint32_t base = 0; base < ncand || (mag_inline && base == 0); base += blockDim.x) {
-    const uint32_t i = base + tid;
+  for (uint32_t base = 0; base < ncand; base += cap_rows) {
+    const uint32_t nb = ncand - base < cap_rows ? ncand - base : cap_rows;
+    if (staged) {
+      for (uint32_t idx = tid; idx < nb * cpr; idx += blockDim.x) {
+        const uint32_t r = idx / cpr, c = idx - r * cpr;
+        const uint32_t row = (uint32_t)buf[base + r].hi;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row != kInvalidRow)
+          v = __ldg(reinterpret_cast<const uint4 *>(p.rows + (size_t)row * p.row_bytes) + c);
+        *reinterpret_cast<uint4 *>(stage + (size_t)r * rstride + (size_t)c * 16) = v;
+      }
+      __syncthreads();
+    }
     double s0 = 0.0, s1 = 0.0;
     uint32_t row = kInvalidRow;
-    if (i < ncand) {
-      row = (uint32_t)buf[i].hi;
+    if (tid < nb) {
+      row = (uint32_t)buf[base + tid].hi;
       if (row != kInvalidRow)
-        lane_exact_sums<METRIC, DTYPE>(qs, p.rows + (size_t)row * p.row_bytes, p.dims, s0, s1);
-    } else if (mag_inline && i == ncand) {
+        lane_exact_sums<METRIC, DTYPE>(
+            qs, staged ? stage + (size_t)tid * rstride : p.rows + (size_t)row * p.row_bytes, p.dims,
+            s0, s1);
+    } else if (mag_inline && base == 0 && tid == nb) {
       s_mag_a = lane_mag_a(qs, p.dims);
     }
-    if (mag_inline) __syncthreads();   // the loop body runs exactly once in this case
-    if (i < ncand) {
+    __syncthreads();   // mag_a is there; the staging area may be refilled
+    if (tid < nb) {
       uint64_t hi = ~0ull, lo = ~0ull;
       if (row != kInvalidRow) {
         const double d = exact_finish<METRIC>(s0, s1, s_mag_a);
@@ -408,12 +463,13 @@ __device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t 
           lo = (uint64_t)row;
         }
       }
-      buf[i].hi = hi;
-      buf[i].lo = lo;
+      buf[base + tid].hi = hi;
+      buf[base + tid].lo = lo;
     }
   }
   __syncthreads();
 
+  TSC_TRACE(p.diag, 3);
   // ---- 3. final order -------------------------------------------------------------------
   uint32_t n2 = 2;
   while (n2 < ncand) n2 <<= 1;
@@ -424,6 +480,7 @@ __device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t 
   }
   __syncthreads();
   bitonic_sort_pairs(buf, n2);
+  TSC_TRACE(p.diag, 4);
 
   // ---- 4. certificate (first pass) / verdict (range pass), by one thread ---------------------
   if (tid == 0) {
@@ -486,6 +543,7 @@ __device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t 
   }
   __syncthreads();
 
+  TSC_TRACE(p.diag, 5);
   // ---- 5. emit (an overflowed range pass keeps the first pass's best-effort result) --------
   if (!(mode == 1 && overflow)) {
     const uint32_t kept = s_count;
@@ -502,14 +560,16 @@ __device__ void tail_query(const TailParams &p, uint32_t qi, int mode, uint32_t 
     if (tid == 0) p.out_counts[qi] = kept;
   }
   __syncthreads();
+  TSC_TRACE(p.diag, 6);
 }
 
 // standalone form: one CTA per query (tensor path, multi-pass scans)
 constexpr int kTailThreads = 256;
 template <int METRIC, int DTYPE>
-__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailParams p, uint32_t sort_cap) {
+__global__ void __launch_bounds__(kTailThreads) tail_kernel(const TailParams p, uint32_t sort_cap,
+                                                            uint32_t smem_bytes) {
   extern __shared__ __align__(16) uint8_t tail_smem[];
-  tail_query<METRIC, DTYPE>(p, blockIdx.x, 0, 0, tail_smem, sort_cap);
+  tail_query<METRIC, DTYPE>(p, blockIdx.x, 0, 0, tail_smem, smem_bytes, sort_cap);
 }
 
 }  // namespace tsc
