@@ -46,6 +46,12 @@ final class TscIndexDesc extends Struct {
   external int kMax;
   @Uint32()
   external int nqMax;
+  @Uint32()
+  external int nDevices; // 0 / 1: one shard on deviceId; 2..8: a GROUP over deviceIds
+  @Array(8)
+  external Array<Int32> deviceIds;
+  @Uint32()
+  external int reserved1;
 }
 
 /// Mirrors `tsc_where_op`: one step of the postfix condition program
@@ -164,7 +170,11 @@ class TostoreCuda {
         .toDartString();
   }
 
-  /// tsc_index_create. Returns 0 on failure.
+  /// tsc_index_create. Returns 0 on failure. With `deviceIds` (2..8 CUDA devices) the
+  /// handle is a GROUP: the column is row-range sharded over those GPUs inside the library
+  /// and every call below (append, delete, filter, search ...) works on it unchanged — one
+  /// `search` call scans all shards and merges their exact top-k over NVLink. This is how
+  /// the single-process Dart host uses all GPUs of a box.
   static int createIndex({
     required int dims,
     required int metricIndex,
@@ -172,6 +182,7 @@ class TostoreCuda {
     required int capacityRows,
     int devDtype = 0,
     int deviceId = 0,
+    List<int>? deviceIds,
     int firstNodeId = 0,
     int kMax = 128,
     int nqMax = 64,
@@ -192,11 +203,40 @@ class TostoreCuda {
         ..capacityRows = capacityRows
         ..firstNodeId = firstNodeId
         ..kMax = kMax
-        ..nqMax = nqMax;
+        ..nqMax = nqMax
+        ..nDevices = deviceIds == null ? 0 : deviceIds.length;
+      for (var i = 0; deviceIds != null && i < deviceIds.length && i < 8; i++) {
+        desc.ref.deviceIds[i] = deviceIds[i];
+      }
       return create(desc, out) == 0 ? out.value : 0;
     } finally {
       calloc.free(desc);
       calloc.free(out);
+    }
+  }
+
+  /// tsc_device_count: GPUs visible to the process (0 when there is none / on error).
+  static int deviceCount() {
+    final lib = _open();
+    if (lib == null) return 0;
+    final n = lib.lookupFunction<Int32 Function(), int Function()>('tsc_device_count')();
+    return n < 0 ? 0 : n;
+  }
+
+  /// tsc_search_flags: verdict of the exactness certificate for the last search, per query:
+  /// 0 exact, 2 = more than 4096 rows tie with the k-th neighbour within the key error bound
+  /// (best-effort result). Empty list on error.
+  static List<int> searchFlags(int handle, int nq) {
+    final lib = _open();
+    if (lib == null || nq <= 0) return const [];
+    final fn = lib.lookupFunction<Int32 Function(Uint64, Uint32, Pointer<Uint32>),
+        int Function(int, int, Pointer<Uint32>)>('tsc_search_flags');
+    final buf = calloc<Uint32>(nq);
+    try {
+      if (fn(handle, nq, buf) != 0) return const [];
+      return List<int>.generate(nq, (i) => buf[i]);
+    } finally {
+      calloc.free(buf);
     }
   }
 

@@ -41,6 +41,15 @@ int main(void) {
   desc.capacity_rows = N;
   desc.k_max = 16;
   desc.nq_max = 8;
+  /* one process, all GPUs of the box: with >= 2 devices the handle is a GROUP (the column is
+   * row-range sharded inside the library); every call below stays the same */
+  {
+    int ndev = tsc_device_count();
+    if (ndev >= 2) {
+      desc.n_devices = (uint32_t)(ndev < 8 ? ndev : 8);
+      for (uint32_t i = 0; i < desc.n_devices; i++) desc.device_ids[i] = (int32_t)i;
+    }
+  }
   uint64_t h = 0;
   CHECK(tsc_index_create(&desc, &h));
   CHECK(tsc_index_append_rows(h, 0, rows, N));          /* flush-time hook */
@@ -88,9 +97,12 @@ int main(void) {
   memset(&st, 0, sizeof st);
   st.struct_size = sizeof st;
   CHECK(tsc_stats_get(h, &st));
-  printf("rows=%llu device_bytes=%llu kernel_launches=%llu last_search_ms=%.3f\n",
+  printf("rows=%llu device_bytes=%llu kernel_launches=%llu last_search_ms=%.3f gpus=%u "
+         "certified=%llu range_pass=%llu uncertified=%llu\n",
          (unsigned long long)st.rows, (unsigned long long)st.device_bytes,
-         (unsigned long long)st.kernel_launches, st.last_search_ms);
+         (unsigned long long)st.kernel_launches, st.last_search_ms, st.n_devices,
+         (unsigned long long)st.certified_queries, (unsigned long long)st.retried_queries,
+         (unsigned long long)st.uncertified_queries);
   CHECK(tsc_index_destroy(h));
   free(rows); free(pk_bytes); free(pk_off); free(year);
   return 0;

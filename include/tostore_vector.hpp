@@ -238,6 +238,13 @@ class GpuVectorStore {
   explicit GpuVectorStore(int deviceId = 0, uint64_t capacityRows = 1u << 20,
                           DeviceDType deviceDType = DeviceDType::float32, uint32_t kMax = 128)
       : device_(deviceId), capacity_(capacityRows), dtype_(deviceDType), k_max_(kMax) {}
+  // One process, several GPUs: every index of this store is a GROUP handle — the column is
+  // row-range sharded over `deviceIds` inside the library (tsc_index_create with n_devices > 1)
+  // and vectorSearch merges the shards over NVLink. Nothing else in this class changes.
+  GpuVectorStore(const std::vector<int> &deviceIds, uint64_t capacityRows,
+                 DeviceDType deviceDType = DeviceDType::float32, uint32_t kMax = 128)
+      : device_(deviceIds.empty() ? 0 : deviceIds[0]), devices_(deviceIds), capacity_(capacityRows),
+        dtype_(deviceDType), k_max_(kMax) {}
   ~GpuVectorStore() { close(); }
   GpuVectorStore(const GpuVectorStore &) = delete;
   GpuVectorStore &operator=(const GpuVectorStore &) = delete;
@@ -255,6 +262,10 @@ class GpuVectorStore {
     d.src_precision = TSC_SRC_F32;       // rows cross the boundary as fp32 (`_toFloat32`)
     d.dev_dtype = (uint8_t)dtype_;
     d.device_id = device_;
+    if (devices_.size() > 1) {
+      d.n_devices = (uint32_t)(devices_.size() < 8 ? devices_.size() : 8);
+      for (uint32_t i = 0; i < d.n_devices; i++) d.device_ids[i] = devices_[i];
+    }
     d.capacity_rows = capacity_;
     d.k_max = k_max_;
     d.nq_max = 64;
@@ -520,6 +531,7 @@ class GpuVectorStore {
   }
 
   int device_;
+  std::vector<int> devices_;   // > 1 entry: group handle over these GPUs
   uint64_t capacity_;
   DeviceDType dtype_;
   uint32_t k_max_;

@@ -18,9 +18,16 @@ tail -3 gpurun_out/r2c_bench.err | tee -a $L
 echo "== ncu full: dense scan" | tee -a $L
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_topk_kernel -s 6 -c 1 -o gpurun_out/r2c_scan_full python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs --recall-queries 0 > gpurun_out/r2c_ncu_scan.log 2>&1
 tail -2 gpurun_out/r2c_ncu_scan.log | tee -a $L
+python tools/ncu_summary.py gpurun_out/r2c_scan_full.ncu-rep > gpurun_out/r2c_scan_ncu_summary.txt 2>&1
+ncu -i gpurun_out/r2c_scan_full.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/r2c_scan_source.csv.gz
+rm -f gpurun_out/r2c_scan_full.ncu-rep
 echo "== ncu full: sparse scan" | tee -a $L
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_topk_sparse -s 3 -c 1 -o gpurun_out/r2c_sparse_full python tools/bench_configs.py c5 > gpurun_out/r2c_ncu_sparse.log 2>&1
 tail -2 gpurun_out/r2c_ncu_sparse.log | tee -a $L
+python tools/ncu_summary.py gpurun_out/r2c_sparse_full.ncu-rep > gpurun_out/r2c_sparse_ncu_summary.txt 2>&1
+ncu -i gpurun_out/r2c_sparse_full.ncu-rep --page source --csv 2>/dev/null | gzip > gpurun_out/r2c_sparse_source.csv.gz
+rm -f gpurun_out/r2c_sparse_full.ncu-rep
+du -sh gpurun_out | tee -a $L
 echo "== launch list of the bench command" | tee -a $L
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2c_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-configs --recall-queries 0 > gpurun_out/r2c_ncu_bench.log 2>&1
 tail -1 gpurun_out/r2c_ncu_bench.log | cut -c1-300 | tee -a $L

@@ -1,7 +1,7 @@
 """Where does a scan launch spend its time? Needs the diagnostics library
 (`make -C tostore_b200/csrc diag`): per-CTA main-loop end times and the phases of the fused
 tail, from globaltimer stamps (tsc_tail.cuh TSC_TRACE).
-    python tools/scan_trace.py [rows] [dims] [k] [reps]"""
+    python tools/scan_trace.py [rows] [dims] [k] [reps] [metric] [dev_dtype]"""
 import ctypes as C
 import os
 import sys
@@ -19,10 +19,12 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_250_000
 d = int(sys.argv[2]) if len(sys.argv) > 2 else 768
 k = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+metric = int(sys.argv[5]) if len(sys.argv) > 5 else 0
+dt = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 L = _native.lib()
 L.tsc_diag_scan_trace.argtypes = [C.c_uint64, C.c_void_p, C.c_uint32, C.c_int32]
 Q = oracle.synth_rows(5, 0, reps + 3, d)
-with GpuVectorIndex(d, 0, capacity_rows=n, k_max=max(16, k), nq_max=8) as ix:
+with GpuVectorIndex(d, metric, capacity_rows=n, dev_dtype=dt, k_max=max(16, k), nq_max=8) as ix:
     ix.append_synthetic(7, n)
     grid = 148
     buf = np.zeros(16 + 2 * grid, dtype=np.uint64)

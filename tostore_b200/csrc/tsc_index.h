@@ -162,6 +162,9 @@ struct Index {
   int t_head = 0, t_pending = 0;  // pending pairs are [t_head - t_pending, t_head)
   uint64_t hot_launches = 0;
   double hot_ms = 0, hot_bytes = 0, hot_flops = 0;
+  int hot_slot = 0;               // timer slot of the scan launch being bracketed
+  double hot_slot_bytes = 0;
+  bool hot_slot_open = false;     // its end event is still owed (after the range launch)
 
   // stats
   uint64_t searches = 0, launches = 0;

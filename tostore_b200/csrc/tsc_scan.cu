@@ -3,6 +3,7 @@
 
 #include "tsc_index.h"
 #include "tsc_scan.cuh"
+#include "tsc_scan_launch.h"
 
 namespace tsc {
 
@@ -30,12 +31,6 @@ int32_t scan_configure(Index *ix) {
   }
   return TSC_OK;
 }
-
-struct ScanPlan {
-  int warps, rows, stages, qb;
-  uint32_t stage_bytes, sort_cap;
-  size_t smem;
-};
 
 static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl,
                       bool sparse = false) {
@@ -80,91 +75,6 @@ static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl,
   return false;
 }
 
-template <int METRIC, int DTYPE, int QB, int R>
-static int32_t run_scan(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
-  static bool attr_done[64] = {false};
-  auto kern = scan_topk_kernel<METRIC, DTYPE, QB, R>;
-  if (!attr_done[ix->device & 63]) {
-    // the fused tail has a few static __shared__ words: the dynamic part stops 1 KB short
-    TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ix->smem_optin - 1024));
-    attr_done[ix->device & 63] = true;
-  }
-  int slot = 0;
-  int32_t rc = TSC_OK;
-  if (p.mode == 0) rc = hot_timer_begin(ix, st, &slot);
-  if (rc != TSC_OK) return rc;
-  kern<<<ix->scan.grid, pl.warps * 32, pl.smem, st>>>(p);
-  TSC_CUDA(cudaGetLastError());
-  ix->launches++;
-  if (p.mode != 0) return TSC_OK;   // range launches are not part of the roofline accounting
-  // algorithmic bytes of one pass: live rows x dims x sizeof(elem)
-  return hot_timer_end(ix, st, slot, (double)p.n_rows * ix->desc.dims * ix->elem_bytes, 0.0);
-}
-
-template <int METRIC, int DTYPE, int QB>
-static int32_t run_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
-  static bool attr_done[64] = {false};
-  auto kern = scan_topk_sparse_kernel<METRIC, DTYPE, QB>;
-  if (!attr_done[ix->device & 63]) {
-    // the fused tail has a few static __shared__ words: the dynamic part stops 1 KB short
-    TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ix->smem_optin - 1024));
-    attr_done[ix->device & 63] = true;
-  }
-  int slot = 0;
-  int32_t rc = TSC_OK;
-  if (p.mode == 0) rc = hot_timer_begin(ix, st, &slot);
-  if (rc != TSC_OK) return rc;
-  kern<<<ix->scan.grid, pl.warps * 32, pl.smem, st>>>(p);
-  TSC_CUDA(cudaGetLastError());
-  ix->launches++;
-  if (p.mode != 0) return TSC_OK;
-  // algorithmic bytes: only live rows are read (+ the bitmap)
-  return hot_timer_end(ix, st, slot,
-                       (double)ix->live_rows * ix->desc.dims * ix->elem_bytes + p.n_rows / 8.0, 0.0);
-}
-
-template <int METRIC, int DTYPE>
-static int32_t dispatch_sparse(Index *ix, const ScanParams &p, const ScanPlan &pl,
-                               cudaStream_t st) {
-  if (pl.qb == 1) return run_sparse<METRIC, DTYPE, 1>(ix, p, pl, st);
-  if (pl.qb == 4) return run_sparse<METRIC, DTYPE, 4>(ix, p, pl, st);
-  return run_sparse<METRIC, DTYPE, 8>(ix, p, pl, st);
-}
-
-template <int METRIC>
-static int32_t dispatch_sparse_dtype(Index *ix, const ScanParams &p, const ScanPlan &pl,
-                                     cudaStream_t st) {
-  switch (ix->desc.dev_dtype) {
-    case TSC_DEV_F32: return dispatch_sparse<METRIC, kF32>(ix, p, pl, st);
-    case TSC_DEV_BF16: return dispatch_sparse<METRIC, kBF16>(ix, p, pl, st);
-    default: return dispatch_sparse<METRIC, kF16>(ix, p, pl, st);
-  }
-}
-
-template <int METRIC, int DTYPE>
-static int32_t dispatch_qr(Index *ix, const ScanParams &p, const ScanPlan &pl, cudaStream_t st) {
-#define TSC_CASE(QB, R) \
-  if (pl.qb == QB && pl.rows == R) return run_scan<METRIC, DTYPE, QB, R>(ix, p, pl, st);
-  TSC_CASE(1, 1) TSC_CASE(1, 2) TSC_CASE(1, 4) TSC_CASE(1, 8)
-  TSC_CASE(4, 1) TSC_CASE(4, 2) TSC_CASE(4, 4)
-  TSC_CASE(8, 1) TSC_CASE(8, 2)
-#undef TSC_CASE
-  set_error("scan: no kernel for qb=%d rows=%d", pl.qb, pl.rows);
-  return TSC_ERR_UNSUPPORTED;
-}
-
-template <int METRIC>
-static int32_t dispatch_dtype(Index *ix, const ScanParams &p, const ScanPlan &pl,
-                              cudaStream_t st) {
-  switch (ix->desc.dev_dtype) {
-    case TSC_DEV_F32: return dispatch_qr<METRIC, kF32>(ix, p, pl, st);
-    case TSC_DEV_BF16: return dispatch_qr<METRIC, kBF16>(ix, p, pl, st);
-    default: return dispatch_qr<METRIC, kF16>(ix, p, pl, st);
-  }
-}
-
 // One scan launch over the shard. mode 0: first pass for queries [q_base, q_base + n), the
 // kernel variant `qb` (1 / 4 / 8 queries per pass); d_cand receives [nq][grid][kprime]
 // composites, *out_lists = grid. mode 1: range pass over retry-list entries
@@ -205,7 +115,7 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
   p.done_counter = ix->d_done;
   const uint32_t m = (uint32_t)ix->scan.grid * c.kprime;
   fill_tail(ix, c, m, false, &p.tail);
-  p.tail_sort_cap = tail_sort_cap(m, c.kprime, mode == 1);
+  p.tail_sort_cap = tail_sort_cap(m, c.kprime, p.tail.list_len, mode == 1);
   if (xchg) {
     fill_xchg(ix, &p.xchg);
     p.x_out_ids = c.x_ids;
@@ -215,13 +125,13 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
     if (xcap > p.tail_sort_cap) p.tail_sort_cap = xcap;
   }
   if (p.fused_tail) {
-    // room to stage the candidates' rows for the re-rank: all of them when that fits
+    // product tiles of the re-rank: all K' + 1 chains side by side when that fits
     const size_t lim = ix->smem_optin - 1024;
-    uint32_t rows_staged = mode == 1 ? 64 : c.kprime;
-    while (rows_staged > 1 &&
-           tail_smem_bytes(p.tail_sort_cap, ix->qld, ix->row_bytes, rows_staged) > lim)
-      rows_staged >>= 1;
-    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld, ix->row_bytes, rows_staged);
+    const bool cosine = ix->desc.metric == TSC_METRIC_COSINE;
+    uint32_t lanes = mode == 1 ? 255 : c.kprime + 1;
+    if (lanes > 255) lanes = 255;
+    while (lanes > 1 && tail_smem_bytes(p.tail_sort_cap, ix->qld, lanes, cosine) > lim) lanes >>= 1;
+    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld, lanes, cosine);
     if (need > ix->smem_optin - 1024) {
       set_error("scan: the tail needs %zu bytes of shared memory", need);
       return TSC_ERR_BAD_DIMS;
@@ -229,21 +139,12 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
     if (need > pl.smem) pl.smem = need;
   }
   p.smem_bytes = (uint32_t)pl.smem;
-  int32_t rc;
-  if (sparse) {
-    switch (ix->desc.metric) {
-      case TSC_METRIC_L2: rc = dispatch_sparse_dtype<kL2>(ix, p, pl, c.st); break;
-      case TSC_METRIC_INNER_PRODUCT: rc = dispatch_sparse_dtype<kIP>(ix, p, pl, c.st); break;
-      default: rc = dispatch_sparse_dtype<kCos>(ix, p, pl, c.st); break;
-    }
-    return rc;
-  }
+  // the kernels live in one translation unit per metric (tsc_scan_l2 / _ip / _cos.cu)
   switch (ix->desc.metric) {
-    case TSC_METRIC_L2: rc = dispatch_dtype<kL2>(ix, p, pl, c.st); break;
-    case TSC_METRIC_INNER_PRODUCT: rc = dispatch_dtype<kIP>(ix, p, pl, c.st); break;
-    default: rc = dispatch_dtype<kCos>(ix, p, pl, c.st); break;
+    case TSC_METRIC_L2: return scan_dispatch_l2(ix, p, pl, sparse, c.st);
+    case TSC_METRIC_INNER_PRODUCT: return scan_dispatch_ip(ix, p, pl, sparse, c.st);
+    default: return scan_dispatch_cos(ix, p, pl, sparse, c.st);
   }
-  return rc;
 }
 
 }  // namespace tsc

@@ -139,8 +139,7 @@ __host__ __device__ inline size_t scan_smem_warp_bytes(int qb, uint32_t kprime, 
 }
 
 // ---- block-level merge: W sorted lists -> one list of kp per query -------------
-// (bitonic sort of the composites in shared memory; every bulk copy this CTA
-// issued has been waited on, so no async write is outstanding)
+// (every bulk copy this CTA issued has been waited on, so no async write is outstanding)
 __device__ __forceinline__ void scan_block_merge(const ScanParams &p, const uint32_t *qi,
                                                  uint32_t nq, uint64_t *sortbuf,
                                                  const uint32_t *lkeys, const uint32_t *lids,
@@ -153,24 +152,32 @@ __device__ __forceinline__ void scan_block_merge(const ScanParams &p, const uint
     for (uint32_t i = (uint32_t)warps * kp + threadIdx.x; i < p.sort_cap; i += blockDim.x)
       sortbuf[i] = ~0ull;
     __syncthreads();
-    for (uint32_t k = 2; k <= p.sort_cap; k <<= 1) {
-      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-        for (uint32_t i = threadIdx.x; i < p.sort_cap; i += blockDim.x) {
-          uint32_t x = i ^ j;
-          if (x > i) {
-            uint64_t a = sortbuf[i], b = sortbuf[x];
-            bool up = (i & k) == 0;
-            if ((a > b) == up) {
-              sortbuf[i] = b;
-              sortbuf[x] = a;
-            }
-          }
-        }
-        __syncthreads();
-      }
-    }
+    // Merge by ranking: every list is sorted, so the position of an element in the merged
+    // order is its own index plus, for every other list, the number of entries below it (one
+    // binary search each). Ties exist only between empty slots; they are broken by list
+    // number (<= for lists before mine, < for lists after), which makes the ranks a
+    // permutation. One pass, no barrier per stage (the bitonic network this replaces spent
+    // ~6 us of every launch in its 36 barriers).
     uint64_t *out = p.cand + ((size_t)qi[q] * gridDim.x + blockIdx.x) * kp;
-    for (uint32_t i = threadIdx.x; i < kp; i += blockDim.x) out[i] = sortbuf[i];
+    for (uint32_t idx = threadIdx.x; idx < (uint32_t)warps * kp; idx += blockDim.x) {
+      const uint32_t w = idx / kp, i = idx - w * kp;
+      const uint64_t v = sortbuf[idx];
+      uint32_t rank = i;
+      for (uint32_t o = 0; o < (uint32_t)warps; o++) {
+        if (o == w) continue;
+        const uint64_t *l = sortbuf + (size_t)o * kp;
+        uint32_t lo = 0, hi = kp;   // first index whose entry is > v (o < w) or >= v (o > w)
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          const uint64_t x = l[mid];
+          const bool below = o < w ? x <= v : x < v;
+          if (below) lo = mid + 1;
+          else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < kp) out[rank] = v;
+    }
   }
 }
 
@@ -181,6 +188,9 @@ template <int QB>
 __device__ __forceinline__ uint32_t scan_queries(const ScanParams &p, uint32_t (&qi)[QB]) {
   uint32_t nq = p.nq;
   if (p.mode == 1) {
+    // launched with programmatic stream serialization: the first pass (whose tail writes
+    // retry_n / range_thr) has to be complete and visible before anything is read
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t n_retry = __ldcg(p.tail.retry_n);
     if (n_retry <= p.q_base) {
       if (p.last_retry && blockIdx.x == 0 && threadIdx.x == 0 && n_retry != 0) *p.tail.retry_n = 0;
@@ -216,6 +226,8 @@ __device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t 
   if (threadIdx.x == 0) *p.done_counter = 0;   // stream order: the next launch sees zero
   __threadfence();
   TSC_TRACE(p.tail.diag, 1);
+  // every other CTA has exited: let the range launch that follows be scheduled now
+  if (p.mode == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   for (uint32_t q = 0; q < nq; q++)
     tail_query<METRIC, DTYPE>(p.tail, qi[q], p.mode, q, smem, p.smem_bytes, p.tail_sort_cap);
   // the last range launch of a search leaves the retry list empty for the next search

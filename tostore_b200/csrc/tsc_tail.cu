@@ -65,6 +65,7 @@ static CertModel cert_gemm(const Index *ix) {
 void fill_tail(const Index *ix, const SearchCtx &c, uint32_t m, bool gemm_keys, TailParams *t) {
   t->cand = ix->d_cand;
   t->m = m;
+  t->list_len = gemm_keys ? 0 : c.kprime;   // scan lists are sorted ascending, K' entries each
   t->kprime = c.kprime;
   t->k = c.k;
   t->rows = ix->d_rows;
@@ -114,12 +115,11 @@ static int32_t run_tail(Index *ix, const TailParams &p, uint32_t nq, uint32_t so
                         cudaStream_t st) {
   static bool attr_done[64] = {false};
   auto kern = tail_kernel<METRIC, DTYPE>;
-  // stage up to 32 candidate rows per batch, within ~100 KB so that two CTAs share an SM
-  uint32_t rows_staged = p.kprime < 32 ? p.kprime : 32;
-  while (rows_staged > 1 &&
-         tail_smem_bytes(sort_cap, p.qld, p.row_bytes, rows_staged) > 100 * 1024)
-    rows_staged >>= 1;
-  const size_t smem = tail_smem_bytes(sort_cap, p.qld, p.row_bytes, rows_staged);
+  // product tiles for all K' + 1 chains at once when that fits in ~64 KB (several CTAs per SM)
+  const bool cosine = METRIC == kCos;
+  uint32_t lanes = p.kprime + 1 < (uint32_t)kTailThreads ? p.kprime + 1 : (uint32_t)kTailThreads;
+  while (lanes > 1 && tail_smem_bytes(sort_cap, p.qld, lanes, cosine) > 64 * 1024) lanes >>= 1;
+  const size_t smem = tail_smem_bytes(sort_cap, p.qld, lanes, cosine);
   if (!attr_done[ix->device & 63]) {
     TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)ix->smem_optin - 4 * 1024));
@@ -153,7 +153,7 @@ int32_t launch_tail(Index *ix, const SearchCtx &c, uint32_t m, bool gemm_keys) {
   }
   TailParams p{};
   fill_tail(ix, c, m, gemm_keys, &p);
-  const uint32_t sort_cap = tail_sort_cap(m, c.kprime, false);
+  const uint32_t sort_cap = tail_sort_cap(m, c.kprime, p.list_len, false);
   switch (ix->desc.metric) {
     case TSC_METRIC_L2: return run_tail_dtype<kL2>(ix, p, c.nq, sort_cap, c.st);
     case TSC_METRIC_INNER_PRODUCT: return run_tail_dtype<kIP>(ix, p, c.nq, sort_cap, c.st);

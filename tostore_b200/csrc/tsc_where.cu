@@ -234,8 +234,8 @@ int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, cons
     const uint64_t words = (ix->rows + 31) / 32;
     const uint64_t want = (words + 7) / 8;    // 8 warps per CTA
     const unsigned blocks = (unsigned)(want < (uint64_t)ix->sm_count * 8 ? want : ix->sm_count * 8);
-    where_eval_kernel<<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, ix->rows, ix->d_filter,
-                                              ix->d_live_count);
+    where_eval_kernel<<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, ix->rows, n_slots,
+                                              ix->d_filter, ix->d_live_count);
     TSC_CUDA(cudaGetLastError());
     ix->launches++;
     TSC_CUDA(cudaMemcpyAsync(&matched, ix->d_live_count, 8, cudaMemcpyDeviceToHost, st));

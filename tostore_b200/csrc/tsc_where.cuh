@@ -115,13 +115,28 @@ __host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog
 // rows written; a leaf on the column the previous leaf used re-uses the loaded value.
 __global__ void __launch_bounds__(256)
 where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_constant__ WhereCols cols,
-                  const uint64_t *__restrict__ args, uint64_t n_rows, uint32_t *__restrict__ out_bits,
-                  unsigned long long *__restrict__ matched) {
+                  const uint64_t *__restrict__ args, uint64_t n_rows, uint32_t n_slots,
+                  uint32_t *__restrict__ out_bits, unsigned long long *__restrict__ matched) {
   const int lane = threadIdx.x & 31;
   const uint64_t n_words = (n_rows + 31) / 32;
   const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long local = 0;
-  for (uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+  // The evaluator loads a column when the program first needs it, one dependent load after
+  // the other: a warp had ~256 bytes in flight and the kernel ran at 24 % of HBM (ncu,
+  // profiles/r02_first_call.log). Every column's lines of the words two iterations ahead are
+  // therefore pulled into L2 first (two 128-byte lines per column and word).
+  auto prefetch = [&](uint64_t w) {
+    if (w < n_words && (lane & 15) == 0) {
+      const uint64_t row = w * 32 + (uint64_t)lane;
+      for (uint32_t c = 0; c < n_slots; c++)
+        if (row < n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(cols.values[c] + row));
+    }
+  };
+  const uint64_t w0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  prefetch(w0);
+  prefetch(w0 + warps);
+  for (uint64_t w = w0; w < n_words; w += warps) {
+    prefetch(w + 2 * warps);
     const uint64_t row = w * 32 + lane;
     bool res = false;
     if (row < n_rows) {
