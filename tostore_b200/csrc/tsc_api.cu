@@ -136,8 +136,6 @@ void free_index(Index *ix) {
     if (ix->t_beg[i]) cudaEventDestroy(ix->t_beg[i]);
     if (ix->t_end[i]) cudaEventDestroy(ix->t_end[i]);
   }
-  if (ix->ev0) cudaEventDestroy(ix->ev0);
-  if (ix->ev1) cudaEventDestroy(ix->ev1);
   if (ix->scratch_ev) cudaEventDestroy(ix->scratch_ev);
   if (ix->stream) cudaStreamDestroy(ix->stream);
   cudaGetLastError();
@@ -166,11 +164,13 @@ int32_t hot_timer_begin(Index *ix, cudaStream_t st, int *slot) {
   }
   *slot = ix->t_head;
   TSC_CUDA(cudaEventRecord(ix->t_beg[*slot], st));
+  if (!ix->search_beg) ix->search_beg = ix->t_beg[*slot];
   return TSC_OK;
 }
 
 int32_t hot_timer_end(Index *ix, cudaStream_t st, int slot, double bytes, double flops) {
   TSC_CUDA(cudaEventRecord(ix->t_end[slot], st));
+  ix->last_hot_end = ix->t_end[slot];
   ix->t_bytes[slot] = bytes;
   ix->t_flops[slot] = flops;
   ix->t_head = (ix->t_head + 1) % Index::kTimers;
@@ -289,9 +289,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
     if (e == cudaSuccess) e = r;
   };
   ok(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-  ok(cudaEventCreate(&ix->ev0));
-  ok(cudaEventCreate(&ix->ev1));
-  ok(cudaEventCreateWithFlags(&ix->scratch_ev, cudaEventDisableTiming));
+  ok(cudaEventCreate(&ix->scratch_ev));
   for (int i = 0; i < Index::kTimers; i++) {
     ok(cudaEventCreate(&ix->t_beg[i]));
     ok(cudaEventCreate(&ix->t_end[i]));
@@ -320,7 +318,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
   ok(dev_alloc(ix, &ix->d_retry_n, 1));
   ok(dev_alloc(ix, &ix->d_range_count, (size_t)kRangeSlots));
   ok(dev_alloc(ix, &ix->d_range_buf, (size_t)kRangeSlots * kRangeCap));
-  ok(dev_alloc(ix, &ix->d_done, 2));
+  ok(dev_alloc(ix, &ix->d_done, 4));
   ok(dev_alloc(ix, &ix->d_cert_stat, (size_t)kStatSlots));
   ok(dev_alloc(ix, &ix->d_loc_counts, (size_t)ix->nq_max));
 #ifdef TSC_DIAG
@@ -339,7 +337,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
     ok(cudaMemsetAsync(ix->d_flags, 0, (size_t)ix->nq_max * 4, ix->stream));
     ok(cudaMemsetAsync(ix->d_retry_n, 0, 4, ix->stream));
     ok(cudaMemsetAsync(ix->d_range_count, 0, kRangeSlots * 4, ix->stream));
-    ok(cudaMemsetAsync(ix->d_done, 0, 8, ix->stream));
+    ok(cudaMemsetAsync(ix->d_done, 0, 16, ix->stream));
     ok(cudaMemsetAsync(ix->d_cert_stat, 0, kStatSlots * 8, ix->stream));
     ok(cudaStreamSynchronize(ix->stream));
   }
@@ -669,9 +667,11 @@ int32_t ix_stats_get(Index *ix, tsc_stats *out) {
   if (ix->host_only) return TSC_OK;
   if (ix->searches && ix->last_ms < 0) {
     TSC_CUDA(cudaSetDevice(ix->device));
-    TSC_CUDA(cudaEventSynchronize(ix->ev1));
     float ms = 0;
-    TSC_CUDA(cudaEventElapsedTime(&ms, ix->ev0, ix->ev1));
+    if (ix->search_beg && ix->scratch_mark) {
+      TSC_CUDA(cudaEventSynchronize(ix->scratch_mark));
+      TSC_CUDA(cudaEventElapsedTime(&ms, ix->search_beg, ix->scratch_mark));
+    }
     ix->last_ms = ms;
     ix->last_gbs = ms > 0 ? ix->last_gbs / (ms * 1e6) : 0;
   }

@@ -82,9 +82,6 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int32
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 // one lane of a converged warp; lets ptxas keep MMA / TMA operands in uniform
 // registers instead of emitting a per-lane R2UR waterfall around every UTCHMMA
 __device__ __forceinline__ bool elect_one() {

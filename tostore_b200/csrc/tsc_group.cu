@@ -378,7 +378,7 @@ int32_t grp_search_flags(Group &g, uint32_t nq, uint32_t *out_flags) {
   for (auto &s : g.shards) {
     Index *ix = s.get();
     TSC_CUDA(cudaSetDevice(ix->device));
-    if (ix->scratch_used) TSC_CUDA(cudaEventSynchronize(ix->scratch_ev));
+    if (ix->scratch_used) TSC_CUDA(cudaEventSynchronize(ix->scratch_mark));
     TSC_CUDA(cudaMemcpy(f.data(), ix->d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost));
     for (uint32_t q = 0; q < nq; q++)
       if (f[q] > out_flags[q]) out_flags[q] = f[q];

@@ -53,7 +53,6 @@ struct Index {
   int sm_count = 148;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
   // geometry of the embedding block in HBM: dense row-major [capacity, ld]
   uint32_t elem_bytes = 4;
@@ -101,7 +100,7 @@ struct Index {
   uint32_t *d_retry_n = nullptr;   // zero between searches
   uint32_t *d_range_count = nullptr; // [kRangeSlots], zero between launches
   uint64_t *d_range_buf = nullptr; // [kRangeSlots][kRangeCap]
-  uint32_t *d_done = nullptr;      // [2] last-CTA tickets (scan, exchange), zero between launches
+  uint32_t *d_done = nullptr;      // [4] last-CTA tickets (scan, exchange), scan work counter; zero between launches
   unsigned long long *d_cert_stat = nullptr;  // [kStatSlots]
   unsigned long long *d_trace = nullptr;      // diagnostics build: phase timestamps (tsc_tail.cuh)
   uint32_t *d_loc_counts = nullptr;  // [nq_max] shard-local result counts of a sharded search
@@ -111,7 +110,10 @@ struct Index {
   bool host_consumer = true;         // the search in flight delivers its result on this shard
   double last_threshold = 0;         // of the host-buffer search in flight (owed range passes)
   // one search at a time uses the scratch above: searches on other streams wait for this
-  cudaEvent_t scratch_ev = nullptr;
+  cudaEvent_t scratch_ev = nullptr;    // recorded at the end of a search unless a timer event already is
+  cudaEvent_t scratch_mark = nullptr;  // the event that marks the end of the last search (not owned)
+  cudaEvent_t search_beg = nullptr;    // first timer event of the last search (not owned)
+  cudaEvent_t last_hot_end = nullptr;  // most recent hot_timer_end event (not owned)
   cudaStream_t scratch_stream = nullptr;
   bool scratch_used = false;
   uint64_t *d_cand = nullptr;      // [nq_max][cand_lists][kprime_max]

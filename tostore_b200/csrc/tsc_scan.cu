@@ -113,6 +113,15 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
   p.last_retry = last_retry ? 1 : 0;
   p.nq_total = c.nq;
   p.done_counter = ix->d_done;
+  p.work_counter = ix->d_done + 2;
+  {
+    // 7/8 of the stages round-robin (a whole number of rounds), the rest on demand
+    const uint64_t total = (ix->rows + (uint64_t)pl.rows - 1) / (uint64_t)pl.rows;
+    const uint64_t gw = (uint64_t)ix->scan.grid * pl.warps;
+    p.static_stages = (total - total / 8) / gw * gw;
+    // small shards: the demand-driven part would be a handful of atomics per warp, all latency
+    if (total / gw < 16) p.static_stages = total;
+  }
   const uint32_t m = (uint32_t)ix->scan.grid * c.kprime;
   fill_tail(ix, c, m, false, &p.tail);
   p.tail_sort_cap = tail_sort_cap(m, c.kprime, p.tail.list_len, mode == 1);
@@ -125,18 +134,21 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
     if (xcap > p.tail_sort_cap) p.tail_sort_cap = xcap;
   }
   if (p.fused_tail) {
-    // product tiles of the re-rank: all K' + 1 chains side by side when that fits
+    // the re-rank stages the candidates' rows in shared memory: whole rows for all K' + 1
+    // chains when that fits (the scan's ring is usually larger already), else column chunks
     const size_t lim = ix->smem_optin - 1024;
-    const bool cosine = ix->desc.metric == TSC_METRIC_COSINE;
-    uint32_t lanes = mode == 1 ? 255 : c.kprime + 1;
-    if (lanes > 255) lanes = 255;
-    while (lanes > 1 && tail_smem_bytes(p.tail_sort_cap, ix->qld, lanes, cosine) > lim) lanes >>= 1;
-    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld, lanes, cosine);
-    if (need > ix->smem_optin - 1024) {
+    const uint32_t chains = mode == 1 ? (uint32_t)pl.warps * 32u : c.kprime + 1;
+    const size_t need = tail_smem_bytes(p.tail_sort_cap, ix->qld, ix->row_bytes, chains, lim);
+    if (need > lim) {
       set_error("scan: the tail needs %zu bytes of shared memory", need);
       return TSC_ERR_BAD_DIMS;
     }
     if (need > pl.smem) pl.smem = need;
+    // the selection's scratch (list prefixes + the entries that pass the head pivot)
+    const uint32_t lvl = (c.kprime + (uint32_t)ix->scan.grid - 1) / (uint32_t)ix->scan.grid;
+    const size_t sel = tail_fixed_bytes(p.tail_sort_cap, ix->qld) +
+                       ((size_t)ix->scan.grid * (4 * lvl < 8 ? 8 : 4 * lvl) + kHeadSelectCap) * 8;
+    if (sel > pl.smem && sel <= lim) pl.smem = sel;
   }
   p.smem_bytes = (uint32_t)pl.smem;
   // the kernels live in one translation unit per metric (tsc_scan_l2 / _ip / _cos.cu)

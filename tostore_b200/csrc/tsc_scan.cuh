@@ -52,6 +52,8 @@ struct ScanParams {
   uint32_t tail_sort_cap;    // Pair128 slots of the tail's sort buffer
   uint32_t smem_bytes;       // dynamic shared memory of this launch (the tail stages rows in it)
   uint32_t *done_counter;    // zero between launches
+  uint32_t *work_counter;    // dynamic stage blocks handed out so far; zero between launches
+  uint64_t static_stages;    // stages [0, static_stages) are dealt round-robin, the rest on demand
   TailParams tail;
   XchgParams xchg;
   int64_t *x_out_ids;        // exchange output (global top-k), [nq_total, k]
@@ -134,8 +136,9 @@ __host__ __device__ inline size_t scan_smem_warp_bytes(int qb, uint32_t kprime, 
                                                       uint32_t stage_bytes) {
   size_t lists = ((size_t)qb * kprime * 8 + 15) & ~(size_t)15;
   size_t bars = ((size_t)stages * 8 + 15) & ~(size_t)15;
+  size_t ids = ((size_t)stages * 4 + 15) & ~(size_t)15;   // which stage each ring slot holds
   size_t ring = (size_t)stages * stage_bytes;
-  return (lists + bars + ring + 127) & ~(size_t)127;
+  return (((lists + bars + ids + 127) & ~(size_t)127) + ring + 127) & ~(size_t)127;
 }
 
 // ---- block-level merge: W sorted lists -> one list of kp per query -------------
@@ -217,13 +220,16 @@ __device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t 
   TSC_TRACE(p.tail.diag, kTraceCta + blockIdx.x);
   if (p.mode == 0) scan_block_merge(p, qi, nq, sortbuf, lkeys, lids, p.kprime, warp, warps, lane);
   TSC_TRACE(p.tail.diag, kTraceCta + gridDim.x + blockIdx.x);
-  if (!p.fused_tail) return;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_ticket = atomicAdd(p.done_counter, 1u);
   __syncthreads();
   if (s_ticket != gridDim.x - 1) return;
-  if (threadIdx.x == 0) *p.done_counter = 0;   // stream order: the next launch sees zero
+  if (threadIdx.x == 0) {   // stream order: the next launch sees zero
+    *p.done_counter = 0;
+    *p.work_counter = 0;
+  }
+  if (!p.fused_tail) return;
   __threadfence();
   TSC_TRACE(p.tail.diag, 1);
   // every other CTA has exited: let the range launch that follows be scheduled now
@@ -283,6 +289,8 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   size_t off = ((size_t)QB * kp * 8 + 15) & ~(size_t)15;
   uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + off);
   off += ((size_t)S * 8 + 15) & ~(size_t)15;
+  uint32_t *slot_stage = reinterpret_cast<uint32_t *>(wbase + off);   // [S]
+  off += ((size_t)S * 4 + 15) & ~(size_t)15;
   off = (off + 127) & ~(size_t)127;
   uint8_t *ring = wbase + off;
 
@@ -306,6 +314,38 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   const uint64_t gw = (uint64_t)blockIdx.x * warps + warp;
   const uint64_t GW = (uint64_t)gridDim.x * warps;
 
+  // Work distribution. SMs do not get equal shares of HBM bandwidth (the last CTA of a
+  // round-robin deal finished ~8 % after the median one: tools/scan_trace.py), so only the
+  // first p.static_stages stages are dealt round-robin; the rest is handed out on demand in
+  // blocks of kDynBlock consecutive stages from an atomic counter. Either way a warp sees its
+  // rows in increasing order. Lane 0 runs the generator and records which stage each ring
+  // slot holds (kNoStage = nothing more: the slots after it hold nothing either).
+  constexpr uint32_t kNoStage = 0xFFFFFFFFu;
+  constexpr uint32_t kDynBlock = 4;
+  uint64_t next_static = gw;
+  uint64_t dyn_next = 0;
+  uint32_t dyn_left = 0;
+  bool dyn_done = false;
+  auto next_stage = [&]() -> uint32_t {
+    if (next_static < p.static_stages) {
+      const uint64_t st = next_static;
+      next_static += GW;
+      return (uint32_t)st;
+    }
+    if (dyn_left == 0) {
+      if (dyn_done) return kNoStage;
+      const uint64_t base = p.static_stages + (uint64_t)atomicAdd(p.work_counter, 1u) * kDynBlock;
+      if (base >= total_stages) {
+        dyn_done = true;
+        return kNoStage;
+      }
+      dyn_next = base;
+      dyn_left = total_stages - base < kDynBlock ? (uint32_t)(total_stages - base) : kDynBlock;
+    }
+    dyn_left--;
+    return (uint32_t)dyn_next++;
+  };
+
   auto issue = [&](uint32_t s, uint64_t st) {
     uint64_t row0 = st * R;
     uint64_t nrow = p.n_rows - row0;
@@ -318,10 +358,12 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
 
   if (lane == 0) {
     for (uint32_t s = 0; s < S; s++) {
-      uint64_t st = gw + (uint64_t)s * GW;
-      if (st < total_stages) issue(s, st);
+      const uint32_t st = next_stage();
+      slot_stage[s] = st;
+      if (st != kNoStage) issue(s, st);
     }
   }
+  __syncwarp();
 
   // mode 0: threshold = the list's largest key; mode 1: fixed T + 1 (key <= T passes)
   uint32_t thr[QB];
@@ -331,7 +373,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
 
   uint32_t s = 0, parity = 0;
   const uint32_t cpr = p.chunks_per_row;
-  for (uint64_t st = gw; st < total_stages; st += GW) {
+  for (;;) {
+    const uint64_t st = slot_stage[s];
+    if (st == kNoStage) break;
     mbar_wait(smem_u32(&bars[s]), parity);
 
     float acc[QB][R];
@@ -382,10 +426,11 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
           }
       }
     }
-    __syncwarp();  // every lane is done reading this stage
-    {
-      uint64_t nst = st + (uint64_t)S * GW;
-      if (lane == 0 && nst < total_stages) issue(s, nst);
+    __syncwarp();  // every lane is done reading this stage (and its slot_stage entry)
+    if (lane == 0) {
+      const uint32_t nst = next_stage();
+      slot_stage[s] = nst;
+      if (nst != kNoStage) issue(s, nst);
     }
 
     // ---- butterfly reduction: every lane ends with the full sums -----------
@@ -425,6 +470,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
     }
   }
 
+  // every copy has been waited on; the tail re-uses the ring (barriers included) as plain memory
+  if (lane == 0)
+    for (uint32_t i = 0; i < S; i++) mbar_inval(smem_u32(&bars[i]));
   scan_finish<METRIC, DTYPE, QB>(p, qi, nq, smem, sortbuf, lkeys, lids, warp, warps, lane);
 }
 
@@ -467,6 +515,8 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
   size_t off = ((size_t)QB * kp * 8 + 15) & ~(size_t)15;
   uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + off);
   off += ((size_t)S * 8 + 15) & ~(size_t)15;
+  uint32_t *slot_stage = reinterpret_cast<uint32_t *>(wbase + off);   // [S]
+  off += ((size_t)S * 4 + 15) & ~(size_t)15;
   off = (off + 127) & ~(size_t)127;
   uint8_t *ring = wbase + off;
 
@@ -629,6 +679,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
     }
   }
   __syncwarp();
+  // every copy has been waited on; the tail re-uses the ring (barriers included) as plain memory
+  if (lane == 0)
+    for (uint32_t i = 0; i < S; i++) mbar_inval(smem_u32(&bars[i]));
   scan_finish<METRIC, DTYPE, QB>(p, qi, nq, smem, sortbuf, lkeys, lids, warp, warps, lane);
 }
 

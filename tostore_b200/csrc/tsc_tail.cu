@@ -115,11 +115,9 @@ static int32_t run_tail(Index *ix, const TailParams &p, uint32_t nq, uint32_t so
                         cudaStream_t st) {
   static bool attr_done[64] = {false};
   auto kern = tail_kernel<METRIC, DTYPE>;
-  // product tiles for all K' + 1 chains at once when that fits in ~64 KB (several CTAs per SM)
-  const bool cosine = METRIC == kCos;
-  uint32_t lanes = p.kprime + 1 < (uint32_t)kTailThreads ? p.kprime + 1 : (uint32_t)kTailThreads;
-  while (lanes > 1 && tail_smem_bytes(sort_cap, p.qld, lanes, cosine) > 64 * 1024) lanes >>= 1;
-  const size_t smem = tail_smem_bytes(sort_cap, p.qld, lanes, cosine);
+  // whole candidate rows for all K' + 1 chains when that fits in ~100 KB (two CTAs per SM),
+  // column chunks otherwise
+  const size_t smem = tail_smem_bytes(sort_cap, p.qld, p.row_bytes, p.kprime + 1, 100 * 1024);
   if (!attr_done[ix->device & 63]) {
     TSC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)ix->smem_optin - 4 * 1024));

@@ -11,11 +11,13 @@
 //      core/ngh_graph_engine.dart:908-946: fp32 inputs widened to fp64, sequential index
 //      order, every multiply and add a separate IEEE double operation (no FMA:
 //      __dmul_rn/__dadd_rn), sqrt / divide correctly rounded — so the distances returned
-//      are bit-identical to the Dart code. The PRODUCTS are independent of each other, so
-//      the whole CTA computes them tile by tile into shared memory (each one an individually
-//      rounded multiply); the ADDITIONS are sequential by definition, so ONE LANE per
-//      candidate applies them strictly left to right — a warp re-ranks 32 candidates in the
-//      time of one, and a lane's critical path is one dependent DADD per element;
+//      are bit-identical to the Dart code. The ADDITIONS are sequential by definition, so
+//      ONE LANE per candidate applies them strictly left to right: a warp re-ranks 32
+//      candidates in the time of one and a lane's critical path is one dependent DADD
+//      (~10 cycles) per element, with the element's widening, subtract and multiply issued
+//      in its shadow. The candidates' rows are staged in shared memory by bulk async copies
+//      (one per candidate, all in flight at once: ONE memory round trip), in column chunks
+//      with two buffers when K' whole rows do not fit;
 //   3. drop `distance > threshold` (:127), sort ascending with Dart's double.compareTo
 //      order (-0.0 < 0.0, NaN last; ties by node id), cut at k (:133-134);
 //   4. CERTIFY the candidate stage. The reference re-ranks everything it kept (:115-134);
@@ -37,7 +39,7 @@
 namespace tsc {
 
 constexpr uint32_t kSelectSortMax = 1024;  // M up to this is simply sorted
-constexpr uint32_t kHeadSelectCap = 256;   // composites the head-pivot filter may let through
+constexpr uint32_t kHeadSelectCap = 1024;  // composites the head-pivot filter may let through
 constexpr uint32_t kMaxRerank = 512;
 constexpr int kRadixBins = 2048;           // 11-bit digits
 constexpr uint32_t kRangeCap = 4096;       // rows the range pass can hold per query
@@ -203,24 +205,32 @@ struct TailParams {
 };
 
 // shared memory of the tail (dynamic):
-//   Pair128[sort_cap] | hist[kRadixBins] | q[qld] fp32 | product tiles
-// A product tile is [2 buffers][1 or 2 arrays][kProdChunk][lanes | 1] doubles; `lanes`
-// chains (candidates + the query's own |q|^2) run side by side per batch.
+//   Pair128[sort_cap] | hist[kRadixBins] | q[qld] fp64 | row stage
+// The row stage holds, per chain of a batch, `chunk` bytes of the candidate's row at a stride
+// of an odd number of 16-byte units (a quarter warp's LDS.128 of eight consecutive chains hits
+// eight different bank groups), once (whole rows fit) or twice (column chunks, double buffered).
 __host__ __device__ inline size_t tail_fixed_bytes(uint32_t sort_cap, uint32_t qld) {
-  return (((size_t)sort_cap * sizeof(Pair128) + (size_t)kRadixBins * 4 + (size_t)qld * 4) + 15) &
-         ~(size_t)15;
+  return (((size_t)sort_cap * sizeof(Pair128) + (size_t)kRadixBins * 4 + (size_t)qld * 8) + 127) &
+         ~(size_t)127;
 }
-__host__ __device__ inline size_t tail_tile_bytes(uint32_t lanes, bool cosine) {
-  return (size_t)2 * (cosine ? 2 : 1) * kProdChunk * (lanes | 1u) * 8;
+__host__ __device__ inline uint32_t tail_stage_stride(uint32_t chunk_bytes) {
+  return ((chunk_bytes >> 4) & 1u) ? chunk_bytes : chunk_bytes + 16u;
 }
-__host__ __device__ inline size_t tail_smem_bytes(uint32_t sort_cap, uint32_t qld, uint32_t lanes,
-                                                  bool cosine) {
-  return tail_fixed_bytes(sort_cap, qld) + tail_tile_bytes(lanes, cosine) + 64;
+constexpr uint32_t kTailMinChunk = 128;   // bytes of a row per chain and buffer, at least
+// what a launch should provide: whole rows for `chains` chains when that stays within `limit`,
+// otherwise `limit` (the tail then works in column chunks and / or several batches)
+__host__ __device__ inline size_t tail_smem_bytes(uint32_t sort_cap, uint32_t qld, uint32_t row_bytes,
+                                                  uint32_t chains, size_t limit) {
+  const size_t fixed = tail_fixed_bytes(sort_cap, qld);
+  const size_t whole = fixed + (size_t)chains * tail_stage_stride(row_bytes) + 64;
+  const size_t least = fixed + (size_t)2 * tail_stage_stride(kTailMinChunk) + 64;
+  if (whole <= limit) return whole;
+  return limit > least ? limit : least;
 }
 __host__ __device__ inline uint32_t tail_sort_cap(uint32_t m, uint32_t kprime, uint32_t list_len,
                                                   bool range) {
   uint32_t need = range ? kRangeCap : (m <= kSelectSortMax ? m : kprime);
-  if (!range && m > kSelectSortMax && list_len > 0 && need < kHeadSelectCap) need = kHeadSelectCap;
+  (void)list_len;
   uint32_t p = 2;
   while (p < need) p <<= 1;
   return p;
@@ -334,36 +344,39 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
                                         uint8_t *sm, size_t sm_bytes, uint32_t sort_cap) {
   Pair128 *buf = reinterpret_cast<Pair128 *>(sm);
   uint32_t *hist = reinterpret_cast<uint32_t *>(sm + (size_t)sort_cap * sizeof(Pair128));
-  float *qs = reinterpret_cast<float *>(hist + kRadixBins);
+  double *qd = reinterpret_cast<double *>(hist + kRadixBins);   // the query, widened
   __shared__ uint64_t s_prefix, s_pivot;
   __shared__ uint32_t s_remaining, s_count, s_bucket, s_valid;
   __shared__ double s_mag_a;
 
   const uint32_t tid = threadIdx.x;
   const uint64_t *cand = p.cand + (size_t)qi * p.m;
-  // head-pivot selection applies: sorted lists, at least K' of them, heads fit the scratch
-  const bool use_heads = mode == 0 && p.m > kSelectSortMax && p.list_len > 0 &&
-                         p.m / p.list_len >= p.kprime && p.m / p.list_len <= kRadixBins / 2 &&
-                         sort_cap >= kHeadSelectCap;
-  // Everything the selection needs from global memory is requested up front, in ONE round
-  // trip: the query, the list heads and this thread's share of the composites (registers).
-  constexpr int kOwn = 16;
-  uint64_t own[kOwn];
-  const bool own_ok = use_heads && p.m <= (uint32_t)kOwn * blockDim.x;
+  // Selection over sorted lists (the scan's per-CTA lists). With L lists, t = ceil(K' / L) and
+  // r = ceil(K' / t): the r-th smallest of the lists' t-th entries, H, is >= the K'-th smallest
+  // composite overall (the r lists at or below it hold t entries <= H each). Everything <= H
+  // is collected (a few more than K' entries: each list is a random 1 / L sample of the rows)
+  // and ranked by counting. Only a PREFIX of every list is read: P = max(8, 4t) entries, one
+  // round trip together with the query; a list whose whole prefix is <= H is walked further.
+  const uint32_t n_lists = p.list_len ? p.m / p.list_len : 0;
+  const uint32_t lvl = n_lists ? (p.kprime + n_lists - 1) / n_lists : 0;          // t
+  const uint32_t lvl_rank = lvl ? (p.kprime + lvl - 1) / lvl : 0;                  // r
+  uint32_t pre = 4 * lvl < 8 ? 8 : 4 * lvl;                                        // P
+  if (pre > p.list_len) pre = p.list_len;
+  uint64_t *prefix = reinterpret_cast<uint64_t *>(sm + tail_fixed_bytes(sort_cap, p.qld));
+  uint64_t *picked = prefix + (size_t)n_lists * pre;   // [kHeadSelectCap]
+  const bool use_heads =
+      mode == 0 && p.m > kSelectSortMax && p.list_len > 0 && lvl <= p.list_len &&
+      n_lists <= kRadixBins / 2 &&
+      tail_fixed_bytes(sort_cap, p.qld) + ((size_t)n_lists * pre + kHeadSelectCap) * 8 <= sm_bytes;
   __syncthreads();   // the caller's use of `sm` is over
-  if (own_ok) {
-#pragma unroll
-    for (int j = 0; j < kOwn; j++) {
-      const uint32_t i = tid + (uint32_t)j * blockDim.x;
-      own[j] = i < p.m ? __ldcg(cand + i) : ~0ull;
+  if (use_heads) {
+    for (uint32_t idx = tid; idx < n_lists * pre; idx += blockDim.x) {
+      const uint32_t l = idx / pre, j = idx - l * pre;
+      prefix[idx] = __ldcg(cand + (size_t)l * p.list_len + j);
     }
   }
-  if (use_heads) {
-    uint64_t *heads = reinterpret_cast<uint64_t *>(hist);
-    const uint32_t nl = p.m / p.list_len;
-    for (uint32_t l = tid; l < nl; l += blockDim.x) heads[l] = __ldcg(cand + (size_t)l * p.list_len);
-  }
-  for (uint32_t i = tid; i < p.qld; i += blockDim.x) qs[i] = p.queries[(size_t)qi * p.qld + i];
+  for (uint32_t i = tid; i < p.qld; i += blockDim.x)
+    qd[i] = (double)p.queries[(size_t)qi * p.qld + i];
   if (tid == 0) {
     s_prefix = 0;
     s_pivot = ~0ull;
@@ -408,51 +421,53 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
     if (!all_in) pivot = buf[p.kprime - 1].hi;
     selected = true;
   } else if (use_heads) {
-    // Sorted lists: H = the K'-th smallest list head is >= the K'-th smallest composite
-    // overall (the K' heads at or below it are K' composites <= H). Rank the heads against
-    // each other, let every composite <= H through, sort the few that pass.
-    const uint32_t nl = p.m / p.list_len;
-    const uint64_t *heads = reinterpret_cast<const uint64_t *>(hist);   // loaded above
-    for (uint32_t i = tid; i < sort_cap; i += blockDim.x) {
-      buf[i].hi = ~0ull;
-      buf[i].lo = 0;
-    }
-    for (uint32_t l = tid; l < nl; l += blockDim.x) {
+    uint64_t *heads = reinterpret_cast<uint64_t *>(hist);
+    for (uint32_t l = tid; l < n_lists; l += blockDim.x) heads[l] = prefix[(size_t)l * pre + lvl - 1];
+    __syncthreads();
+    for (uint32_t l = tid; l < n_lists; l += blockDim.x) {
       const uint64_t v = heads[l];
       uint32_t rank = 0;
-      for (uint32_t j = 0; j < nl; j++) {
+      for (uint32_t j = 0; j < n_lists; j++) {
         const uint64_t w = heads[j];
-        rank += (w < v) || (w == v && j < l);   // empty lists tie at ~0: order them by index
+        rank += (w < v) || (w == v && j < l);   // empty entries tie at ~0: order them by index
       }
-      if (rank == p.kprime - 1) s_pivot = v;
+      if (rank == lvl_rank - 1) s_pivot = v;
     }
     __syncthreads();
     const uint64_t H = s_pivot;
-    if ((uint32_t)(H >> 32) != kEmptyKey) {   // else: fewer than K' non-empty lists -> radix path
-      if (own_ok) {
-#pragma unroll
-        for (int j = 0; j < kOwn; j++)
-          if (own[j] <= H) {
-            const uint32_t s = atomicAdd(&s_count, 1u);
-            if (s < sort_cap) buf[s].hi = own[j];
-          }
-      } else {
-        for (uint32_t i = tid; i < p.m; i += blockDim.x) {
-          const uint64_t v = __ldcg(cand + i);
-          if (v <= H) {
-            const uint32_t s = atomicAdd(&s_count, 1u);
-            if (s < sort_cap) buf[s].hi = v;
+    if ((uint32_t)(H >> 32) != kEmptyKey) {   // else: fewer than K' entries in reach -> radix path
+      for (uint32_t idx = tid; idx < n_lists * pre; idx += blockDim.x) {
+        uint64_t v = prefix[idx];
+        if (v > H) continue;
+        uint32_t sl = atomicAdd(&s_count, 1u);
+        if (sl < kHeadSelectCap) picked[sl] = v;
+        const uint32_t l = idx / pre;
+        if (idx - l * pre == pre - 1) {   // the whole prefix passed: walk on
+          for (uint32_t j = pre; j < p.list_len; j++) {
+            v = __ldcg(cand + (size_t)l * p.list_len + j);
+            if (v > H) break;
+            sl = atomicAdd(&s_count, 1u);
+            if (sl < kHeadSelectCap) picked[sl] = v;
           }
         }
       }
       __syncthreads();
       const uint32_t cnt = s_count;   // >= K' by construction
-      if (cnt <= sort_cap) {
-        uint32_t n2 = 2;
-        while (n2 < cnt) n2 <<= 1;
-        bitonic_sort_pairs(buf, n2);
+      if (cnt <= kHeadSelectCap) {
+        // composites are distinct (distinct rows): counting the smaller ones is the rank
+        for (uint32_t i = tid; i < cnt; i += blockDim.x) {
+          const uint64_t v = picked[i];
+          uint32_t rank = 0;
+          for (uint32_t j = 0; j < cnt; j++) rank += picked[j] < v;
+          if (rank < p.kprime) {
+            buf[rank].hi = v;
+            buf[rank].lo = 0;
+          }
+          if (rank == p.kprime - 1) s_pivot = v;
+        }
+        __syncthreads();
         ncand = p.kprime;
-        pivot = buf[p.kprime - 1].hi;
+        pivot = s_pivot;
         selected = true;
       }
       __syncthreads();
@@ -497,136 +512,142 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
 
   // ---- 2. exact fp64 re-rank -------------------------------------------------------------
   // Chain 0 is the query's own |q|^2 (magA of _cosineSimlarity, also the certificate's
-  // ||q||^2), chains 1..ncand the candidates. Per tile of kProdChunk elements every thread
-  // computes products (each an individually rounded IEEE multiply of exactly widened fp32
-  // values: order-free) into shared memory, transposed so that the chain lanes read
-  // consecutive words; then lane c adds its chain's tile left to right. The products of the
-  // next tile are prepared while the lanes add the current one (two buffers).
-  constexpr int NA = METRIC == kCos ? 2 : 1;
-  double *tiles = reinterpret_cast<double *>(sm + tail_fixed_bytes(sort_cap, p.qld));
-  uint32_t lanes_max = 0;
+  // ||q||^2), chains 1..ncand the candidates; thread c of a batch owns chain base + c. Every
+  // thread with a live candidate issues ONE bulk copy of its row (or of the current column
+  // chunk of it) into its stage slot and arrives on the buffer's mbarrier with the byte count;
+  // everybody else just arrives. The chain lanes then walk their slot 16 bytes at a time:
+  // widen, (subtract,) multiply — each an individually rounded IEEE operation on exactly
+  // widened fp32 values — and add to the running sum, strictly in index order.
+  constexpr int E = Chunk<DTYPE>::kElems;
+  constexpr uint32_t kEsz = 16 / E;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  uint8_t *stage = sm + tail_fixed_bytes(sort_cap, p.qld);
+  const uint32_t need_bytes = ((p.dims + E - 1) / E) * 16u;   // <= row_bytes
+  const uint32_t n_chains = ncand + 1;
+  // batch geometry: `lanes` chains side by side, `chunk` bytes of each row per buffer
+  uint32_t lanes = n_chains < blockDim.x ? n_chains : blockDim.x;
+  uint32_t chunk = 0, nbuf = 1;
   {
     const size_t fixed = tail_fixed_bytes(sort_cap, p.qld);
     const size_t avail = sm_bytes > fixed + 64 ? sm_bytes - fixed - 64 : 0;
-    lanes_max = (uint32_t)(avail / ((size_t)2 * NA * kProdChunk * 8));
-    if (lanes_max > 1 && !(lanes_max & 1u)) lanes_max--;   // the padded width (lanes | 1) must fit
-    if (lanes_max > blockDim.x) lanes_max = blockDim.x;
-  }
-  // pull the candidates' rows towards L2 (they were streamed with evict-first)
-  if (ncand <= kMaxRerank) {
-    const uint32_t lines = (p.row_bytes + 127) / 128;
-    for (uint32_t idx = tid; idx < ncand * lines; idx += blockDim.x) {
-      const uint32_t row = (uint32_t)buf[idx / lines].hi;
-      if (row != kInvalidRow)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rows + (size_t)row * p.row_bytes +
-                                                     (size_t)(idx % lines) * 128));
+    for (;;) {
+      if ((size_t)lanes * tail_stage_stride(need_bytes) <= avail) {
+        chunk = need_bytes;
+        nbuf = 1;
+        break;
+      }
+      uint32_t c = (uint32_t)(avail / ((size_t)2 * lanes)) & ~15u;
+      if (c >= 16 && tail_stage_stride(c) * (size_t)2 * lanes > avail) c -= 16;
+      if (c >= kTailMinChunk || lanes == 1) {
+        chunk = c;
+        nbuf = 2;
+        break;
+      }
+      lanes = (lanes + 1) >> 1;
     }
   }
-  const uint32_t n_chains = ncand + 1;
-  const uint32_t n_tiles = (p.dims + kProdChunk - 1) / kProdChunk;
-  for (uint32_t base = 0; base < n_chains && lanes_max > 0; base += lanes_max) {
-    const uint32_t nb = n_chains - base < lanes_max ? n_chains - base : lanes_max;
-    const uint32_t lp = nb | 1u;                        // padded tile width
-    const size_t tile_doubles = (size_t)NA * kProdChunk * lp;
-    // Products of tile t -> tiles[t & 1]. Item idx = (chain r, element e): consecutive threads
-    // take consecutive elements of one row (coalesced), the tile is stored transposed.
-    // Small batches (the usual K' + 1 chains) split the work in two so that the row loads of
-    // tile t + 1 are in flight while the lanes add tile t: load_tile / store_tile.
-    constexpr int kPf = 4;
-    const bool pf = nb * kProdChunk <= kPf * blockDim.x;
-    float bv[kPf];
-    auto item = [&](uint32_t idx, uint32_t t, uint32_t &r, uint32_t &e, uint32_t &i, uint32_t &row) {
-      r = idx / kProdChunk;
-      e = idx - r * kProdChunk;
-      i = t * kProdChunk + e;
-      const uint32_t c = base + r;
-      row = c == 0 ? kInvalidRow : (uint32_t)buf[c - 1].hi;
+  const uint32_t stride = tail_stage_stride(chunk);
+  const uint32_t n_chunks = chunk ? (need_bytes + chunk - 1) / chunk : 0;
+  const uint64_t policy = policy_evict_first();
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar[0]), blockDim.x);
+    mbar_init(smem_u32(&s_bar[1]), blockDim.x);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t uses0 = 0, uses1 = 0;   // completed phases of the two barriers (uniform)
+  for (uint32_t base = 0; base < n_chains && chunk != 0; base += lanes) {
+    const uint32_t nb = n_chains - base < lanes ? n_chains - base : lanes;
+    const uint32_t chain = base + tid;
+    const bool mine = tid < nb;
+    const bool is_q = mine && chain == 0;
+    uint32_t row = kInvalidRow;
+    if (mine && chain > 0) row = (uint32_t)buf[chain - 1].hi;
+    const bool has_row = row != kInvalidRow;
+    // chunk t of every chain of the batch -> buffer t & (nbuf - 1)
+    auto issue = [&](uint32_t t) {
+      const uint32_t b = t & (nbuf - 1u);
+      const uint32_t bar = smem_u32(&s_bar[b]);
+      const uint32_t off = t * chunk;
+      const uint32_t bytes = need_bytes - off < chunk ? need_bytes - off : chunk;
+      if (has_row) {
+        mbar_expect_tx(bar, bytes);   // arrive + expect
+        bulk_g2s(smem_u32(stage + ((size_t)b * lanes + tid) * stride),
+                 p.rows + (size_t)row * p.row_bytes + off, bytes, bar, policy);
+      } else {
+        mbar_arrive(bar);
+      }
     };
-    auto product = [&](double *dst, uint32_t r, uint32_t e, uint32_t i, bool is_q, bool has_row,
-                       float bf) {
-      double p0 = 0.0, p1 = 0.0;
-      if (i < p.dims) {
-        const double a = (double)qs[i];
-        if (is_q) {
-          p0 = __dmul_rn(a, a);
-        } else if (has_row) {
-          const double b = (double)bf;
-          if (METRIC == kL2) {
-            const double diff = __dsub_rn(a, b);
-            p0 = __dmul_rn(diff, diff);
-          } else {
-            p0 = __dmul_rn(a, b);
-            if (METRIC == kCos) p1 = __dmul_rn(b, b);
+    issue(0);
+    if (nbuf == 2 && n_chunks > 1) issue(1);
+    double s0 = 0.0, s1 = 0.0;   // +0.0: `double sum = 0.0` of the Dart loops
+    for (uint32_t t = 0; t < n_chunks; t++) {
+      const uint32_t b = t & (nbuf - 1u);
+      if (mine) {
+        mbar_wait(smem_u32(&s_bar[b]), (b ? uses1 : uses0) & 1u);
+        const uint32_t off = t * chunk;
+        const uint32_t bytes = need_bytes - off < chunk ? need_bytes - off : chunk;
+        const uint32_t e0 = off / kEsz;                       // first element of the chunk
+        const uint32_t ne = p.dims - e0 < bytes / kEsz ? p.dims - e0 : bytes / kEsz;
+        // a chain without a row (the query's, an empty candidate slot) reads slot 0's bytes
+        // and discards them
+        const uint4 *src = reinterpret_cast<const uint4 *>(
+            stage + ((size_t)b * lanes + (has_row ? tid : 0u)) * stride);
+        const double *qa = qd + e0;
+        const uint32_t nv = ne / E;
+#pragma unroll 2
+        for (uint32_t v = 0; v < nv; v++) {
+          float bf[E];
+          Chunk<DTYPE>::unpack(src[v], bf);
+#pragma unroll
+          for (int e = 0; e < E; e += 2) {
+            const double2 a2 = *reinterpret_cast<const double2 *>(qa + v * E + e);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const double a = h ? a2.y : a2.x;
+              const double bw = (double)bf[e + h];
+              if (METRIC == kL2) {
+                const double x = is_q ? a : __dsub_rn(a, bw);
+                s0 = __dadd_rn(s0, __dmul_rn(x, x));
+              } else {
+                const double x = is_q ? a : bw;
+                s0 = __dadd_rn(s0, __dmul_rn(a, x));
+                if (METRIC == kCos) s1 = __dadd_rn(s1, __dmul_rn(bw, bw));
+              }
+            }
+          }
+        }
+        if (nv * E < ne) {   // dims is not a multiple of the vector width: the last few
+          float bf[E];
+          Chunk<DTYPE>::unpack(src[nv], bf);
+#pragma unroll
+          for (int e = 0; e < E; e++) {
+            if (nv * E + e < ne) {
+              const double a = qa[nv * E + e];
+              const double bw = (double)bf[e];
+              if (METRIC == kL2) {
+                const double x = is_q ? a : __dsub_rn(a, bw);
+                s0 = __dadd_rn(s0, __dmul_rn(x, x));
+              } else {
+                const double x = is_q ? a : bw;
+                s0 = __dadd_rn(s0, __dmul_rn(a, x));
+                if (METRIC == kCos) s1 = __dadd_rn(s1, __dmul_rn(bw, bw));
+              }
+            }
           }
         }
       }
-      dst[(size_t)e * lp + r] = p0;
-      if (METRIC == kCos) dst[(size_t)(kProdChunk + e) * lp + r] = p1;
-    };
-    auto load_tile = [&](uint32_t t) {
-#pragma unroll
-      for (int j = 0; j < kPf; j++) {
-        const uint32_t idx = tid + (uint32_t)j * blockDim.x;
-        bv[j] = 0.0f;
-        if (idx < nb * kProdChunk) {
-          uint32_t r, e, i, row;
-          item(idx, t, r, e, i, row);
-          if (row != kInvalidRow && i < p.dims)
-            bv[j] = load_elem<DTYPE>(p.rows + (size_t)row * p.row_bytes, i);
-        }
-      }
-    };
-    auto store_tile = [&](uint32_t t) {
-      double *dst = tiles + (size_t)(t & 1u) * tile_doubles;
-#pragma unroll
-      for (int j = 0; j < kPf; j++) {
-        const uint32_t idx = tid + (uint32_t)j * blockDim.x;
-        if (idx < nb * kProdChunk) {
-          uint32_t r, e, i, row;
-          item(idx, t, r, e, i, row);
-          product(dst, r, e, i, base + r == 0, row != kInvalidRow, bv[j]);
-        }
-      }
-    };
-    auto make_tile = [&](uint32_t t) {
-      double *dst = tiles + (size_t)(t & 1u) * tile_doubles;
-      for (uint32_t idx = tid; idx < nb * kProdChunk; idx += blockDim.x) {
-        uint32_t r, e, i, row;
-        item(idx, t, r, e, i, row);
-        float bf = 0.0f;
-        if (row != kInvalidRow && i < p.dims)
-          bf = load_elem<DTYPE>(p.rows + (size_t)row * p.row_bytes, i);
-        product(dst, r, e, i, base + r == 0, row != kInvalidRow, bf);
-      }
-    };
-    make_tile(0);
-    __syncthreads();
-    double s0 = 0.0, s1 = 0.0;   // +0.0: `double sum = 0.0` of the Dart loops
-    for (uint32_t t = 0; t < n_tiles; t++) {
-      if (t + 1 < n_tiles) {
-        if (pf) load_tile(t + 1);
-        else make_tile(t + 1);
-      }
-      if (tid < nb) {
-        const double *src = tiles + (size_t)(t & 1u) * tile_doubles + tid;
-        // elements past dims are +0.0 products: adding them changes nothing (a running
-        // sum that started at +0.0 is never -0.0)
-#pragma unroll 8
-        for (int e = 0; e < kProdChunk; e++) {
-          s0 = __dadd_rn(s0, src[(size_t)e * lp]);
-          if (METRIC == kCos) s1 = __dadd_rn(s1, src[(size_t)(kProdChunk + e) * lp]);
-        }
-      }
-      if (pf && t + 1 < n_tiles) store_tile(t + 1);
-      __syncthreads();
+      if (b) uses1++;
+      else uses0++;
+      __syncthreads();   // the buffer is free again
+      if (t + nbuf < n_chunks) issue(t + nbuf);
     }
-    if (base == 0 && tid == 0) s_mag_a = s0;
+    if (is_q) s_mag_a = s0;
     __syncthreads();
-    if (tid < nb && base + tid > 0) {
-      const uint32_t ci = base + tid - 1;
-      const uint32_t row = (uint32_t)buf[ci].hi;
+    if (mine && chain > 0) {
+      const uint32_t ci = chain - 1;
       uint64_t hi = ~0ull, lo = ~0ull;
-      if (row != kInvalidRow) {
+      if (has_row) {
         const double d = exact_finish<METRIC>(s0, s1, s_mag_a);
         const bool drop = (p.threshold == p.threshold) && (d > p.threshold);  // :127
         if (!drop) {
@@ -639,9 +660,15 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
     }
     __syncthreads();
   }
+  if (tid == 0) {
+    mbar_inval(smem_u32(&s_bar[0]));
+    mbar_inval(smem_u32(&s_bar[1]));
+  }
   TSC_TRACE(p.diag, 3);
 
   // ---- 3. final order -------------------------------------------------------------------
+  // up to 32: bitonic network in registers of warp 0; up to 1024: rank by counting, out of
+  // place through the (now free) row stage; beyond (range pass): bitonic sort in place
   uint32_t n2 = 2;
   while (n2 < ncand) n2 <<= 1;
   if (n2 > sort_cap) n2 = sort_cap;
@@ -650,7 +677,24 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
     buf[i].lo = ~0ull;
   }
   __syncthreads();
-  bitonic_sort_pairs(buf, n2);
+  if (n2 > 32 && ncand <= 1024 &&
+      tail_fixed_bytes(sort_cap, p.qld) + (size_t)ncand * sizeof(Pair128) <= sm_bytes) {
+    Pair128 *sorted = reinterpret_cast<Pair128 *>(stage);
+    for (uint32_t i = tid; i < ncand; i += blockDim.x) {
+      const Pair128 a = buf[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < ncand; j++) {
+        const Pair128 o = buf[j];
+        rank += pair_gt(a, o) || (a.hi == o.hi && a.lo == o.lo && j < i);   // dropped ones tie
+      }
+      sorted[rank] = a;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < ncand; i += blockDim.x) buf[i] = sorted[i];
+    __syncthreads();
+  } else {
+    bitonic_sort_pairs(buf, n2);
+  }
   TSC_TRACE(p.diag, 4);
 
   // ---- 4. certificate (first pass) / verdict (range pass), by one thread ---------------------
