@@ -149,3 +149,53 @@ def test_tf32_path_parity_with_oracle(metric):
             oi, od = oracle.search(rows, Qp[q], metric, k)
             assert cnt[q] == k and (ids[q] == oi).all(), (q, ids[q], oi)
             assert (bits(dist[q]) == bits(od)).all()
+
+
+# ---- k above the kernel's list capacity (K' > 32): truncated lists + certificate ---------------
+
+@pytest.mark.parametrize("dt,metric", [(1, 2), (2, 1), (0, 0)])
+def test_gemm_path_large_k(dt, metric):
+    """A k=100 batch stays on the tensor cores: every (CTA, column half) list keeps its 32 best
+    rows, the tail re-ranks the K' = k + 64 best of their union and the certificate bounds what
+    the truncated lists may have dropped. ids / distances equal the oracle."""
+    import tostore_b200 as T
+    n, dims, nq, k = 60000, 128, 40, 100
+    rows = onp.round_dev(oracle.synth_rows(71, 0, n, dims), dt)
+    Q = oracle.synth_rows(72, 0, nq, dims)
+    Qp = np.stack([onp.normalize_f32(q) if metric == 2 else q for q in Q])
+    with T.GpuVectorIndex(dims, metric, capacity_rows=n, dev_dtype=dt, k_max=128, nq_max=64) as ix:
+        ix.append_synthetic(71, n)
+        ix.stats_reset()
+        ids, dist, cnt = ix.search(Qp, k)
+        st = ix.stats()
+        assert st.last_path == 2 and st.uncertified_queries == 0
+        for q in range(0, nq, 5):
+            oi, od = oracle.search(rows, Qp[q], metric, k)
+            assert cnt[q] == k and (ids[q] == oi).all(), (q, ids[q][:8], oi[:8])
+            assert (bits(dist[q]) == bits(od)).all()
+
+
+def test_gemm_path_large_k_clustered_rows_take_the_range_pass():
+    """Adversarial layout for truncated lists: the 100 nearest rows of query 0 are CONSECUTIVE
+    rows, so one list would have to hold all of them and drops most. The certificate must notice
+    (the full list's largest key is below the K'-th candidate) and the range pass must repair
+    the result."""
+    import tostore_b200 as T
+    n, dims, nq, k = 40000, 128, 16, 100
+    rng = np.random.default_rng(5)
+    rows = oracle.synth_rows(73, 0, n, dims).copy()
+    Q = oracle.synth_rows(74, 0, nq, dims).copy()
+    start = 12345
+    rows[start:start + 120] = Q[0][None, :] + 0.01 * rng.standard_normal((120, dims)).astype(np.float32)
+    rows16 = onp.round_dev(rows, 1)
+    with T.GpuVectorIndex(dims, 0, capacity_rows=n, dev_dtype=1, k_max=128, nq_max=16) as ix:
+        ix.append_rows(rows)
+        ix.stats_reset()
+        ids, dist, cnt = ix.search(Q, k)
+        st = ix.stats()
+        assert st.last_path == 2
+        assert st.retried_queries >= 1 and st.uncertified_queries == 0
+        for q in (0, 1, 7):
+            oi, od = oracle.search(rows16, Q[q], 0, k)
+            assert cnt[q] == k and (ids[q] == oi).all(), (q, ids[q][:8], oi[:8])
+            assert (bits(dist[q]) == bits(od)).all()

@@ -9,6 +9,11 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np  # noqa: E402
 
+if "--diag" in sys.argv:   # tools only: the diagnostics build honours the TSC_SCAN_* / TSC_GEMM_* switches
+    sys.argv.remove("--diag")
+    from tostore_b200 import _native  # noqa: E402
+    _native.LIB_PATH = os.path.join(os.path.dirname(_native.LIB_PATH), "libtostore_cuda_diag.so")
+
 PEAKS = {"hbm_gbs": 6545.6, "bf16_tflops": 1622.2, "bf16_tflops_sustained": 1365.6}
 try:
     PEAKS.update(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json"))))

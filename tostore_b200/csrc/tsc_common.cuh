@@ -15,6 +15,8 @@ namespace tsc {
 constexpr int kWarp = 32;
 constexpr uint32_t kInvalidRow = 0xFFFFFFFFu;
 constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;  // sorts after every real key
+constexpr uint32_t kMaxRerank = 512;         // candidates the first pass of the tail re-ranks, at most
+constexpr int kGemmMaxKp = 32;               // entries per candidate list of the tensor path, at most
 
 // metric / dtype codes: include/tostore_cuda.h
 enum : int { kL2 = 0, kIP = 1, kCos = 2 };

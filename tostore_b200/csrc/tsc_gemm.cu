@@ -66,7 +66,9 @@ static int32_t cached_map(Index::TmapSlot *slot, int dtype, const void *ptr, uin
 bool gemm_supported(const Index *ix, uint32_t kprime) {
   // 16-bit columns: kind::f16 on a storage-type copy of the queries; fp32 columns: kind::tf32
   // on the fp32 queries as they are
-  return kprime <= (uint32_t)kGemmMaxKp && ix->d_norm2 != nullptr && !ix->host_only;
+  // K' beyond the kernel's list capacity: the lists are truncated to kGemmMaxKp entries and the
+  // tail's certificate accounts for what they dropped (tsc_tail.cuh, trunc_len)
+  return kprime <= kMaxRerank && ix->d_norm2 != nullptr && !ix->host_only;
 }
 
 int32_t gemm_update_norms(Index *ix, uint64_t first_row, uint64_t n, cudaStream_t st) {

@@ -30,6 +30,7 @@ void set_error(const char *fmt, ...);
 struct ScanConfig {
   int grid = 0;        // CTAs (multiple of the SM count)
   int warps = 8;       // warps per CTA
+  int sparse_warps = 16;   // ... of the sparse scan (K6): latency-bound per warp, wants more of them
   int rows = 0;        // R rows per stage (0 = auto)
   int stages = 0;      // S (0 = auto)
   int stage_target = 6144;  // bytes per stage aimed for when R is auto
@@ -281,6 +282,7 @@ int32_t grp_search_flags(Group &g, uint32_t nq, uint32_t *out_flags);
 struct SearchCtx {
   const float *d_q = nullptr;    // [nq, qld] fp32, padded
   uint32_t nq = 0, k = 0, kprime = 0;
+  uint32_t gemm_list_kp = 0;     // tensor path: entries per candidate list (<= kprime)
   double threshold = 0;
   int64_t *loc_ids = nullptr;
   double *loc_dist = nullptr;

@@ -208,8 +208,11 @@ static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, 
       if (p2p) need_exchange = false;
       ends_on_timer = !ix->hot_slot_open;
     } else {
+      uint32_t list_kp = c.kprime;
       if (use_gemm) {
-        rc = launch_gemm(ix, d_q, nq, c.kprime, ix->d_cand, &lists, nullptr, st);
+        if (list_kp > (uint32_t)kGemmMaxKp) list_kp = (uint32_t)kGemmMaxKp;
+        c.gemm_list_kp = list_kp;
+        rc = launch_gemm(ix, d_q, nq, list_kp, ix->d_cand, &lists, nullptr, st);
         if (rc != TSC_OK) return rc;
       } else {
         for (uint32_t q0 = 0; q0 < nq;) {
@@ -221,7 +224,7 @@ static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, 
           q0 += n;
         }
       }
-      rc = launch_tail(ix, c, lists * c.kprime, use_gemm);
+      rc = launch_tail(ix, c, lists * list_kp, use_gemm);
       if (rc != TSC_OK) return rc;
       uint32_t n_retry = (nq + kRangeSlots - 1) / kRangeSlots;
       if (n_retry > kRetryLaunches) n_retry = kRetryLaunches;

@@ -66,6 +66,9 @@ void fill_tail(const Index *ix, const SearchCtx &c, uint32_t m, bool gemm_keys, 
   t->cand = ix->d_cand;
   t->m = m;
   t->list_len = gemm_keys ? 0 : c.kprime;   // scan lists are sorted ascending, K' entries each
+  // tensor-path lists hold at most kGemmMaxKp entries: shorter than K' means rows were dropped
+  // per list, which the certificate has to account for
+  t->trunc_len = (gemm_keys && c.gemm_list_kp < c.kprime) ? c.gemm_list_kp : 0;
   t->kprime = c.kprime;
   t->k = c.k;
   t->rows = ix->d_rows;

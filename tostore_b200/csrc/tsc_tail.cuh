@@ -40,7 +40,6 @@ namespace tsc {
 
 constexpr uint32_t kSelectSortMax = 1024;  // M up to this is simply sorted
 constexpr uint32_t kHeadSelectCap = 1024;  // composites the head-pivot filter may let through
-constexpr uint32_t kMaxRerank = 512;
 constexpr int kRadixBins = 2048;           // 11-bit digits
 constexpr uint32_t kRangeCap = 4096;       // rows the range pass can hold per query
 constexpr uint32_t kRangeSlots = 8;        // queries per range pass (= the scan kernel's QB max)
@@ -179,6 +178,8 @@ struct TailParams {
   const uint64_t *cand;     // [nq][m] composites (ordered key << 32 | shard row), first pass
   uint32_t m;               // candidates per query
   uint32_t list_len;        // > 0: cand[q] is m / list_len lists, each sorted ascending (scan)
+  uint32_t trunc_len;       // > 0: cand[q] is m / trunc_len unsorted lists that each kept only
+                            // their trunc_len < K' best rows (tensor path, large k)
   uint32_t kprime;          // candidates re-ranked by the first pass (<= kMaxRerank)
   uint32_t k;               // results per query
   const uint8_t *rows;      // shard rows, device storage dtype
@@ -508,6 +509,32 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
     all_in = (uint32_t)(pivot >> 32) == kEmptyKey;
   }
   __syncthreads();
+  // Truncated lists (tensor path, K' above the kernel's list capacity): a row outside the
+  // union of the lists was displaced by trunc_len better rows of ITS list, so its key is >= the
+  // largest key of that (full) list. The certificate's "no candidate below this" bound is the
+  // smaller of the K'-th smallest composite and every full list's largest key.
+  if (mode == 0 && p.trunc_len != 0) {
+    if (tid == 0) s_bucket = kEmptyKey;
+    __syncthreads();
+    const uint32_t nl = p.m / p.trunc_len;
+    for (uint32_t l = tid; l < nl; l += blockDim.x) {
+      uint32_t mx = 0;
+      bool full = true;
+      for (uint32_t j = 0; j < p.trunc_len; j++) {
+        const uint64_t v = __ldcg(cand + (size_t)l * p.trunc_len + j);
+        if ((uint32_t)v == kInvalidRow) full = false;
+        else if ((uint32_t)(v >> 32) > mx) mx = (uint32_t)(v >> 32);
+      }
+      if (full) atomicMin(&s_bucket, mx);
+    }
+    __syncthreads();
+    const uint32_t excl = s_bucket;
+    if (excl != kEmptyKey) {
+      all_in = false;
+      if ((uint32_t)(pivot >> 32) > excl) pivot = (uint64_t)excl << 32;
+    }
+    __syncthreads();
+  }
   TSC_TRACE(p.diag, 2);
 
   // ---- 2. exact fp64 re-rank -------------------------------------------------------------

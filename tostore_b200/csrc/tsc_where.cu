@@ -232,7 +232,7 @@ int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, cons
   if (ix->rows) {
     TSC_CUDA(cudaMemsetAsync(ix->d_live_count, 0, 8, st));
     const uint64_t words = (ix->rows + 31) / 32;
-    const uint64_t want = (words + 7) / 8;    // 8 warps per CTA
+    const uint64_t want = (words + 8 * kWhereWords - 1) / (8 * kWhereWords);   // 8 warps per CTA
     const unsigned blocks = (unsigned)(want < (uint64_t)ix->sm_count * 8 ? want : ix->sm_count * 8);
     where_eval_kernel<<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, ix->rows, n_slots,
                                               ix->d_filter, ix->d_live_count);

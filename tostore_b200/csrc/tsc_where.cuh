@@ -55,101 +55,154 @@ __host__ __device__ __forceinline__ uint64_t where_key_i64(int64_t v) {
 }
 // Dart double.compareTo order; every NaN is the same (largest) key
 __host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
-  if ((b & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) return 0xFFFFFFFFFFFFFFFFull;
-  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  const uint64_t k = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  return (b & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull ? 0xFFFFFFFFFFFFFFFFull : k;
 }
 
-// One row of the program. `load(slot, key, isnull)` fetches the row's value of a column
-// as an order-preserving key; shared by the kernel and by the host self-test
-// (tsc_selftest_where), so the CPU test-suite exercises the same evaluation code.
-template <class Load>
-__host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog,
-                                                        const uint64_t *args, Load load) {
-  uint64_t stack = 0;
+// U rows of the program side by side. `load(slot, key[U], isnull[U])` fetches the U rows' values
+// of a column as order-preserving keys. The program is walked ONCE for all U rows, so the U loads
+// a leaf needs are independent of each other and in flight together (on the device: U
+// coalesced 256-byte warp loads per leaf instead of one). Shared by the kernel (U = 4) and by
+// the host self-test (tsc_selftest_where, U = 1), so the CPU test-suite exercises the same
+// evaluation code.
+template <int U, class Load>
+__host__ __device__ __forceinline__ void where_eval_rows(const WhereProgram &prog,
+                                                         const uint64_t *args, Load load,
+                                                         bool (&out)[U]) {
+  uint64_t stack[U], key[U];
+  bool isnull[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    stack[u] = 0;
+    key[u] = 0;
+    isnull[u] = true;
+  }
   uint32_t last_col = 0xFFFFFFFFu;
-  uint64_t key = 0;
-  bool isnull = true;
   for (uint32_t i = 0; i < prog.n_ops; i++) {
     const WhereDevOp &op = prog.ops[i];
-    bool r;
     if (op.kind == kWLeaf) {
       if (op.op < kOpTrue && op.col != last_col) {
         last_col = op.col;
         load(op.col, key, isnull);
       }
+      // Every comparison is a range test in key space: r = NULL ? on_null : (lo <= key <= hi) ^ neg.
+      // The operator is decoded ONCE per leaf (uniform over the warp) and the per-row work is two
+      // 64-bit compares; IN / NOT IN walk their list. (A per-row switch over the operators was
+      // if-converted by the compiler into ~80 instructions per row and leaf: the kernel was
+      // issue-bound at 21 % of HBM, profiles/r02_where_*.)
+      uint64_t lo = op.lo, hi = op.lo;
+      bool neg = false, on_null = false, list = false;
       switch (op.op) {
-        case kOpEq: r = !isnull && key == op.lo; break;
-        case kOpNe: r = isnull || key != op.lo; break;
-        case kOpGt: r = !isnull && key > op.lo; break;
-        case kOpGe: r = !isnull && key >= op.lo; break;
-        case kOpLt: r = !isnull && key < op.lo; break;
-        case kOpLe: r = !isnull && key <= op.lo; break;
-        case kOpBetween: r = !isnull && key >= op.lo && key <= op.hi; break;
-        case kOpIn:
-        case kOpNotIn: {
-          bool any = false;
-          for (uint32_t j = 0; j < op.n; j++) any |= (key == args[op.args_off + j]);
-          r = op.op == kOpIn ? (!isnull && any) : (isnull || !any);
-          break;
-        }
-        case kOpIsNull: r = isnull; break;
-        case kOpIsNotNull: r = !isnull; break;
-        case kOpTrue: r = true; break;
-        default: r = false; break;
+        case kOpEq: break;
+        case kOpNe: neg = true; on_null = true; break;
+        case kOpGt: hi = ~0ull; if (lo == ~0ull) { lo = 1; hi = 0; } else lo = lo + 1; break;
+        case kOpGe: hi = ~0ull; break;
+        case kOpLt: if (hi == 0) { lo = 1; hi = 0; } else { hi = hi - 1; lo = 0; } break;
+        case kOpLe: lo = 0; break;
+        case kOpBetween: hi = op.hi; break;
+        case kOpIn: list = true; break;
+        case kOpNotIn: list = true; neg = true; on_null = true; break;
+        case kOpIsNull: lo = 1; hi = 0; on_null = true; break;
+        case kOpIsNotNull: lo = 0; hi = ~0ull; break;
+        case kOpTrue: lo = 0; hi = ~0ull; on_null = true; break;
+        default: lo = 1; hi = 0; break;
       }
-      stack = (stack << 1) | (r ? 1ull : 0ull);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint64_t k = key[u];
+        bool in;
+        if (list) {
+          in = false;
+          for (uint32_t j = 0; j < op.n; j++) in |= (k == args[op.args_off + j]);
+        } else {
+          in = k >= lo && k <= hi;
+        }
+        const bool r = isnull[u] ? on_null : (in != neg);
+        stack[u] = (stack[u] << 1) | (r ? 1ull : 0ull);
+      }
     } else {
       // n-ary AND / OR over the top n stack bits (n <= 63, checked on the host)
       const uint32_t n = op.n;
       const uint64_t m = (1ull << n) - 1ull;
-      const uint64_t top = stack & m;
-      r = (n == 0) ? true : (op.kind == kWAnd ? top == m : top != 0);
-      stack = ((stack >> n) << 1) | (r ? 1ull : 0ull);
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const uint64_t top = stack[u] & m;
+        const bool r = (n == 0) ? true : (op.kind == kWAnd ? top == m : top != 0);
+        stack[u] = ((stack[u] >> n) << 1) | (r ? 1ull : 0ull);
+      }
     }
   }
-  return prog.n_ops == 0 || (stack & 1ull);
+#pragma unroll
+  for (int u = 0; u < U; u++) out[u] = prog.n_ops == 0 || (stack[u] & 1ull);
 }
 
-// One thread per row, one warp per 32-row bitmap word (ballot), grid-stride over words.
-// HBM traffic: 8 bytes per row per leaf (coalesced 256-byte warp loads) + 4 bytes per 32
-// rows written; a leaf on the column the previous leaf used re-uses the loaded value.
+// one row: `load(slot, key, isnull)`
+template <class Load>
+__host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog,
+                                                        const uint64_t *args, Load load) {
+  bool out[1];
+  where_eval_rows<1>(prog, args,
+                     [&](uint32_t c, uint64_t (&key)[1], bool (&isnull)[1]) {
+                       load(c, key[0], isnull[0]);
+                     },
+                     out);
+  return out[0];
+}
+
+// One thread per row and bitmap word, kWhereWords consecutive words (128 rows) per warp and
+// step: every leaf on a new column is kWhereWords independent coalesced 256-byte warp loads.
+// (One word per step left a warp with 256 bytes in flight: 24 % of HBM, ncu in
+// profiles/r02_first_call.log; L2 prefetching two steps ahead did not help.)
+// HBM traffic: 8 bytes per row per distinct column + 4 bytes per 32 rows written.
+constexpr int kWhereWords = 4;
 __global__ void __launch_bounds__(256)
 where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_constant__ WhereCols cols,
                   const uint64_t *__restrict__ args, uint64_t n_rows, uint32_t n_slots,
                   uint32_t *__restrict__ out_bits, unsigned long long *__restrict__ matched) {
+  (void)n_slots;
   const int lane = threadIdx.x & 31;
   const uint64_t n_words = (n_rows + 31) / 32;
+  const uint64_t n_groups = (n_words + kWhereWords - 1) / kWhereWords;
   const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long local = 0;
-  // The evaluator loads a column when the program first needs it, one dependent load after
-  // the other: a warp had ~256 bytes in flight and the kernel ran at 24 % of HBM (ncu,
-  // profiles/r02_first_call.log). Every column's lines of the words two iterations ahead are
-  // therefore pulled into L2 first (two 128-byte lines per column and word).
-  auto prefetch = [&](uint64_t w) {
-    if (w < n_words && (lane & 15) == 0) {
-      const uint64_t row = w * 32 + (uint64_t)lane;
-      for (uint32_t c = 0; c < n_slots; c++)
-        if (row < n_rows) asm volatile("prefetch.global.L2 [%0];" ::"l"(cols.values[c] + row));
-    }
-  };
-  const uint64_t w0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  prefetch(w0);
-  prefetch(w0 + warps);
-  for (uint64_t w = w0; w < n_words; w += warps) {
-    prefetch(w + 2 * warps);
-    const uint64_t row = w * 32 + lane;
-    bool res = false;
-    if (row < n_rows) {
-      res = where_eval_row(prog, args, [&](uint32_t c, uint64_t &key, bool &isnull) {
-        const uint64_t raw = __ldg(cols.values[c] + row);
-        key = cols.is_f64[c] ? where_key_f64_bits(raw) : (raw ^ 0x8000000000000000ull);
-        isnull = (__ldg(cols.nulls[c] + (row >> 5)) >> (row & 31)) & 1u;
-      });
-    }
-    const unsigned bits = __ballot_sync(0xFFFFFFFFu, res);
-    if (lane == 0) {
-      out_bits[w] = bits;
-      local += __popc(bits);
+  for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups;
+       g += warps) {
+    const uint64_t row0 = g * kWhereWords * 32 + lane;
+    bool res[kWhereWords];
+    where_eval_rows<kWhereWords>(
+        prog, args,
+        [&](uint32_t c, uint64_t (&key)[kWhereWords], bool (&isnull)[kWhereWords]) {
+          // all loads first, no branch between them (rows past the end re-read the last row:
+          // their result is masked below), then the conversions
+          uint64_t raw[kWhereWords];
+          uint32_t nb[kWhereWords];
+          const uint64_t *vals = cols.values[c];
+          const uint32_t *nulls = cols.nulls[c];
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) {
+            uint64_t row = row0 + (uint64_t)u * 32;
+            row = row < n_rows ? row : n_rows - 1;
+            raw[u] = __ldg(vals + row);
+            nb[u] = __ldg(nulls + (row >> 5)) >> (row & 31);
+          }
+          const bool f64 = cols.is_f64[c] != 0;
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) {
+            const uint64_t kf = where_key_f64_bits(raw[u]), ki = raw[u] ^ 0x8000000000000000ull;
+            key[u] = f64 ? kf : ki;
+            isnull[u] = nb[u] & 1u;
+          }
+        },
+        res);
+#pragma unroll
+    for (int u = 0; u < kWhereWords; u++) {
+      const uint64_t row = row0 + (uint64_t)u * 32;
+      const unsigned bits = __ballot_sync(0xFFFFFFFFu, res[u] && row < n_rows);
+      const uint64_t w = g * kWhereWords + u;
+      if (lane == 0 && w < n_words) {
+        out_bits[w] = bits;
+        local += __popc(bits);
+      }
     }
   }
   if (lane == 0 && local) atomicAdd(matched, local);
