@@ -56,6 +56,10 @@ def parse_args():
                     help="N>1: row-range shards of ONE corpus with a top-k exchange per query (default, "
                          "what BASELINE's north_star asks for) or N independent full replicas, each "
                          "serving its own queries (no exchange; the corpus fits one GPU)")
+    ap.add_argument("--diag-lib", action="store_true", help="tools only: load libtostore_cuda_diag.so")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="device loop without tsc_index_set_pipelining (every search then waits for the "
+                         "previous one's tail and carries timer events)")
     ap.add_argument("--exchange", default="p2p", choices=["nccl", "p2p"],
                     help="N>1: push over NVLink peer memory fused into the scan kernel (default) or "
                          "ncclAllGather + merge kernel")
@@ -207,6 +211,9 @@ def run_b200(args):
     import torch
 
     import oracle  # only for the cpu_baseline leg and the recall check (after the timed regions)
+    if args.diag_lib:   # tools only: experiments with the diagnostics build's switches
+        from tostore_b200 import _native
+        _native.LIB_PATH = os.path.join(os.path.dirname(_native.LIB_PATH), "libtostore_cuda_diag.so")
     from tostore_b200 import METRIC_L2, GpuVectorIndex
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,6 +273,11 @@ def run_b200(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing (`value`) -----------------------------------------
+    # Throughput mode of the public device API: the HBM pass of query i+1 overlaps the tail
+    # (selection, fp64 re-rank, certificate, shard exchange) of query i; all work of every
+    # query is still done and results are complete in stream order.
+    pipelined = not args.no_pipeline
+    ix.set_pipelining(pipelined)
     for i in range(warmup):
         step_device(i)
     sync_all()
@@ -292,6 +304,7 @@ def run_b200(args):
     hot_bytes = st.hot_bytes_total / max(st.hot_launches, 1)
     dev_ids = o_ids.cpu().numpy()
     dev_dist = o_dist.cpu().numpy()
+    ix.set_pipelining(False)
 
     # ---- end to end through the host-buffer plugin call (`e2e`) ----------------------
     # tsc_search with HOST buffers on every rank: H2D of the query, the kernels (for a
@@ -381,7 +394,10 @@ def run_b200(args):
                    "exchange": xname,
                    "l2_flush": "inputs larger than L2 (each pass streams the whole shard; "
                                f"{(hi - lo) * d * 4 / 1e9:.2f} GB per GPU vs 126 MB L2)",
-                   "queries": "distinct synthetic query per step"},
+                   "queries": "distinct synthetic query per step",
+                   "device_loop": ("pipelined (tsc_index_set_pipelining): the scan of query i+1 overlaps the "
+                                   "tail of query i; the hot-kernel timer samples every 16th search"
+                                   if pipelined else "one search after the other, every search timed")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "traffic_source": traffic_src,

@@ -267,6 +267,22 @@ int32_t tsc_search_device(uint64_t handle, const float *d_queries, uint32_t nq,
                           uint32_t k, double distance_threshold, int64_t *d_out_ids,
                           double *d_out_dist, uint32_t *d_out_counts,
                           void *cuda_stream);
+/* Throughput mode for back-to-back DEVICE-buffer searches of up to 8 queries on ONE stream.
+ * on != 0: the scan launch of search i+1 is made a programmatic dependent of search i's
+ * kernels, so its HBM pass overlaps search i's tail (selection, exact re-rank, certificate,
+ * shard exchange) and the launch gaps; it waits for search i to complete before it publishes
+ * anything, and results still become visible in stream order. Contract while it is on:
+ * (1) the query buffers of consecutive searches must not be produced by KERNELS enqueued
+ * between those searches on the same stream (memcpys and anything enqueued before the
+ * previous search are fine) — the overlapping launch reads its queries before the previous
+ * kernels are formally complete; (2) the stream of the previous search must still exist
+ * when a search is issued on another stream; (3) NO range pass runs in-stream: a query whose
+ * exactness certificate fails keeps its best-effort result, tsc_search_flags reports 1 for it
+ * and tsc_stats counts it under uncertified_queries — the caller re-issues such queries with
+ * pipelining off (a launch between two scans would keep them from overlapping). Only every
+ * 16th search carries the CUDA events of the hot-kernel timer (events would serialise the
+ * launches). Host-buffer searches are unaffected. Off by default. */
+int32_t tsc_index_set_pipelining(uint64_t handle, int32_t on);
 /* Host mirror of VectorIndexManager.vectorSearch's arithmetic around the engine
  * call (core/vector_index_manager.dart:514-520, :576-587): _toFloat32
  * (truncate / zero-pad `values[len]` to dims), _normalizeFloat32 for cosine,

@@ -33,6 +33,7 @@ MOCK = textwrap.dedent('''
         @staticmethod
         def comm_unique_id(): return b"x" * 128
         def search_device(self, *a, **k): FakeStats.kernel_launches += 2
+        def set_pipelining(self, on): pass
         def search(self, q, k): return (np.zeros((1, k), dtype=np.int64), np.zeros((1, k)), np.ones(1, dtype=np.uint32))
         def stats(self): return FakeStats
         def stats_reset(self): pass

@@ -94,6 +94,8 @@ CONFIGS = {
     "c2t": lambda: [measure("c2t batch-1024 L2 10M x 768 fp32 k=10 (tf32 tensor path)", 10_000_000, 768, 0, 0,
                             1024, 10, 5)],
     "c3": lambda: [measure("c3 batch-1024 cosine 10M x 768 bf16 k=10", 10_000_000, 768, 2, 1, 1024, 10, 10)],
+    "c3k": lambda: [measure("c3k batch-1024 cosine 10M x 768 bf16 k=100 (tensor path, truncated lists)", 10_000_000,
+                            768, 2, 1, 1024, 100, 5)],
     "c3s": lambda: [measure("c3s single-query cosine 10M x 768 bf16 k=10 (scan)", 10_000_000, 768, 2, 1, 1, 10, 20)],
     "c4": lambda: [measure("c4 shard: IP 12.5M x 1536 fp16 k=100 (1 of 8 GPUs)", 12_500_000, 1536, 1, 2, 1, 100, 20)],
     "c5": lambda: [measure("c5 shard: L2 12.5M x 384 fp32 k=10, 10% WHERE mask (1 of 4 GPUs)", 12_500_000, 384,

@@ -20,7 +20,7 @@ EXPORTS = (
     "tsc_index_append_rows", "tsc_index_append_pages", "tsc_index_append_synthetic",
     "tsc_index_set_deleted", "tsc_index_apply_graph_pages", "tsc_index_set_filter",
     "tsc_search", "tsc_search_submit", "tsc_search_poll", "tsc_search_wait", "tsc_search_flags",
-    "tsc_search_device", "tsc_vector_search", "tsc_vector_search_batch", "tsc_merge_shards",
+    "tsc_search_device", "tsc_index_set_pipelining", "tsc_vector_search", "tsc_vector_search_batch", "tsc_merge_shards",
     "tsc_selftest_query_prep", "tsc_selftest_distance_to_score",
     "tsc_comm_unique_id", "tsc_comm_init", "tsc_search_sharded",
     "tsc_comm_p2p_export", "tsc_comm_p2p_import",
@@ -115,6 +115,7 @@ def lib():
     L.tsc_search_poll.argtypes = [u64, C.POINTER(i32)]
     L.tsc_search_wait.argtypes = [u64]
     L.tsc_search_device.argtypes = [u64, vp, u32, u32, C.c_double, vp, vp, vp, vp]
+    L.tsc_index_set_pipelining.argtypes = [u64, i32]
     L.tsc_vector_search.argtypes = [u64, vp, u64, u32, C.c_double, vp, vp, vp, C.POINTER(u32)]
     L.tsc_vector_search_batch.argtypes = [u64, vp, u64, u32, u32, C.c_double, vp, vp, vp, vp]
     L.tsc_selftest_query_prep.argtypes = [u32, i32, vp, u64, vp]

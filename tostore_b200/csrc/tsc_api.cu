@@ -22,6 +22,7 @@ namespace tsc {
 
 // ---- error string -----------------------------------------------------------
 static thread_local char g_err[512] = "";
+const char *last_error_text() { return g_err; }
 void set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -199,6 +200,25 @@ static int32_t ensure_stage(Index *ix, size_t bytes) {
 
 int32_t ensure_stage_bytes(Index *ix, size_t bytes) { return ensure_stage(ix, bytes); }
 
+// The search scratch is one per index: a search on another stream waits for the previous one.
+// Pipelined searches record no event of their own; the mark is then taken here, on the stream
+// the previous search ran on (which must still exist).
+int32_t order_after_last_search(Index *ix, cudaStream_t st) {
+  if (!ix->scratch_used || ix->scratch_stream == st) return TSC_OK;
+  if (!ix->scratch_mark) {
+    TSC_CUDA(cudaEventRecord(ix->scratch_ev, ix->scratch_stream));
+    ix->scratch_mark = ix->scratch_ev;
+  }
+  TSC_CUDA(cudaStreamWaitEvent(st, ix->scratch_mark, 0));
+  return TSC_OK;
+}
+int32_t sync_last_search(Index *ix) {
+  if (!ix->scratch_used) return TSC_OK;
+  if (ix->scratch_mark) TSC_CUDA(cudaEventSynchronize(ix->scratch_mark));
+  else TSC_CUDA(cudaStreamSynchronize(ix->scratch_stream));
+  return TSC_OK;
+}
+
 int32_t refresh_live(Index *ix, cudaStream_t st) {
   if (!ix->live_dirty && ix->live_rows_for == ix->rows) return TSC_OK;
   if (ix->has_deleted || ix->has_filter) {
@@ -318,7 +338,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
   ok(dev_alloc(ix, &ix->d_retry_n, 1));
   ok(dev_alloc(ix, &ix->d_range_count, (size_t)kRangeSlots));
   ok(dev_alloc(ix, &ix->d_range_buf, (size_t)kRangeSlots * kRangeCap));
-  ok(dev_alloc(ix, &ix->d_done, 4));
+  ok(dev_alloc(ix, &ix->d_done, 8));
   ok(dev_alloc(ix, &ix->d_cert_stat, (size_t)kStatSlots));
   ok(dev_alloc(ix, &ix->d_loc_counts, (size_t)ix->nq_max));
 #ifdef TSC_DIAG
@@ -337,7 +357,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
     ok(cudaMemsetAsync(ix->d_flags, 0, (size_t)ix->nq_max * 4, ix->stream));
     ok(cudaMemsetAsync(ix->d_retry_n, 0, 4, ix->stream));
     ok(cudaMemsetAsync(ix->d_range_count, 0, kRangeSlots * 4, ix->stream));
-    ok(cudaMemsetAsync(ix->d_done, 0, 16, ix->stream));
+    ok(cudaMemsetAsync(ix->d_done, 0, 32, ix->stream));
     ok(cudaMemsetAsync(ix->d_cert_stat, 0, kStatSlots * 8, ix->stream));
     ok(cudaStreamSynchronize(ix->stream));
   }
@@ -668,9 +688,9 @@ int32_t ix_stats_get(Index *ix, tsc_stats *out) {
   if (ix->searches && ix->last_ms < 0) {
     TSC_CUDA(cudaSetDevice(ix->device));
     float ms = 0;
-    if (ix->search_beg && ix->scratch_mark) {
-      TSC_CUDA(cudaEventSynchronize(ix->scratch_mark));
-      TSC_CUDA(cudaEventElapsedTime(&ms, ix->search_beg, ix->scratch_mark));
+    if (ix->timed_beg && ix->timed_end) {
+      TSC_CUDA(cudaEventSynchronize(ix->timed_end));
+      TSC_CUDA(cudaEventElapsedTime(&ms, ix->timed_beg, ix->timed_end));
     }
     ix->last_ms = ms;
     ix->last_gbs = ms > 0 ? ix->last_gbs / (ms * 1e6) : 0;
@@ -881,6 +901,29 @@ int32_t tsc_stats_get(uint64_t handle, tsc_stats *out) {
     return TSC_ERR_BAD_ARG;
   }
   TSC_DISPATCH(handle, grp_stats_get(*g, out), ix_stats_get(ix, out))
+}
+
+// Pipelined device-buffer searches: see include/tostore_cuda.h
+static int32_t ix_set_pipelining(Index *ix, int32_t on) {
+  std::lock_guard<std::mutex> lk(ix->mu);
+  if (ix->host_only) {
+    set_error("set_pipelining: host-only self-test handle");
+    return TSC_ERR_UNSUPPORTED;
+  }
+  ix->pipeline = on != 0;
+  ix->timer_every = on != 0 ? 16 : 1;
+  ix->timer_tick = 0;
+  return TSC_OK;
+}
+static int32_t grp_set_pipelining(Group &g, int32_t on) {
+  for (auto &s : g.shards) {
+    int32_t rc = ix_set_pipelining(s.get(), on);
+    if (rc != TSC_OK) return rc;
+  }
+  return TSC_OK;
+}
+int32_t tsc_index_set_pipelining(uint64_t handle, int32_t on) {
+  TSC_DISPATCH(handle, grp_set_pipelining(*g, on), ix_set_pipelining(ix, on))
 }
 
 int32_t tsc_stats_reset(uint64_t handle) {

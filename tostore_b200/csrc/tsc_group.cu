@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <thread>
 
 #include "tsc_index.h"
 
@@ -38,6 +40,75 @@ static int32_t for_shards(Group &g, uint64_t first, uint64_t n, Fn fn) {
     if (rc != TSC_OK) return rc;
   }
   return TSC_OK;
+}
+
+// ---- shard workers ---------------------------------------------------------------------
+struct GroupWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  Index *ix = nullptr;
+  enum Job { kNone, kBegin, kEnd, kQuit } job = kNone;
+  bool done = true;
+  // arguments / results of the job
+  const float *queries = nullptr;
+  uint32_t nq = 0, k = 0;
+  double threshold = 0;
+  int32_t rc = TSC_OK;
+  std::string err;
+
+  void run() {
+    cudaSetDevice(ix->device);
+    std::unique_lock<std::mutex> lk(mu);
+    for (;;) {
+      cv.wait(lk, [&] { return job != kNone; });
+      if (job == kQuit) return;
+      const Job j = job;
+      lk.unlock();
+      int32_t r = TSC_OK;
+      if (j == kBegin) {
+        ix->last_threshold = threshold;
+        r = ix_search_begin(ix, queries, nq, k, threshold);
+      } else {
+        r = ix_search_end(ix, nq, k, nullptr, nullptr, nullptr);
+      }
+      lk.lock();
+      rc = r;
+      if (r != TSC_OK) err = last_error_text();
+      job = kNone;
+      done = true;
+      cv.notify_all();
+    }
+  }
+  void post(Job j) {
+    std::lock_guard<std::mutex> lk(mu);
+    job = j;
+    done = false;
+    cv.notify_all();
+  }
+  int32_t wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done; });
+    if (rc != TSC_OK) set_error("%s", err.c_str());
+    return rc;
+  }
+};
+
+static void start_workers(Group &g) {
+  for (size_t s = 1; s < g.shards.size(); s++) {
+    std::unique_ptr<GroupWorker> w(new GroupWorker);
+    w->ix = g.shards[s].get();
+    GroupWorker *raw = w.get();
+    w->th = std::thread([raw] { raw->run(); });
+    g.workers.push_back(std::move(w));
+  }
+}
+
+Group::~Group() {
+  for (auto &w : workers) {
+    w->post(GroupWorker::kQuit);
+    if (w->th.joinable()) w->th.join();
+  }
 }
 
 int32_t grp_create(const tsc_index_desc *d, uint64_t *out_handle) {
@@ -99,6 +170,7 @@ int32_t grp_create(const tsc_index_desc *d, uint64_t *out_handle) {
     for (uint32_t r = 0; r < n; r++) ix->x_peer[r] = g->shards[r]->d_xbuf;
     ix->p2p_ready = true;
   }
+  start_workers(*g);
   *out_handle = register_group(g);
   return TSC_OK;
 }
@@ -325,8 +397,8 @@ int32_t grp_stats_reset(Group &g) {
   return TSC_OK;
 }
 
-// One search over all shards. The shards that only push (1..n-1) are launched first, the
-// root (shard 0: it waits for everybody's pairs and merges) last.
+// One search over all shards: the workers enqueue shards 1..n-1 (they only push their top-k),
+// the calling thread enqueues the root (shard 0: it waits for everybody's pairs and merges).
 int32_t grp_search_begin(Group &g, const float *queries, uint32_t nq, uint32_t k,
                          double threshold) {
   Index *root = g.shards[0].get();
@@ -338,11 +410,20 @@ int32_t grp_search_begin(Group &g, const float *queries, uint32_t nq, uint32_t k
     set_error("search: k=%u outside [1, k_max=%u]", k, root->k_max);
     return TSC_ERR_BAD_ARG;
   }
-  for (size_t i = g.shards.size(); i-- > 0;) {
-    g.shards[i]->last_threshold = threshold;
-    int32_t rc = ix_search_begin(g.shards[i].get(), queries, nq, k, threshold);
-    if (rc != TSC_OK) return rc;   // the exchange of this epoch will time out on the others
+  for (auto &w : g.workers) {
+    w->queries = queries;
+    w->nq = nq;
+    w->k = k;
+    w->threshold = threshold;
+    w->post(GroupWorker::kBegin);
   }
+  root->last_threshold = threshold;
+  int32_t rc = ix_search_begin(root, queries, nq, k, threshold);
+  for (auto &w : g.workers) {
+    const int32_t r2 = w->wait();   // a failed shard: the exchange of this epoch times out on the others
+    if (rc == TSC_OK) rc = r2;
+  }
+  if (rc != TSC_OK) return rc;
   g.search_pending = true;
   g.pend_nq = nq;
   g.pend_k = k;
@@ -355,9 +436,14 @@ int32_t grp_search_end(Group &g, int64_t *out_ids, double *out_dist, uint32_t *o
     return TSC_ERR_BAD_ARG;
   }
   g.search_pending = false;
+  for (auto &w : g.workers) {
+    w->nq = g.pend_nq;
+    w->k = g.pend_k;
+    w->post(GroupWorker::kEnd);
+  }
   int32_t rc = ix_search_end(g.shards[0].get(), g.pend_nq, g.pend_k, out_ids, out_dist, out_counts);
-  for (size_t i = 1; i < g.shards.size(); i++) {
-    int32_t r2 = ix_search_end(g.shards[i].get(), g.pend_nq, g.pend_k, nullptr, nullptr, nullptr);
+  for (auto &w : g.workers) {
+    const int32_t r2 = w->wait();
     if (rc == TSC_OK) rc = r2;
   }
   return rc;
@@ -378,7 +464,10 @@ int32_t grp_search_flags(Group &g, uint32_t nq, uint32_t *out_flags) {
   for (auto &s : g.shards) {
     Index *ix = s.get();
     TSC_CUDA(cudaSetDevice(ix->device));
-    if (ix->scratch_used) TSC_CUDA(cudaEventSynchronize(ix->scratch_mark));
+    {
+      int32_t src = sync_last_search(ix);
+      if (src != TSC_OK) return src;
+    }
     TSC_CUDA(cudaMemcpy(f.data(), ix->d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost));
     for (uint32_t q = 0; q < nq; q++)
       if (f[q] > out_flags[q]) out_flags[q] = f[q];

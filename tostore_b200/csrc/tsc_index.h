@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tostore_cuda.h"
@@ -101,7 +102,8 @@ struct Index {
   uint32_t *d_retry_n = nullptr;   // zero between searches
   uint32_t *d_range_count = nullptr; // [kRangeSlots], zero between launches
   uint64_t *d_range_buf = nullptr; // [kRangeSlots][kRangeCap]
-  uint32_t *d_done = nullptr;      // [4] last-CTA tickets (scan, exchange), scan work counter; zero between launches
+  uint32_t *d_done = nullptr;      // [8] zero between launches: [0] scan ticket, [1] exchange ticket, [2] scan work counter,
+                                   // [3] / [4] work counter / ticket of the range launches (they may overlap the next scan)
   unsigned long long *d_cert_stat = nullptr;  // [kStatSlots]
   unsigned long long *d_trace = nullptr;      // diagnostics build: phase timestamps (tsc_tail.cuh)
   uint32_t *d_loc_counts = nullptr;  // [nq_max] shard-local result counts of a sharded search
@@ -112,8 +114,16 @@ struct Index {
   double last_threshold = 0;         // of the host-buffer search in flight (owed range passes)
   // one search at a time uses the scratch above: searches on other streams wait for this
   cudaEvent_t scratch_ev = nullptr;    // recorded at the end of a search unless a timer event already is
+  // Pipelined device searches (tsc_index_set_pipelining): the scan launch of search i+1 is a
+  // programmatic dependent of search i's range launch and overlaps search i's tail; stream
+  // events would serialise the two, so only every timer_every-th search is timed and the
+  // end-of-search mark is recorded lazily (scratch_mark == nullptr: not recorded yet).
+  bool pipeline = false;
+  uint32_t timer_every = 1, timer_tick = 0;
+  bool search_timed = true;            // the search being enqueued carries the timer events
   cudaEvent_t scratch_mark = nullptr;  // the event that marks the end of the last search (not owned)
-  cudaEvent_t search_beg = nullptr;    // first timer event of the last search (not owned)
+  cudaEvent_t search_beg = nullptr;    // first timer event of the search being enqueued (not owned)
+  cudaEvent_t timed_beg = nullptr, timed_end = nullptr;   // event pair of the last TIMED search (not owned)
   cudaEvent_t last_hot_end = nullptr;  // most recent hot_timer_end event (not owned)
   cudaStream_t scratch_stream = nullptr;
   bool scratch_used = false;
@@ -181,14 +191,24 @@ void free_index(Index *ix);               // deleter of IndexRef: releases the d
 IndexRef lookup_index(uint64_t handle);   // empty + error string when unknown (or a group)
 uint64_t register_index(IndexRef ix);
 int32_t ensure_stage_bytes(Index *ix, size_t bytes);
-int32_t refresh_live(Index *ix, cudaStream_t st);   // recombine deleted / filter -> live when stale
+int32_t refresh_live(Index *ix, cudaStream_t st);
+int32_t order_after_last_search(Index *ix, cudaStream_t st);   // st waits for the last search's scratch use
+int32_t sync_last_search(Index *ix);                           // host waits for it
+   // recombine deleted / filter -> live when stale
 int32_t launch_pad_queries(Index *ix, const float *d_queries, uint32_t nq, cudaStream_t st);
 
 // A group: one logical column row-range sharded over the GPUs of one process
 // (tsc_index_create with n_devices > 1). Shard s owns node ids
 // [first + s * per_shard, first + (s + 1) * per_shard) on device_ids[s]; shard 0 is the
 // root of the exchange: it merges the shards' exact top-k and the host reads from it.
+// One host thread per shard 1..n-1 of a group (shard 0 is driven by the calling thread): a
+// search's launches go out to all GPUs side by side instead of one device after the other
+// (8 shards: ~150 us of serial launch work per query otherwise).
+struct GroupWorker;
+const char *last_error_text();      // this thread's error string
 struct Group {
+  ~Group();
+  std::vector<std::unique_ptr<GroupWorker>> workers;   // [n_shards - 1]
   std::mutex mu;                    // serialises calls on the group handle
   tsc_index_desc desc{};            // as given: capacity / first_node_id of the whole column
   std::vector<IndexRef> shards;

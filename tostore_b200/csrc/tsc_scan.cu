@@ -115,9 +115,11 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
   p.fused_tail = (fused || mode == 1) ? 1 : 0;
   p.xchg_in_tail = xchg ? 1 : 0;
   p.last_retry = last_retry ? 1 : 0;
+  p.no_range = (mode == 0 && p.fused_tail && ix->pipeline) ? 1 : 0;
   p.nq_total = c.nq;
-  p.done_counter = ix->d_done;
-  p.work_counter = ix->d_done + 2;
+  // first passes and range launches keep separate tickets and work counters
+  p.done_counter = ix->d_done + (mode == 1 ? 4 : 0);
+  p.work_counter = ix->d_done + (mode == 1 ? 3 : 2);
   {
     // 7/8 of the stages round-robin (a whole number of rounds), the rest on demand
     const uint64_t total = (ix->rows + (uint64_t)pl.rows - 1) / (uint64_t)pl.rows;
@@ -128,6 +130,7 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
   }
   const uint32_t m = (uint32_t)ix->scan.grid * c.kprime;
   fill_tail(ix, c, m, false, &p.tail);
+  p.tail.defer_retry = p.no_range;
   p.tail_sort_cap = tail_sort_cap(m, c.kprime, p.tail.list_len, mode == 1);
   if (xchg) {
     fill_xchg(ix, &p.xchg);

@@ -48,6 +48,7 @@ struct ScanParams {
   int fused_tail;            // the last CTA runs the tail (always in mode 1)
   int xchg_in_tail;          // ... and the shard exchange
   int last_retry;            // mode 1: the last range launch of the search resets retry_n
+  int no_range;              // mode 0: no range launch follows this first pass (pipelined searches)
   uint32_t nq_total;         // queries of the whole search (exchange loop)
   uint32_t tail_sort_cap;    // Pair128 slots of the tail's sort buffer
   uint32_t smem_bytes;       // dynamic shared memory of this launch (the tail stages rows in it)
@@ -192,7 +193,10 @@ __device__ __forceinline__ uint32_t scan_queries(const ScanParams &p, uint32_t (
   uint32_t nq = p.nq;
   if (p.mode == 1) {
     // launched with programmatic stream serialization: the first pass (whose tail writes
-    // retry_n / range_thr) has to be complete and visible before anything is read
+    // retry_n / range_thr) has to be complete and visible before anything is read. Whatever
+    // follows this launch in the same way (the next search's first pass, pipelining) may be
+    // scheduled right away: it waits for THIS grid before it publishes anything.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t n_retry = __ldcg(p.tail.retry_n);
     if (n_retry <= p.q_base) {
@@ -218,6 +222,10 @@ __device__ __forceinline__ void scan_finish(const ScanParams &p, const uint32_t 
                                             int warps, int lane) {
   __shared__ uint32_t s_ticket;
   TSC_TRACE(p.tail.diag, kTraceCta + blockIdx.x);
+  // A pipelined first pass ran its main loop beside the previous search's tail / range launch;
+  // from here on it touches what they use (candidate lists, tickets, flags, results): wait for
+  // them to complete (returns at once for a launch without a programmatic dependency).
+  if (p.mode == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.mode == 0) scan_block_merge(p, qi, nq, sortbuf, lkeys, lids, p.kprime, warp, warps, lane);
   TSC_TRACE(p.tail.diag, kTraceCta + gridDim.x + blockIdx.x);
   __threadfence();

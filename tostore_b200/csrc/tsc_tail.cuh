@@ -199,6 +199,8 @@ struct TailParams {
   uint32_t *range_thr;      // [nq] ordered fp32 key T: the range pass collects key <= T
   uint32_t *retry_list;     // compacted indices of the queries that need the range pass
   uint32_t *retry_n;
+  int defer_retry;          // no range launch follows (pipelined searches): an uncertified query is
+                            // only flagged kFlagRetry; the caller re-issues it
   uint32_t *range_count;    // [kRangeSlots] rows collected per slot of the running range pass
   uint64_t *range_buf;      // [kRangeSlots][kRangeCap] composites
   unsigned long long *stat; // [kStatSlots] kStat*
@@ -774,9 +776,11 @@ __device__ __noinline__ void tail_query(const TailParams &p, uint32_t qi, int mo
       } else {
         flag = kFlagRetry;
         atomicAdd(p.stat + kStatRetryAsked, 1ull);
-        p.range_thr[qi] = thr_key;
-        const uint32_t s = atomicAdd(p.retry_n, 1u);
-        p.retry_list[s] = qi;
+        if (!p.defer_retry) {
+          p.range_thr[qi] = thr_key;
+          const uint32_t s = atomicAdd(p.retry_n, 1u);
+          p.retry_list[s] = qi;
+        }
       }
     } else {
       atomicAdd(p.stat + kStatCertified, 1ull);

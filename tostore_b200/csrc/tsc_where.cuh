@@ -65,11 +65,14 @@ __host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
 // coalesced 256-byte warp loads per leaf instead of one). Shared by the kernel (U = 4) and by
 // the host self-test (tsc_selftest_where, U = 1), so the CPU test-suite exercises the same
 // evaluation code.
-template <int U, class Load>
-__host__ __device__ __forceinline__ void where_eval_rows(const WhereProgram &prog,
-                                                         const uint64_t *args, Load load,
-                                                         bool (&out)[U]) {
-  uint64_t stack[U], key[U];
+// Stack = uint32_t for programs of up to 32 steps (the bit-stack cannot get deeper than the
+// program is long; 64-bit shifts cost two instructions each), uint64_t otherwise.
+template <int U, class Stack, class Load>
+__host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &prog,
+                                                           const uint64_t *args, Load load,
+                                                           bool (&out)[U]) {
+  Stack stack[U];
+  uint64_t key[U];
   bool isnull[U];
 #pragma unroll
   for (int u = 0; u < U; u++) {
@@ -118,22 +121,29 @@ __host__ __device__ __forceinline__ void where_eval_rows(const WhereProgram &pro
           in = k >= lo && k <= hi;
         }
         const bool r = isnull[u] ? on_null : (in != neg);
-        stack[u] = (stack[u] << 1) | (r ? 1ull : 0ull);
+        stack[u] = (Stack)(stack[u] << 1) | (Stack)(r ? 1 : 0);
       }
     } else {
       // n-ary AND / OR over the top n stack bits (n <= 63, checked on the host)
       const uint32_t n = op.n;
-      const uint64_t m = (1ull << n) - 1ull;
+      const Stack m = (Stack)(((Stack)1 << (n & (sizeof(Stack) * 8 - 1))) - 1);   // n < width: host-checked
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const uint64_t top = stack[u] & m;
+        const Stack top = stack[u] & m;
         const bool r = (n == 0) ? true : (op.kind == kWAnd ? top == m : top != 0);
-        stack[u] = ((stack[u] >> n) << 1) | (r ? 1ull : 0ull);
+        stack[u] = (Stack)(((stack[u] >> n) << 1) | (Stack)(r ? 1 : 0));
       }
     }
   }
 #pragma unroll
-  for (int u = 0; u < U; u++) out[u] = prog.n_ops == 0 || (stack[u] & 1ull);
+  for (int u = 0; u < U; u++) out[u] = prog.n_ops == 0 || (stack[u] & 1);
+}
+template <int U, class Load>
+__host__ __device__ __forceinline__ void where_eval_rows(const WhereProgram &prog,
+                                                         const uint64_t *args, Load load,
+                                                         bool (&out)[U]) {
+  if (prog.n_ops < 32) where_eval_rows_t<U, uint32_t>(prog, args, load, out);
+  else where_eval_rows_t<U, uint64_t>(prog, args, load, out);
 }
 
 // one row: `load(slot, key, isnull)`
@@ -185,13 +195,15 @@ where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_consta
             raw[u] = __ldg(vals + row);
             nb[u] = __ldg(nulls + (row >> 5)) >> (row & 31);
           }
-          const bool f64 = cols.is_f64[c] != 0;
+          if (cols.is_f64[c] != 0) {   // uniform
 #pragma unroll
-          for (int u = 0; u < kWhereWords; u++) {
-            const uint64_t kf = where_key_f64_bits(raw[u]), ki = raw[u] ^ 0x8000000000000000ull;
-            key[u] = f64 ? kf : ki;
-            isnull[u] = nb[u] & 1u;
+            for (int u = 0; u < kWhereWords; u++) key[u] = where_key_f64_bits(raw[u]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < kWhereWords; u++) key[u] = raw[u] ^ 0x8000000000000000ull;
           }
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) isnull[u] = nb[u] & 1u;
         },
         res);
 #pragma unroll

@@ -230,6 +230,13 @@ class GpuVectorIndex:
         N.check(fn(self.handle, d_queries, nq, k, thr, d_ids, d_dist, d_counts, stream or None),
                 "tsc_search_sharded" if sharded else "tsc_search_device")
 
+    def set_pipelining(self, on: bool) -> None:
+        """Throughput mode for back-to-back `search_device` calls on one stream: the HBM pass of
+        search i+1 overlaps the tail / exchange of search i (tsc_index_set_pipelining; see the
+        header for the contract on query buffers)."""
+        N.check(self._lib.tsc_index_set_pipelining(self.handle, 1 if on else 0),
+                "tsc_index_set_pipelining")
+
     def vector_search(self, values, k: int, threshold: Optional[float] = None):
         """fp64 query of any length -> (ids, dist, score) with the reference's
         query preparation and score mapping done inside the library."""
