@@ -91,7 +91,8 @@ typedef struct tsc_index_desc {
   uint8_t dev_dtype;       /* TSC_DEV_*                                          */
   uint8_t reserved0;
   int32_t device_id;       /* CUDA device ordinal that holds this shard          */
-  uint64_t capacity_rows;  /* rows reserved in HBM for this shard                */
+  uint64_t capacity_rows;  /* rows reserved in HBM for this shard; an UNSHARDED   */
+                           /* column grows beyond it on demand (append_rows, ...) */
   uint64_t first_node_id;  /* nodeId of shard row 0 (row-range sharding)         */
   uint32_t k_max;          /* largest topK that will be requested (<= 128)       */
   uint32_t nq_max;         /* largest query batch per call                       */
@@ -127,6 +128,11 @@ typedef struct tsc_stats {
   uint64_t range_rows;          /* rows the range passes re-ranked             */
   uint32_t n_devices;           /* 1, or the shard count of a group            */
   uint32_t reserved2;
+  /* tensor-core path (last_path == 2): algorithmic flops (2 * nq * rows * dims) of the last
+   * search over its device time, and that as a fraction of B200's nominal dense peak for the
+   * MMA kind used (kind::f16 2250 TFLOP/s, kind::tf32 1125); 0 on the scan path */
+  double last_tflops;
+  double last_tensor_util;
 } tsc_stats;
 
 /* ---- library ---- */

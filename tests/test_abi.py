@@ -33,7 +33,7 @@ def test_struct_layout_matches_header():
     from tostore_b200 import _native as N
     from tostore_b200 import where as W
     assert C.sizeof(N.IndexDesc) == 80          # 40 (v1) + n_devices 4 + device_ids 32 + reserved 4
-    assert C.sizeof(N.Stats) == 152 and N.Stats.certified_queries.offset == 112
+    assert C.sizeof(N.Stats) == 168 and N.Stats.certified_queries.offset == 112   # + last_tflops, last_tensor_util
     assert N.IndexDesc.capacity_rows.offset == 16 and N.IndexDesc.k_max.offset == 32
     assert C.sizeof(W.WhereOp) == 48 and W.WhereOp.i_lo.offset == 8 and W.WhereOp.args_offset.offset == 40
     assert C.sizeof(N.NghInfo) == 72 and N.NghInfo.next_node_id.offset == 24
@@ -55,7 +55,7 @@ def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
 #include <string.h>
 #include "tostore_cuda.h"
 _Static_assert(sizeof(tsc_index_desc) == 80, "tsc_index_desc");
-_Static_assert(sizeof(tsc_stats) == 152, "tsc_stats");
+_Static_assert(sizeof(tsc_stats) == 168, "tsc_stats");
 _Static_assert(sizeof(tsc_where_op) == 48, "tsc_where_op");
 _Static_assert(sizeof(tsc_ngh_info) == 72, "tsc_ngh_info");
 int main(void) {

@@ -68,6 +68,7 @@ class Stats(C.Structure):
         ("certified_queries", C.c_uint64), ("retried_queries", C.c_uint64),
         ("uncertified_queries", C.c_uint64), ("range_rows", C.c_uint64),
         ("n_devices", C.c_uint32), ("reserved2", C.c_uint32),
+        ("last_tflops", C.c_double), ("last_tensor_util", C.c_double),
     ]
 
 

@@ -14,6 +14,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda.h>
+
 #include "tsc_index.h"
 #include "tsc_ingest.cuh"
 #include "tsc_tail.cuh"
@@ -80,6 +82,130 @@ static cudaError_t dev_alloc(Index *ix, T **p, size_t n) {
   return e;
 }
 
+// ---- the row block: virtual memory management ------------------------------------------
+// (driver API through cudaGetDriverEntryPoint: the library links the runtime statically)
+struct VmmApi {
+  CUresult (*AddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *,
+                     unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+  CUresult (*GetGranularity)(size_t *, const CUmemAllocationProp *,
+                             CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+static VmmApi g_vmm;
+static std::mutex g_vmm_mu;
+static int32_t vmm_load() {
+  std::lock_guard<std::mutex> lk(g_vmm_mu);
+  if (g_vmm.ok) return TSC_OK;
+  auto get = [](const char *name, void **fn) {
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) {
+      set_error("driver entry point %s unavailable: %s", name, cudaGetErrorString(e));
+      cudaGetLastError();
+      return false;
+    }
+    return true;
+  };
+  if (!get("cuMemAddressReserve", (void **)&g_vmm.AddressReserve) ||
+      !get("cuMemAddressFree", (void **)&g_vmm.AddressFree) ||
+      !get("cuMemCreate", (void **)&g_vmm.Create) || !get("cuMemRelease", (void **)&g_vmm.Release) ||
+      !get("cuMemMap", (void **)&g_vmm.Map) || !get("cuMemUnmap", (void **)&g_vmm.Unmap) ||
+      !get("cuMemSetAccess", (void **)&g_vmm.SetAccess) ||
+      !get("cuMemGetAllocationGranularity", (void **)&g_vmm.GetGranularity))
+    return TSC_ERR_CUDA;
+  g_vmm.ok = true;
+  return TSC_OK;
+}
+static CUmemAllocationProp vmm_prop(int device) {
+  CUmemAllocationProp p{};
+  p.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  p.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  p.location.id = device;
+  return p;
+}
+// reserve the address range of the row block: as many rows as the device could ever hold
+static int32_t rows_reserve(Index *ix) {
+  int32_t rc = vmm_load();
+  if (rc != TSC_OK) return rc;
+  const CUmemAllocationProp prop = vmm_prop(ix->device);
+  size_t gran = 0;
+  if (g_vmm.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !gran) {
+    set_error("index_create: cuMemGetAllocationGranularity failed");
+    return TSC_ERR_CUDA;
+  }
+  size_t free_b = 0, total_b = 0;
+  TSC_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t want = total_b;
+  const size_t all_rows = (size_t)0xFFFFFFFEull * ix->row_bytes;
+  if (want > all_rows) want = all_rows;
+  const size_t first = (size_t)ix->capacity * ix->row_bytes;
+  if (want < first) want = first;
+  want = (want + gran - 1) / gran * gran;
+  CUdeviceptr va = 0;
+  if (g_vmm.AddressReserve(&va, want, 0, 0, 0) != CUDA_SUCCESS) {
+    set_error("index_create: cannot reserve %.1f GB of device address space", want / 1e9);
+    return TSC_ERR_OOM;
+  }
+  ix->rows_va = va;
+  ix->rows_va_bytes = want;
+  ix->vmm_gran = gran;
+  ix->d_rows = reinterpret_cast<uint8_t *>(va);
+  return TSC_OK;
+}
+// map physical memory so that bytes [0, need) of the row block are backed
+static int32_t rows_map_to(Index *ix, size_t need) {
+  if (need <= ix->rows_mapped) return TSC_OK;
+  if (need > ix->rows_va_bytes) {
+    set_error("the column would need %.1f GB: more than the device has", need / 1e9);
+    return TSC_ERR_OOM;
+  }
+  const size_t add = (need - ix->rows_mapped + ix->vmm_gran - 1) / ix->vmm_gran * ix->vmm_gran;
+  const CUmemAllocationProp prop = vmm_prop(ix->device);
+  CUmemGenericAllocationHandle h = 0;
+  if (g_vmm.Create(&h, add, &prop, 0) != CUDA_SUCCESS) {
+    set_error("out of device memory: %.2f GB more for the embedding column", add / 1e9);
+    return TSC_ERR_OOM;
+  }
+  if (g_vmm.Map(ix->rows_va + ix->rows_mapped, add, 0, h, 0) != CUDA_SUCCESS) {
+    g_vmm.Release(h);
+    set_error("cuMemMap failed for the embedding column");
+    return TSC_ERR_CUDA;
+  }
+  CUmemAccessDesc acc{};
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = ix->device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (g_vmm.SetAccess(ix->rows_va + ix->rows_mapped, add, &acc, 1) != CUDA_SUCCESS) {
+    g_vmm.Unmap(ix->rows_va + ix->rows_mapped, add);
+    g_vmm.Release(h);
+    set_error("cuMemSetAccess failed for the embedding column");
+    return TSC_ERR_CUDA;
+  }
+  ix->rows_chunks.emplace_back((unsigned long long)h, add);
+  ix->rows_mapped += add;
+  ix->device_bytes += add;
+  return TSC_OK;
+}
+static void rows_release(Index *ix) {
+  if (!ix->rows_va || !g_vmm.ok) return;
+  size_t off = 0;
+  for (auto &c : ix->rows_chunks) {
+    g_vmm.Unmap(ix->rows_va + off, c.second);
+    g_vmm.Release((CUmemGenericAllocationHandle)c.first);
+    off += c.second;
+  }
+  g_vmm.AddressFree(ix->rows_va, ix->rows_va_bytes);
+  ix->rows_chunks.clear();
+  ix->rows_va = 0;
+  ix->d_rows = nullptr;
+}
+
 void free_index(Index *ix) {
   if (ix->host_only) {
     delete ix;
@@ -87,7 +213,7 @@ void free_index(Index *ix) {
   }
   cudaSetDevice(ix->device);
   if (ix->stream) cudaStreamSynchronize(ix->stream);
-  cudaFree(ix->d_rows);
+  rows_release(ix);
   cudaFree(ix->d_deleted);
   cudaFree(ix->d_filter);
   cudaFree(ix->d_live);
@@ -314,7 +440,14 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
     ok(cudaEventCreate(&ix->t_beg[i]));
     ok(cudaEventCreate(&ix->t_end[i]));
   }
-  ok(dev_alloc(ix, &ix->d_rows, (size_t)ix->capacity * ix->row_bytes));
+  if (e == cudaSuccess) {
+    int32_t vrc = rows_reserve(ix);
+    if (vrc == TSC_OK) vrc = rows_map_to(ix, (size_t)ix->capacity * ix->row_bytes);
+    if (vrc != TSC_OK) {
+      free_index(ix);
+      return vrc;
+    }
+  }
   ok(dev_alloc(ix, &ix->d_deleted, ix->mask_words));
   ok(dev_alloc(ix, &ix->d_filter, ix->mask_words));
   ok(dev_alloc(ix, &ix->d_live, ix->mask_words));
@@ -392,6 +525,74 @@ int32_t ix_clear(Index *ix) {
   return TSC_OK;
 }
 
+// Grow the column of an unsharded handle so that it holds rows [0, rows_needed): more
+// physical memory behind the row block (no copy), the small per-row arrays (norms, bitmaps,
+// attribute columns) re-allocated and copied. The reference grows by adding partition files
+// (model/ngh_index_meta.dart:178-232); a shard's capacity is its node-id range and stays fixed.
+template <typename T>
+static int32_t regrow(Index *ix, T **p, size_t old_n, size_t new_n, int fill_byte) {
+  T *q = nullptr;
+  cudaError_t e = cudaMalloc((void **)&q, new_n * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("out of device memory growing the column (%.2f GB)", new_n * sizeof(T) / 1e9);
+    cudaGetLastError();
+    return TSC_ERR_OOM;
+  }
+  TSC_CUDA(cudaMemcpyAsync(q, *p, old_n * sizeof(T), cudaMemcpyDeviceToDevice, ix->stream));
+  TSC_CUDA(cudaMemsetAsync(q + old_n, fill_byte, (new_n - old_n) * sizeof(T), ix->stream));
+  TSC_CUDA(cudaStreamSynchronize(ix->stream));
+  cudaFree(*p);
+  *p = q;
+  ix->device_bytes += (new_n - old_n) * sizeof(T);
+  return TSC_OK;
+}
+
+int32_t ix_ensure_capacity(Index *ix, uint64_t rows_needed, const char *what) {
+  if (rows_needed <= ix->capacity) return TSC_OK;
+  if (ix->in_group || ix->p2p_ready || ix->nccl_comm || ix->host_only) {
+    set_error("%s: rows up to %llu exceed the shard's capacity %llu (a shard's capacity is its "
+              "node-id range)", what, (unsigned long long)rows_needed,
+              (unsigned long long)ix->capacity);
+    return TSC_ERR_OOM;
+  }
+  if (rows_needed >= 0xFFFFFFFFull) {
+    set_error("%s: a shard holds at most 2^32-2 rows", what);
+    return TSC_ERR_OOM;
+  }
+  uint64_t cap = ix->capacity + ix->capacity / 2;
+  if (cap < rows_needed) cap = rows_needed;
+  if (cap > 0xFFFFFFFEull) cap = 0xFFFFFFFEull;
+  // if 1.5 x does not fit in memory any more, what is needed may still do
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if ((size_t)cap * ix->row_bytes <= ix->rows_va_bytes) break;
+    cap = rows_needed;
+  }
+  TSC_CUDA(cudaSetDevice(ix->device));
+  int32_t rc = sync_last_search(ix);   // nothing may be reading the arrays that move
+  if (rc != TSC_OK) return rc;
+  TSC_CUDA(cudaStreamSynchronize(ix->stream));
+  rc = rows_map_to(ix, (size_t)cap * ix->row_bytes);
+  if (rc != TSC_OK && cap > rows_needed) {
+    cap = rows_needed;
+    rc = rows_map_to(ix, (size_t)cap * ix->row_bytes);
+  }
+  if (rc != TSC_OK) return rc;
+  const uint64_t old_words = ix->mask_words, new_words = (cap + 31) / 32 + 1;
+  if ((rc = regrow(ix, &ix->d_norm2, (size_t)ix->capacity, (size_t)cap, 0)) != TSC_OK) return rc;
+  if ((rc = regrow(ix, &ix->d_deleted, (size_t)old_words, (size_t)new_words, 0)) != TSC_OK) return rc;
+  if ((rc = regrow(ix, &ix->d_filter, (size_t)old_words, (size_t)new_words, 0xFF)) != TSC_OK) return rc;
+  if ((rc = regrow(ix, &ix->d_live, (size_t)old_words, (size_t)new_words, 0xFF)) != TSC_OK) return rc;
+  for (auto &c : ix->columns) {
+    if ((rc = regrow(ix, &c.d_values, (size_t)ix->capacity, (size_t)cap, 0)) != TSC_OK) return rc;
+    if ((rc = regrow(ix, &c.d_null, (size_t)old_words, (size_t)new_words, 0xFF)) != TSC_OK) return rc;
+  }
+  ix->capacity = cap;
+  ix->desc.capacity_rows = cap;
+  ix->mask_words = new_words;
+  ix->live_dirty = true;
+  return TSC_OK;
+}
+
 static int32_t check_append_range(Index *ix, uint64_t first_node_id, uint64_t n_rows,
                                   uint64_t *row0) {
   uint64_t base = ix->desc.first_node_id;
@@ -402,12 +603,7 @@ static int32_t check_append_range(Index *ix, uint64_t first_node_id, uint64_t n_
     return TSC_ERR_BAD_ARG;
   }
   *row0 = first_node_id - base;
-  if (*row0 + n_rows > ix->capacity) {
-    set_error("append: %llu rows at %llu exceed capacity %llu", (unsigned long long)n_rows,
-              (unsigned long long)*row0, (unsigned long long)ix->capacity);
-    return TSC_ERR_OOM;
-  }
-  return TSC_OK;
+  return ix_ensure_capacity(ix, *row0 + n_rows, "append");
 }
 
 int32_t ix_append_rows(Index *ix, uint64_t first_node_id, const void *rows, uint64_t n_rows) {
@@ -703,6 +899,10 @@ int32_t ix_stats_get(Index *ix, tsc_stats *out) {
   out->last_search_ms = ix->last_ms < 0 ? 0 : ix->last_ms;
   out->last_scan_gbs = ix->last_ms < 0 ? 0 : ix->last_gbs;
   out->last_path = ix->last_path;
+  if (ix->last_path == 2 && ix->last_ms > 0) {
+    out->last_tflops = ix->last_flops / (ix->last_ms * 1e9);
+    out->last_tensor_util = out->last_tflops / (ix->desc.dev_dtype == TSC_DEV_F32 ? 1125.0 : 2250.0);
+  }
   TSC_CUDA(cudaSetDevice(ix->device));
   if (ix->t_pending) {
     int32_t rc = hot_timer_resolve(ix);

@@ -137,6 +137,7 @@ int32_t grp_create(const tsc_index_desc *d, uint64_t *out_handle) {
     IndexRef ix;
     int32_t rc = ix_create(&one, &ix);
     if (rc != TSC_OK) return rc;
+    ix->in_group = true;
     g->shards.push_back(ix);
   }
   // peer access in both directions, then every shard learns every receive buffer
@@ -375,6 +376,8 @@ int32_t grp_stats_get(Group &g, tsc_stats *out) {
     if (st.hot_ms_total > acc.hot_ms_total) acc.hot_ms_total = st.hot_ms_total;
     if (st.last_search_ms > acc.last_search_ms) acc.last_search_ms = st.last_search_ms;
     acc.last_scan_gbs += st.last_scan_gbs;
+    acc.last_tflops += st.last_tflops;                 // shards run side by side
+    acc.last_tensor_util += st.last_tensor_util / (double)g.shards.size();
     acc.certified_queries += st.certified_queries;
     acc.retried_queries += st.retried_queries;
     acc.uncertified_queries += st.uncertified_queries;

@@ -62,6 +62,13 @@ struct Index {
   uint32_t row_bytes = 0;
   uint32_t qld = 0;         // padded query length (== ld)
   uint8_t *d_rows = nullptr;
+  // The row block lives in a reserved virtual address range that physical memory is mapped
+  // into chunk by chunk (CUDA virtual memory management): growing the column adds a chunk
+  // behind the mapped part, the address of every existing row stays what it was.
+  unsigned long long rows_va = 0;     // CUdeviceptr of the reservation (== d_rows)
+  size_t rows_va_bytes = 0, rows_mapped = 0, vmm_gran = 0;
+  std::vector<std::pair<unsigned long long, size_t>> rows_chunks;   // (allocation handle, bytes)
+  bool in_group = false;              // shard of a group handle: its capacity is its node-id range
   uint64_t capacity = 0, rows = 0;
 
   // liveness: deleted (tombstones) and filter (WHERE) bitmaps -> live
@@ -113,6 +120,7 @@ struct Index {
   bool host_consumer = true;         // the search in flight delivers its result on this shard
   double last_threshold = 0;         // of the host-buffer search in flight (owed range passes)
   // one search at a time uses the scratch above: searches on other streams wait for this
+  double last_flops = 0;               // algorithmic flops of the last timed search (tensor path), else 0
   cudaEvent_t scratch_ev = nullptr;    // recorded at the end of a search unless a timer event already is
   // Pipelined device searches (tsc_index_set_pipelining): the scan launch of search i+1 is a
   // programmatic dependent of search i's range launch and overlaps search i's tail; stream
@@ -191,6 +199,8 @@ void free_index(Index *ix);               // deleter of IndexRef: releases the d
 IndexRef lookup_index(uint64_t handle);   // empty + error string when unknown (or a group)
 uint64_t register_index(IndexRef ix);
 int32_t ensure_stage_bytes(Index *ix, size_t bytes);
+// make room for rows [0, rows_needed) (unsharded handles grow; shards answer TSC_ERR_OOM). Caller holds ix->mu.
+int32_t ix_ensure_capacity(Index *ix, uint64_t rows_needed, const char *what);
 int32_t refresh_live(Index *ix, cudaStream_t st);
 int32_t order_after_last_search(Index *ix, cudaStream_t st);   // st waits for the last search's scratch use
 int32_t sync_last_search(Index *ix);                           // host waits for it

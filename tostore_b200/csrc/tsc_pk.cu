@@ -17,6 +17,7 @@ int32_t ix_set_primary_keys(Index *ix, uint64_t first_node_id, const uint8_t *ut
   }
   std::lock_guard<std::mutex> lk(ix->mu);
   const uint64_t base = ix->desc.first_node_id;
+  // (mappings follow their rows: an append that grew the column has raised the capacity already)
   if (first_node_id < base || first_node_id - base + n > ix->capacity) {
     set_error("set_primary_keys: node ids [%llu, %llu) outside shard [%llu, %llu)",
               (unsigned long long)first_node_id, (unsigned long long)(first_node_id + n),

@@ -253,6 +253,7 @@ static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, 
       uint32_t passes = (nq + 7) / 8;
       if (nq <= 4 || use_gemm) passes = 1;
       ix->last_gbs = (double)passes * (double)ix->rows * ix->desc.dims * ix->elem_bytes;  // bytes
+      ix->last_flops = use_gemm ? 2.0 * nq * (double)ix->rows * ix->desc.dims : 0.0;
       ix->last_ms = -1.0;  // resolved lazily from the events
     }
   }

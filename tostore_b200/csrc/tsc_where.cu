@@ -162,10 +162,9 @@ int32_t ix_column_append(Index *ix, uint32_t column_id, uint64_t first_node_id, 
     return TSC_ERR_BAD_ARG;
   }
   const uint64_t row0 = first_node_id - base;
-  if (row0 + n > ix->capacity) {
-    set_error("column_append: %llu rows at %llu exceed capacity %llu", (unsigned long long)n,
-              (unsigned long long)row0, (unsigned long long)ix->capacity);
-    return TSC_ERR_OOM;
+  {
+    int32_t grc = ix_ensure_capacity(ix, row0 + n, "column_append");
+    if (grc != TSC_OK) return grc;
   }
   TSC_CUDA(cudaSetDevice(ix->device));
   TSC_CUDA(cudaMemcpyAsync(c->d_values + row0, values, n * 8, cudaMemcpyHostToDevice, ix->stream));
