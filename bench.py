@@ -408,10 +408,16 @@ def run_b200(args):
                                   "(DESIGN.md K1: 90 % of the 8.18 TB/s ncu reports as DRAM peak)",
                      "kernel": "scan_topk_kernel<L2,f32,QB=1> (scan + fused tail)",
                      "kernel_ms": hot_ms, "algorithmic_bytes_per_launch": hot_bytes,
-                     "kernel_share_of_step": hot_ms / (total_ms / steps) if total_ms else None},
+                     "kernel_share_of_step": hot_ms / (total_ms / steps) if total_ms else None,
+                     "kernel_share_note": ("kernel_ms is the event-timed duration of the sampled, "
+                                           "non-overlapped launches; in the pipelined loop consecutive "
+                                           "launches overlap by the tail, so the share can exceed 1")
+                     if pipelined else None},
         "e2e": {"value": steps * (world if replicas else 1) / (e2e_ms * 1e-3), "unit": "queries/s",
                 "h2d_bytes_per_step": d * 4 * world,            # every rank copies its query in
-                "d2h_bytes_per_step": (k * 16 + 8) * (world if replicas else 1),
+                # the library brings ids | dist | counts | flags back as ONE block sized for
+                # (nq_max = 8, k_max = 16): 2 * 8 * 16 * 8 + 2 * 32 bytes, on every rank
+                "d2h_bytes_per_step": (2 * 8 * 16 * 8 + 2 * 32) * world,
                 "ms_per_step": e2e_ms / steps,
                 "api": "tsc_search (host buffers)" + (", called on every rank; rank 0 receives the "
                                                       "merged result" if sharded else "")},

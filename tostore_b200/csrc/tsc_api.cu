@@ -226,10 +226,7 @@ void free_index(Index *ix) {
   cudaFree(ix->d_enorm);
   cudaFree(ix->d_progress);
   cudaFree(ix->d_cand);
-  cudaFree(ix->d_out_ids);
-  cudaFree(ix->d_out_dist);
-  cudaFree(ix->d_out_counts);
-  cudaFree(ix->d_flags);
+  cudaFree(ix->d_out_block);
   cudaFree(ix->d_range_thr);
   cudaFree(ix->d_retry_list);
   cudaFree(ix->d_retry_n);
@@ -255,10 +252,7 @@ void free_index(Index *ix) {
     cudaFree(c.d_null);
   }
   cudaFreeHost(ix->h_queries);
-  cudaFreeHost(ix->h_out_ids);
-  cudaFreeHost(ix->h_out_dist);
-  cudaFreeHost(ix->h_out_counts);
-  cudaFreeHost(ix->h_flags);
+  cudaFreeHost(ix->h_out_block);
   for (int i = 0; i < Index::kTimers; i++) {
     if (ix->t_beg[i]) cudaEventDestroy(ix->t_beg[i]);
     if (ix->t_end[i]) cudaEventDestroy(ix->t_end[i]);
@@ -462,10 +456,22 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
   ok(dev_alloc(ix, &ix->d_progress, (size_t)4096));
   if (d->dev_dtype != TSC_DEV_F32) ok(dev_alloc(ix, &ix->d_q16, (size_t)ix->nq_max * ix->qld));
   ok(dev_alloc(ix, &ix->d_cand, (size_t)ix->nq_max * ix->cand_lists * ix->kprime_max));
-  ok(dev_alloc(ix, &ix->d_out_ids, (size_t)ix->nq_max * ix->k_max));
-  ok(dev_alloc(ix, &ix->d_out_dist, (size_t)ix->nq_max * ix->k_max));
-  ok(dev_alloc(ix, &ix->d_out_counts, (size_t)ix->nq_max));
-  ok(dev_alloc(ix, &ix->d_flags, (size_t)ix->nq_max));
+  {
+    const size_t nk8 = (size_t)ix->nq_max * ix->k_max * 8, n4 = ((size_t)ix->nq_max * 4 + 7) & ~(size_t)7;
+    ix->out_block_bytes = 2 * nk8 + 2 * n4;
+    ok(dev_alloc(ix, &ix->d_out_block, ix->out_block_bytes));
+    ok(cudaMallocHost((void **)&ix->h_out_block, ix->out_block_bytes));
+    if (e == cudaSuccess) {
+      ix->d_out_ids = reinterpret_cast<int64_t *>(ix->d_out_block);
+      ix->d_out_dist = reinterpret_cast<double *>(ix->d_out_block + nk8);
+      ix->d_out_counts = reinterpret_cast<uint32_t *>(ix->d_out_block + 2 * nk8);
+      ix->d_flags = reinterpret_cast<uint32_t *>(ix->d_out_block + 2 * nk8 + n4);
+      ix->h_out_ids = reinterpret_cast<int64_t *>(ix->h_out_block);
+      ix->h_out_dist = reinterpret_cast<double *>(ix->h_out_block + nk8);
+      ix->h_out_counts = reinterpret_cast<uint32_t *>(ix->h_out_block + 2 * nk8);
+      ix->h_flags = reinterpret_cast<uint32_t *>(ix->h_out_block + 2 * nk8 + n4);
+    }
+  }
   ok(dev_alloc(ix, &ix->d_range_thr, (size_t)ix->nq_max));
   ok(dev_alloc(ix, &ix->d_retry_list, (size_t)ix->nq_max));
   ok(dev_alloc(ix, &ix->d_retry_n, 1));
@@ -479,10 +485,6 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
 #endif
   ok(cudaEventCreateWithFlags(&ix->host_done, cudaEventDisableTiming));
   ok(cudaMallocHost((void **)&ix->h_queries, (size_t)ix->nq_max * ix->qld * 4));
-  ok(cudaMallocHost((void **)&ix->h_out_ids, (size_t)ix->nq_max * ix->k_max * 8));
-  ok(cudaMallocHost((void **)&ix->h_out_dist, (size_t)ix->nq_max * ix->k_max * 8));
-  ok(cudaMallocHost((void **)&ix->h_out_counts, (size_t)ix->nq_max * 4));
-  ok(cudaMallocHost((void **)&ix->h_flags, (size_t)ix->nq_max * 4));
   if (e == cudaSuccess) {
     ok(cudaMemsetAsync(ix->d_deleted, 0, ix->mask_words * 4, ix->stream));
     ok(cudaMemsetAsync(ix->d_filter, 0xFF, ix->mask_words * 4, ix->stream));

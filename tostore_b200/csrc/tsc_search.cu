@@ -330,15 +330,21 @@ int32_t ix_search_begin(Index *ix, const float *queries, uint32_t nq, uint32_t k
                           ix->d_out_counts, st, ix_sharded(ix));
   if (rc != TSC_OK) return rc;
   ix->host_consumer = ix_is_consumer(ix);
-  if (ix->host_consumer) {
-    TSC_CUDA(cudaMemcpyAsync(ix->h_out_ids, ix->d_out_ids, (size_t)nq * k * 8,
+  if (ix->out_block_bytes <= 16384) {
+    // small result block: everything (ids, dist, counts, flags) in one copy
+    TSC_CUDA(cudaMemcpyAsync(ix->h_out_block, ix->d_out_block, ix->out_block_bytes,
                              cudaMemcpyDeviceToHost, st));
-    TSC_CUDA(cudaMemcpyAsync(ix->h_out_dist, ix->d_out_dist, (size_t)nq * k * 8,
-                             cudaMemcpyDeviceToHost, st));
-    TSC_CUDA(cudaMemcpyAsync(ix->h_out_counts, ix->d_out_counts, (size_t)nq * 4,
-                             cudaMemcpyDeviceToHost, st));
+  } else {
+    if (ix->host_consumer) {
+      TSC_CUDA(cudaMemcpyAsync(ix->h_out_ids, ix->d_out_ids, (size_t)nq * k * 8,
+                               cudaMemcpyDeviceToHost, st));
+      TSC_CUDA(cudaMemcpyAsync(ix->h_out_dist, ix->d_out_dist, (size_t)nq * k * 8,
+                               cudaMemcpyDeviceToHost, st));
+      TSC_CUDA(cudaMemcpyAsync(ix->h_out_counts, ix->d_out_counts, (size_t)nq * 4,
+                               cudaMemcpyDeviceToHost, st));
+    }
+    TSC_CUDA(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
   }
-  TSC_CUDA(cudaMemcpyAsync(ix->h_flags, ix->d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
   TSC_CUDA(cudaEventRecord(ix->host_done, st));
   return TSC_OK;
 }
