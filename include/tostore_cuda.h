@@ -299,7 +299,7 @@ int32_t tsc_vector_search(uint64_t handle, const double *values, uint64_t len,
 
 /* Batch form (additive; the reference's API is single-query): nq query vectors of `len`
  * values each [nq][len], prepared like single queries and searched in one call (the
- * tensor-core path for 16-bit columns and nq >= 9). out_ids / out_dist / out_score are
+ * tensor-core path from 5 queries on 16-bit columns, from 9 on fp32 columns). out_ids / out_dist / out_score are
  * [nq][k], out_counts [nq]. */
 int32_t tsc_vector_search_batch(uint64_t handle, const double *values, uint64_t len, uint32_t nq,
                                 uint32_t k, double distance_threshold, int64_t *out_ids,

@@ -59,9 +59,12 @@ def test_gemm_path_parity_with_oracle(dt, metric):
         ix.append_synthetic(61, n)
         ids, dist, cnt = ix.search(Qp, k)
         assert ix.stats().last_path == 2                    # tensor-core path taken
-        ids8, dist8, _ = ix.search(Qp[:8], k)               # scan path on the same index
+        ids8, dist8, _ = ix.search(Qp[:4], k)               # scan path on the same index
         assert ix.stats().last_path == 1
-        assert (ids[:8] == ids8).all() and (bits(dist[:8]) == bits(dist8)).all()
+        assert (ids[:4] == ids8).all() and (bits(dist[:4]) == bits(dist8)).all()
+        ids6, dist6, _ = ix.search(Qp[:6], k)               # 16-bit columns: tensor path from 5 queries
+        assert ix.stats().last_path == 2
+        assert (ids[:6] == ids6).all() and (bits(dist[:6]) == bits(dist6)).all()
         for q in range(0, nq, 7):
             oi, od = oracle.search(rows, Qp[q], metric, k)
             assert cnt[q] == k and (ids[q] == oi).all(), (q, ids[q], oi)

@@ -59,6 +59,16 @@ def test_pipelined_equals_unpipelined_and_oracle(n, dims, metric, dt, nq_per_cal
             assert (bits(b[1][q]) == bits(od)).all()
         st = ix.stats()
         assert st.uncertified_queries == 0 and st.hot_launches > 0   # sampled timer still reports
+        if n >= 100_000:
+            # the sparse (per-live-row) scan kernel shares the pipelined chain
+            rng = np.random.default_rng(7)
+            keep = rng.random(n) < 0.1
+            ix.set_filter(keep)
+            a = run_stream(ix, Q, k, nq_per_call, False)
+            b = run_stream(ix, Q, k, nq_per_call, True)
+            assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all() and (a[2] == b[2]).all()
+            oi, od = oracle.search(rows, Q[5], metric, k, deleted=~keep)
+            assert (b[0][5] == oi).all() and (bits(b[1][5]) == bits(od)).all()
 
 
 def test_pipelined_search_flags_what_it_cannot_certify():

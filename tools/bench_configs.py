@@ -91,6 +91,8 @@ CONFIGS = {
     "c1": lambda: [measure("c1 brute-force L2 10k x 128 fp32 k=10", 10_000, 128, 0, 0, 1, 10, 200)],
     "c2": lambda: [measure("c2 single-query L2 10M x 768 fp32 k=10", 10_000_000, 768, 0, 0, 1, 10, 30)],
     "c2b": lambda: [measure("c2b 8-query L2 10M x 768 fp32 k=10 (scan, one pass)", 10_000_000, 768, 0, 0, 8, 10, 10)],
+    "c2q": lambda: [measure(f"c2q {q}-query L2 10M x 768 fp32 k=10", 10_000_000, 768, 0, 0, q, 10, 8) for q in (2, 4, 8)],
+    "c3q": lambda: [measure(f"c3q {q}-query cosine 10M x 768 bf16 k=10", 10_000_000, 768, 2, 1, q, 10, 8) for q in (2, 4, 8)],
     "c2t": lambda: [measure("c2t batch-1024 L2 10M x 768 fp32 k=10 (tf32 tensor path)", 10_000_000, 768, 0, 0,
                             1024, 10, 5)],
     "c3": lambda: [measure("c3 batch-1024 cosine 10M x 768 bf16 k=10", 10_000_000, 768, 2, 1, 1024, 10, 10)],

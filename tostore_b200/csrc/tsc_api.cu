@@ -408,6 +408,7 @@ int32_t ix_create(const tsc_index_desc *d, IndexRef *out) {
   ix->sm_count = prop.multiProcessorCount;
   ix->smem_optin = prop.sharedMemPerBlockOptin;
   ix->elem_bytes = d->dev_dtype == TSC_DEV_F32 ? 4 : 2;
+  ix->gemm_min_nq = d->dev_dtype == TSC_DEV_F32 ? 9 : 5;
   uint32_t epc = 16 / ix->elem_bytes;
   ix->ld = (d->dims + epc - 1) / epc * epc;
   ix->row_bytes = ix->ld * ix->elem_bytes;

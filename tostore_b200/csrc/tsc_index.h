@@ -92,7 +92,10 @@ struct Index {
   int *d_progress = nullptr;       // diagnostics scratch of the tensor-core path
   uint16_t *d_q16 = nullptr;       // [nq_max, qld] queries in the storage dtype (GEMM path)
   float *d_enorm = nullptr;        // [nq_max] |q16 - q| of the converted queries (certificate)
-  uint32_t gemm_min_nq = 9;        // batches at least this large take the tensor-core path
+  // batches at least this large take the tensor-core path: 9 for fp32 columns (8 queries: scan
+  // 10.9 ms, tf32 GEMM 12.4), 5 for 16-bit columns (8 queries: scan 15.0 ms, GEMM 8.2; 4 queries:
+  // 6.9 vs 6.4) — 10M x 768, profiles/r02_small_batches.txt
+  uint32_t gemm_min_nq = 9;
   // TMA descriptors of the tensor path, encoded once per (pointer, extent) instead of per launch
   struct TmapSlot {
     alignas(64) unsigned char bytes[128];   // a CUtensorMap
@@ -318,6 +321,7 @@ struct SearchCtx {
   const float *d_q = nullptr;    // [nq, qld] fp32, padded
   uint32_t nq = 0, k = 0, kprime = 0;
   uint32_t gemm_list_kp = 0;     // tensor path: entries per candidate list (<= kprime)
+  bool pipelined = false;        // device-buffer search of a handle with pipelining on
   double threshold = 0;
   int64_t *loc_ids = nullptr;
   double *loc_dist = nullptr;

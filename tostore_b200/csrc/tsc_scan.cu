@@ -24,6 +24,7 @@ int32_t scan_configure(Index *ix) {
   // sparse scan: 16 warps per SM read 5.19 TB/s of live rows at 10 % density, 8 warps 3.89
   // (profiles/r02_sparse_warps.txt; the plain-load gather ceiling is 5.70)
   ix->scan.sparse_warps = env_int("TSC_SCAN_SPARSE_WARPS", 16);
+  ix->gemm_min_nq = (uint32_t)env_int("TSC_GEMM_MIN_NQ", (int)ix->gemm_min_nq);   // diagnostics build only
   ix->scan.rows = env_int("TSC_SCAN_ROWS", 0);
   ix->scan.stages = env_int("TSC_SCAN_STAGES", 0);
   ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 6144);
@@ -115,7 +116,7 @@ int32_t launch_scan(Index *ix, const SearchCtx &c, int mode, uint32_t q_base, ui
   p.fused_tail = (fused || mode == 1) ? 1 : 0;
   p.xchg_in_tail = xchg ? 1 : 0;
   p.last_retry = last_retry ? 1 : 0;
-  p.no_range = (mode == 0 && p.fused_tail && ix->pipeline) ? 1 : 0;
+  p.no_range = (mode == 0 && p.fused_tail && c.pipelined) ? 1 : 0;
   p.nq_total = c.nq;
   // first passes and range launches keep separate tickets and work counters
   p.done_counter = ix->d_done + (mode == 1 ? 4 : 0);

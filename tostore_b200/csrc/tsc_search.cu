@@ -148,7 +148,7 @@ int32_t ix_xchg_alloc(Index *ix, int n_ranks, int rank, int root) {
 // d_counts is the merge over all shards (valid on the consumer ranks).
 static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, double threshold,
                           int64_t *d_ids, double *d_dist, uint32_t *d_counts, cudaStream_t st,
-                          bool sharded) {
+                          bool sharded, bool device_api) {
   // the search scratch is one per index: order this search after the previous one
   {
     int32_t orc = order_after_last_search(ix, st);
@@ -162,6 +162,7 @@ static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, 
   c.threshold = threshold;
   c.st = st;
   c.sharded = sharded;
+  c.pipelined = device_api && ix->pipeline;   // host-buffer searches always repair in-stream
   const size_t nk = (size_t)nq * k;
   if (sharded) {
     c.loc_ids = (int64_t *)ix->d_gather_send;
@@ -203,7 +204,7 @@ static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, 
     uint32_t lists = 0;
     const bool fused_path = !use_gemm && nq <= 8;
     // (the NCCL exchange enqueues work after the kernels: such searches keep their events)
-    ix->search_timed = !(ix->pipeline && fused_path && (!sharded || p2p)) ||
+    ix->search_timed = !(c.pipelined && fused_path && (!sharded || p2p)) ||
                        (ix->timer_tick++ % ix->timer_every) == 0;
     if (!use_gemm && nq <= 8) {
       // the whole search in one kernel (+ one range launch that normally exits at once)
@@ -215,7 +216,7 @@ static int32_t run_search(Index *ix, const float *d_q, uint32_t nq, uint32_t k, 
       // one launch back; measured: 564 -> 557 us per query with it, 532 without, 1.25M rows).
       // A query whose certificate fails is flagged instead (tsc_search_flags = 1, counted as
       // uncertified in tsc_stats) and is re-issued by the caller.
-      if (!ix->pipeline) {
+      if (!c.pipelined) {
         rc = launch_scan(ix, c, 1, 0, 0, qb, true, p2p, true, nullptr);
         if (rc != TSC_OK) return rc;
       }
@@ -327,7 +328,7 @@ int32_t ix_search_begin(Index *ix, const float *queries, uint32_t nq, uint32_t k
   TSC_CUDA(cudaMemcpyAsync(ix->d_queries, ix->h_queries, (size_t)nq * qld * 4,
                            cudaMemcpyHostToDevice, st));
   int32_t rc = run_search(ix, ix->d_queries, nq, k, threshold, ix->d_out_ids, ix->d_out_dist,
-                          ix->d_out_counts, st, ix_sharded(ix));
+                          ix->d_out_counts, st, ix_sharded(ix), false);
   if (rc != TSC_OK) return rc;
   ix->host_consumer = ix_is_consumer(ix);
   if (ix->out_block_bytes <= 16384) {
@@ -535,7 +536,7 @@ int32_t tsc_search_device(uint64_t handle, const float *d_queries, uint32_t nq, 
     if (prc != TSC_OK) return prc;
     q = ix->d_queries;
   }
-  return run_search(ix, q, nq, k, threshold, d_out_ids, d_out_dist, d_out_counts, st, false);
+  return run_search(ix, q, nq, k, threshold, d_out_ids, d_out_dist, d_out_counts, st, false, true);
   TSC_API_CATCH
 }
 
@@ -563,7 +564,7 @@ int32_t tsc_search_sharded(uint64_t handle, const float *d_queries, uint32_t nq,
     if (prc != TSC_OK) return prc;
     q = ix->d_queries;
   }
-  return run_search(ix, q, nq, k, threshold, d_out_ids, d_out_dist, d_out_counts, st, true);
+  return run_search(ix, q, nq, k, threshold, d_out_ids, d_out_dist, d_out_counts, st, true, true);
   TSC_API_CATCH
 }
 

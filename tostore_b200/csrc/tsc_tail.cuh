@@ -310,6 +310,7 @@ __device__ __forceinline__ void radix_pass(const uint64_t *cand, uint32_t m, int
       if ((int)tid >= o) inc += t;
     }
     const uint32_t exc = inc - sum, rem = *s_remaining;
+    __syncwarp();   // every lane has read s_remaining before the one that owns the bucket rewrites it
     if (exc < rem && rem <= inc) {  // exactly one lane: m >= remaining entries match
       uint32_t cum = exc, b = tid * per;
       for (uint32_t i = 0; i < per; i++) {

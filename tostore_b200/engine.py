@@ -255,7 +255,7 @@ class GpuVectorIndex:
     def vector_search_batch(self, values, k: int, threshold: Optional[float] = None):
         """Batch form of `vector_search` (additive): values [nq, len] fp64, every query
         prepared like a single one, one search call (tensor-core path for 16-bit columns and
-        nq >= 9). Returns (ids [nq,k], dist [nq,k], score [nq,k], counts [nq])."""
+        nq >= 5 on 16-bit columns, nq >= 9 on fp32 columns). Returns (ids [nq,k], dist [nq,k], score [nq,k], counts [nq])."""
         v = np.ascontiguousarray(values, dtype=np.float64)
         if v.ndim != 2:
             raise ValueError("values must be [nq, len]")
