@@ -561,6 +561,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
               p.dbg_keys[(size_t)q * p.n_rows + r0 + j] =
                   fmaf(__uint_as_float(v[j]), sc_s[j], bi_s[j]) + 0.0f;
       }
+      // Padded query rows (q >= nq: zero queries) would tie every column at one key, keep
+      // R at -inf and send all 256 columns of every tile through the exact test: measured
+      // (8 queries in a 128-row tile, profiles/r02_small_batches.txt) 7 x the instructions of
+      // a full tile and a kernel at 23 % of HBM. They have nothing to find: skip them.
+      if (q >= p.nq) return;
       const float *f = reinterpret_cast<const float *>(&v[0]);
       float g[4];
 #pragma unroll
