@@ -153,6 +153,6 @@ def test_c_example_compiles_and_fails_loudly_without_gpu(tmp_path):
                            os.path.join(ROOT, "examples", "minimal.c"), "-o", str(exe), "-L", libdir,
                            "-ltostore_cuda", f"-Wl,-rpath,{libdir}", "-lm"])
     if torch.cuda.is_available():
-        pytest.skip("GPU present: the example would run for real (see tools/gpu_r2_first.sh)")
+        pytest.skip("GPU present: the example would run for real (see tools/history/gpu_r2_first.sh)")
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 1 and "TSC_ERR_CUDA" in out.stderr

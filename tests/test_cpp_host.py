@@ -2,7 +2,7 @@
 QueryCondition builder produces programs whose evaluation (library host self-test, the code
 the GPU kernel shares) equals the oracle's restatement of the reference's matcher
 (handler/value_matcher.dart:476-612). The GPU half of examples/vector_store_demo.cc runs on
-a B200 only (tools/gpu_r2_first.sh)."""
+a B200 only (tools/history/gpu_r2_first.sh)."""
 import math
 import os
 import shutil
@@ -53,7 +53,7 @@ def demo(tmp_path_factory):
 def test_cpp_query_condition_builder_equals_oracle(demo):
     import torch
     if torch.cuda.is_available():
-        pytest.skip("GPU present: the demo's second half would run for real (tools/gpu_r2_first.sh)")
+        pytest.skip("GPU present: the demo's second half would run for real (tools/history/gpu_r2_first.sh)")
     out = subprocess.run([demo], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     got = dict(line.split() for line in out.stdout.splitlines() if " " in line and set(line.split()[-1]) <= {"0", "1"})
