@@ -12,7 +12,7 @@ OUT=${TMPDIR:-/tmp}/tsc_asan
 mkdir -p $OUT
 SRC=tostore_b200/csrc
 make -C $SRC -j8 >/dev/null
-for f in tsc_api tsc_where tsc_pk tsc_loader; do
+for f in tsc_api tsc_search tsc_group tsc_where tsc_pk tsc_loader; do
   /usr/local/cuda/bin/nvcc -O1 -g -std=c++17 -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ \
     -cudart static --expt-relaxed-constexpr \
     -Xcompiler -fPIC,-ffp-contract=off,$SAN,-fno-omit-frame-pointer \
@@ -20,8 +20,10 @@ for f in tsc_api tsc_where tsc_pk tsc_loader; do
 done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -cudart static -shared \
-  -o $OUT/libtostore_cuda.so $OUT/tsc_api.o $OUT/tsc_where.o $OUT/tsc_pk.o $OUT/tsc_loader.o \
-  $SRC/build/tsc_scan.o $SRC/build/tsc_select.o $SRC/build/tsc_gemm.o -ldl -lpthread \
+  -o $OUT/libtostore_cuda.so $OUT/tsc_api.o $OUT/tsc_search.o $OUT/tsc_group.o $OUT/tsc_where.o \
+  $OUT/tsc_pk.o $OUT/tsc_loader.o $SRC/build/tsc_scan.o $SRC/build/tsc_scan_l2.o \
+  $SRC/build/tsc_scan_ip.o $SRC/build/tsc_scan_cos.o $SRC/build/tsc_tail.o $SRC/build/tsc_gemm.o \
+  -ldl -lpthread \
   -Xcompiler $SAN
 cp tostore_b200/libtostore_cuda.so $OUT/libtostore_cuda.so.orig
 trap 'cp $OUT/libtostore_cuda.so.orig tostore_b200/libtostore_cuda.so' EXIT

@@ -212,7 +212,9 @@ void free_index(Index *ix) {
     return;
   }
   cudaSetDevice(ix->device);
-  if (ix->stream) cudaStreamSynchronize(ix->stream);
+  // searches may still be running on caller-owned streams; cudaFree would wait for them
+  // implicitly, unmapping the row block (cuMemUnmap) does not
+  cudaDeviceSynchronize();
   rows_release(ix);
   cudaFree(ix->d_deleted);
   cudaFree(ix->d_filter);
