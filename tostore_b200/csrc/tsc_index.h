@@ -31,6 +31,8 @@ void set_error(const char *fmt, ...);
 struct ScanConfig {
   int grid = 0;        // CTAs (multiple of the SM count)
   int warps = 8;       // warps per CTA
+  int warps16 = 16;    // ... for 16-bit columns: twice the elements per byte, latency-bound at 8 warps
+                       // (bf16 cosine 10M x 768: 2.70 ms at 8 warps, 2.26 ms at 16; fp32 is faster at 8)
   int sparse_warps = 16;   // ... of the sparse scan (K6): latency-bound per warp, wants more of them
   int rows = 0;        // R rows per stage (0 = auto)
   int stages = 0;      // S (0 = auto)

@@ -24,13 +24,14 @@ int32_t scan_configure(Index *ix) {
   // sparse scan: 16 warps per SM read 5.19 TB/s of live rows at 10 % density, 8 warps 3.89
   // (profiles/r02_sparse_warps.txt; the plain-load gather ceiling is 5.70)
   ix->scan.sparse_warps = env_int("TSC_SCAN_SPARSE_WARPS", 16);
+  ix->scan.warps16 = env_int("TSC_SCAN_WARPS16", env_int("TSC_SCAN_WARPS", 16));
   ix->gemm_min_nq = (uint32_t)env_int("TSC_GEMM_MIN_NQ", (int)ix->gemm_min_nq);   // diagnostics build only
   ix->scan.rows = env_int("TSC_SCAN_ROWS", 0);
   ix->scan.stages = env_int("TSC_SCAN_STAGES", 0);
   ix->scan.stage_target = env_int("TSC_SCAN_STAGE_BYTES", 6144);
   ix->scan.inflight_target = env_int("TSC_SCAN_INFLIGHT_BYTES", 96 * 1024);
   if (ix->scan.warps < 1 || ix->scan.warps > 16 || ix->scan.grid < 1 || ix->scan.sparse_warps < 1 ||
-      ix->scan.sparse_warps > 16) {
+      ix->scan.sparse_warps > 16 || ix->scan.warps16 < 1 || ix->scan.warps16 > 16) {
     set_error("bad TSC_SCAN_* override");
     return TSC_ERR_BAD_ARG;
   }
@@ -40,7 +41,8 @@ int32_t scan_configure(Index *ix) {
 static bool plan_scan(const Index *ix, int qb, uint32_t kprime, ScanPlan *pl,
                       bool sparse = false) {
   const size_t budget = ix->smem_optin - 1024;
-  for (int w = sparse ? ix->scan.sparse_warps : ix->scan.warps; w >= 1; w >>= 1) {
+  const int w0 = sparse ? ix->scan.sparse_warps : (ix->elem_bytes == 2 ? ix->scan.warps16 : ix->scan.warps);
+  for (int w = w0; w >= 1; w >>= 1) {
     int r = sparse ? 1 : ix->scan.rows;  // sparse: one live row per stage
     if (r <= 0) {
       r = 8;

@@ -127,8 +127,25 @@ __device__ __forceinline__ uint32_t scan_key(float acc, float bb) {
 }
 
 // Shared-memory footprint (must match the carve-up in the kernel).
+// Query rows in shared memory. fp32 columns: as they are. 16-bit columns: a lane needs the 8
+// query elements of its chunk = two LDS.128 at a 32-byte lane stride, which is a 2-way bank
+// conflict (308 M conflicts in one C4 launch, ncu); so every block of 256 elements (one chunk
+// per lane) is stored as its 32 first halves followed by its 32 second halves and both loads
+// are conflict-free. Stride = qld rounded up to whole blocks.
+__host__ __device__ inline uint32_t scan_q_stride(uint32_t qld) { return (qld + 255u) & ~255u; }
 __host__ __device__ inline size_t scan_smem_query_bytes(int qb, uint32_t qld) {
-  return ((size_t)qb * qld * 4 + 127) & ~(size_t)127;
+  return ((size_t)qb * scan_q_stride(qld) * 4 + 127) & ~(size_t)127;
+}
+template <int E>
+__device__ __forceinline__ uint32_t scan_q_slot(uint32_t e) {   // element index -> slot in its row
+  if (E == 4) return e;
+  const uint32_t r = e & 255u;
+  return (e & ~255u) + ((r >> 2) & 1u) * 128u + (r >> 3) * 4u + (r & 3u);
+}
+template <int E>
+__device__ __forceinline__ const float4 *scan_q_chunk(const float *row, uint32_t c, int h) {
+  if (E == 4) return reinterpret_cast<const float4 *>(row + (size_t)c * 4);
+  return reinterpret_cast<const float4 *>(row + ((size_t)(c >> 5) << 8) + (size_t)h * 128 + (size_t)(c & 31u) * 4);
 }
 __host__ __device__ inline size_t scan_smem_sort_bytes(uint32_t sort_cap) {
   return ((size_t)sort_cap * 8 + 127) & ~(size_t)127;
@@ -303,9 +320,11 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
   uint8_t *ring = wbase + off;
 
   // ---- queries -> smem (zero rows for q >= nq), lists -> empty --------------
+  const uint32_t qstride = scan_q_stride(p.qld);
   for (uint32_t i = threadIdx.x; i < (uint32_t)QB * p.qld; i += blockDim.x) {
-    uint32_t q = i / p.qld;
-    qs[i] = (q < nq) ? p.queries[(size_t)qi[q] * p.qld + (i - q * p.qld)] : 0.0f;
+    const uint32_t q = i / p.qld, e = i - q * p.qld;
+    qs[(size_t)q * qstride + scan_q_slot<E>(e)] =
+        (q < nq) ? p.queries[(size_t)qi[q] * p.qld + e] : 0.0f;
   }
   for (uint32_t i = lane; i < (uint32_t)QB * kp; i += 32) {
     lkeys[i] = kEmptyKey;
@@ -412,10 +431,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_kernel(const ScanParams p) {
 #pragma unroll
       for (int q = 0; q < QB; q++) {
         float a[E];
-        const float4 *qp = reinterpret_cast<const float4 *>(qs + (size_t)q * p.qld + (size_t)c * E);
 #pragma unroll
         for (int h = 0; h < E / 4; h++) {
-          float4 t = qp[h];
+          const float4 t = *scan_q_chunk<E>(qs + (size_t)q * qstride, c, h);
           a[4 * h + 0] = t.x;
           a[4 * h + 1] = t.y;
           a[4 * h + 2] = t.z;
@@ -528,9 +546,11 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
   off = (off + 127) & ~(size_t)127;
   uint8_t *ring = wbase + off;
 
+  const uint32_t qstride = scan_q_stride(p.qld);
   for (uint32_t i = threadIdx.x; i < (uint32_t)QB * p.qld; i += blockDim.x) {
-    uint32_t q = i / p.qld;
-    qs[i] = (q < nq) ? p.queries[(size_t)qi[q] * p.qld + (i - q * p.qld)] : 0.0f;
+    const uint32_t q = i / p.qld, e = i - q * p.qld;
+    qs[(size_t)q * qstride + scan_q_slot<E>(e)] =
+        (q < nq) ? p.queries[(size_t)qi[q] * p.qld + e] : 0.0f;
   }
   for (uint32_t i = lane; i < (uint32_t)QB * kp; i += 32) {
     lkeys[i] = kEmptyKey;
@@ -635,10 +655,9 @@ __global__ void __launch_bounds__(512, 1) scan_topk_sparse_kernel(const ScanPara
 #pragma unroll
       for (int q = 0; q < QB; q++) {
         float a[E];
-        const float4 *qp = reinterpret_cast<const float4 *>(qs + (size_t)q * p.qld + (size_t)c * E);
 #pragma unroll
         for (int h = 0; h < E / 4; h++) {
-          float4 t = qp[h];
+          const float4 t = *scan_q_chunk<E>(qs + (size_t)q * qstride, c, h);
           a[4 * h + 0] = t.x;
           a[4 * h + 1] = t.y;
           a[4 * h + 2] = t.z;
