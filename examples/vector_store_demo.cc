@@ -24,14 +24,26 @@ static std::optional<double> rating(int r) {
   return v[r];
 }
 
+// name: text field (UTF-8 here, UTF-16 code units below), one NULL, one value with a line break
+static const char *kName[kRows] = {"alice", "Alice", nullptr, "bob", "al", "alice\nsmith", "a%b", "zo\xc3\xab",
+                                   "\xf0\x9f\x98\x80 grin", "", "bobby", "a_b"};
+
 static void evaluate(const char *name, const QueryCondition &qc) {
   const std::map<std::string, std::pair<uint32_t, DataType>> cols = {{"price", {0, DataType::integer}},
-                                                                      {"rating", {1, DataType::doubleType}}};
+                                                                      {"rating", {1, DataType::doubleType}},
+                                                                      {"name", {2, DataType::text}}};
   auto prog = qc.compile(cols);
-  const uint32_t ids[2] = {0, 1};
-  const uint8_t types[2] = {TSC_COL_I64, TSC_COL_F64};
-  uint64_t vals[2][kRows];
-  uint8_t nulls[2][kRows];
+  const uint32_t ids[3] = {0, 1, 2};
+  const uint8_t types[3] = {TSC_COL_I64, TSC_COL_F64, TSC_COL_TEXT};
+  uint64_t vals[3][kRows] = {};
+  uint8_t nulls[3][kRows];
+  std::u16string row_units;
+  uint64_t row_offs[3][kRows + 1] = {};
+  for (int r = 0; r < kRows; r++) {
+    nulls[2][r] = !kName[r];
+    if (kName[r]) row_units += utf8ToUtf16(kName[r]);
+    row_offs[2][r + 1] = row_units.size();
+  }
   for (int r = 0; r < kRows; r++) {
     nulls[0][r] = !kPrice[r];
     int64_t p = kPrice[r].value_or(0);
@@ -42,9 +54,11 @@ static void evaluate(const char *name, const QueryCondition &qc) {
     std::memcpy(&vals[1][r], &d, 8);
   }
   uint8_t match[kRows];
-  check(tsc_selftest_where(prog.ops.data(), (uint32_t)prog.ops.size(), prog.in_args.data(),
-                           (uint32_t)prog.in_args.size(), 2, ids, types, &vals[0][0], &nulls[0][0], kRows, match),
-        "tsc_selftest_where");
+  check(tsc_selftest_where_text(prog.ops.data(), (uint32_t)prog.ops.size(), prog.in_args.data(),
+                                (uint32_t)prog.in_args.size(), (const uint16_t *)prog.text_units.data(),
+                                prog.text_offsets.data(), prog.n_texts(), 3, ids, types, &vals[0][0], &nulls[0][0],
+                                (const uint16_t *)row_units.data(), &row_offs[0][0], kRows, match),
+        "tsc_selftest_where_text");
   std::printf("%s ", name);
   for (int r = 0; r < kRows; r++) std::putchar(match[r] ? '1' : '0');
   std::putchar('\n');
@@ -69,6 +83,18 @@ int main() {
   evaluate("or_groups", QueryCondition().where("price", "<", int64_t{0}).orWhere("rating", ">=", int64_t{4})
                             .where("price", "IS NOT").orWhere("price", "=", int64_t{0}));
 
+  // text field: String.compareTo order, operands trimmed, LIKE as ValueMatcher.matchesLike
+  evaluate("name_eq", QueryCondition().where("name", "=", std::string("  alice ")));
+  evaluate("name_ne", QueryCondition().where("name", "!=", std::string("bob")));        // NULL != x is true
+  evaluate("name_gt", QueryCondition().where("name", ">", std::string("b")));
+  evaluate("name_in", QueryCondition().whereIn("name", {std::string("bob"), std::string("zo\xc3\xab"), std::string("")}));
+  evaluate("name_like_prefix", QueryCondition().where("name", "LIKE", std::string("al%")));
+  evaluate("name_like_any", QueryCondition().where("name", "LIKE", std::string("%")));  // not across a line break
+  evaluate("name_like_one", QueryCondition().where("name", "LIKE", std::string("a_b")));
+  evaluate("name_like_astral", QueryCondition().where("name", "LIKE", std::string("__ grin")));
+  evaluate("name_not_like_and_price", QueryCondition().where("name", "NOT LIKE", std::string("%b%"))
+                                          .where("price", ">=", int64_t{7}));
+
   // ---- part 2: the ToStore-shaped flow on a GPU ----
   if (tsc_device_count() <= 0) {
     std::printf("no CUDA device: skipping the GPU part (%s)\n", tsc_last_error());
@@ -79,7 +105,7 @@ int main() {
     VectorIndexConfig cfg;
     cfg.distanceMetric = VectorDistanceMetric::cosine;
     db.createVectorIndex("items", "embedding", VectorFieldConfig{64, VectorPrecision::float32}, cfg,
-                         {{"price", DataType::integer}, {"rating", DataType::doubleType}});
+                         {{"price", DataType::integer}, {"rating", DataType::doubleType}, {"name", DataType::text}});
     std::vector<Record> recs;
     for (int r = 0; r < 1000; r++) {
       Record rec;
@@ -89,6 +115,7 @@ int main() {
       rec.embedding = VectorData::fromList(v);
       rec.fields["price"] = int64_t{r % 50};
       if (r % 9) rec.fields["rating"] = (r % 11) * 0.5;
+      rec.fields["name"] = std::string(r % 3 ? "widget " : "gadget ") + std::to_string(r % 7);
       recs.push_back(std::move(rec));
     }
     std::printf("inserted %zu\n", db.batchInsert("items", recs));
@@ -100,6 +127,11 @@ int main() {
     qc.where("price", "<", int64_t{10}).where("rating", ">=", 2.0);
     std::printf("WHERE price < 10 AND rating >= 2:\n");
     for (auto &r : db.vectorSearch("items", "embedding", VectorData::fromList(q), 5, std::nullopt, std::nullopt, &qc))
+      std::printf("  %s distance=%.12g score=%.6f\n", r.primaryKey.c_str(), r.distance, r.score);
+    QueryCondition qt;
+    qt.where("name", "LIKE", std::string("gadget%")).where("price", "<", int64_t{25});
+    std::printf("WHERE name LIKE 'gadget%%' AND price < 25:\n");
+    for (auto &r : db.vectorSearch("items", "embedding", VectorData::fromList(q), 5, std::nullopt, std::nullopt, &qt))
       std::printf("  %s distance=%.12g score=%.6f\n", r.primaryKey.c_str(), r.distance, r.score);
     std::printf("deleted %zu\n", db.deleteKeys("items", {"item-123"}));
     for (auto &r : db.vectorSearch("items", "embedding", VectorData::fromList(q), 3))

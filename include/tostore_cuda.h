@@ -217,19 +217,21 @@ int32_t tsc_index_set_filter(uint64_t handle, const uint64_t *bitmap_words,
  * -0.0 < 0.0, NaN above +inf and equal to itself; NULL != x is true, NULL NOT IN is
  * true, every ordering operator / IN / BETWEEN is false on NULL; a childless AND or OR
  * is true :476-493). ---- */
-enum { TSC_COL_I64 = 0, TSC_COL_F64 = 1 };
+enum { TSC_COL_I64 = 0, TSC_COL_F64 = 1, TSC_COL_TEXT = 2 };
 enum { TSC_W_LEAF = 0, TSC_W_AND = 1, TSC_W_OR = 2 };
 enum {
   TSC_OP_EQ = 0, TSC_OP_NE = 1, TSC_OP_GT = 2, TSC_OP_GE = 3, TSC_OP_LT = 4, TSC_OP_LE = 5,
   TSC_OP_BETWEEN = 6, TSC_OP_IN = 7, TSC_OP_NOT_IN = 8, TSC_OP_IS_NULL = 9,
-  TSC_OP_IS_NOT_NULL = 10, TSC_OP_TRUE = 11, TSC_OP_FALSE = 12
+  TSC_OP_IS_NOT_NULL = 10, TSC_OP_TRUE = 11, TSC_OP_FALSE = 12,
+  TSC_OP_LIKE = 13, TSC_OP_NOT_LIKE = 14   /* text columns only */
 };
 typedef struct tsc_where_op {
   uint8_t kind;          /* TSC_W_*                                               */
   uint8_t op;            /* TSC_OP_* (leaves)                                     */
   uint16_t n;            /* AND / OR: children popped; IN / NOT IN: list length   */
   uint32_t column_id;    /* leaves: the column the operator reads                 */
-  int64_t i_lo, i_hi;    /* operand(s) when the column is TSC_COL_I64             */
+  int64_t i_lo, i_hi;    /* operand(s) when the column is TSC_COL_I64; TSC_COL_TEXT:
+                          * index of the operand string in the program's text pool   */
   double f_lo, f_hi;     /* operand(s) when the column is TSC_COL_F64             */
   uint32_t args_offset;  /* IN / NOT IN: first element in `in_args`               */
   uint32_t reserved;
@@ -248,6 +250,36 @@ int32_t tsc_index_column_append(uint64_t handle, uint32_t column_id, uint64_t fi
  * Columns shorter than the embedding column read as NULL beyond their end. */
 int32_t tsc_index_filter_where(uint64_t handle, const tsc_where_op *ops, uint32_t n_ops,
                                const void *in_args, uint32_t n_in_args, uint64_t *out_matched);
+
+/* ---- text fields (DataType.text) in the WHERE prefilter. A TSC_COL_TEXT column is
+ * dictionary-encoded in HBM: distinct strings once, as UTF-16 code units (a Dart String's
+ * own code units, `String.codeUnits`), rows hold the code. Order is Dart's
+ * String.compareTo — lexicographic over code units (text matcher,
+ * handler/value_matcher.dart:211-240); LIKE / NOT LIKE follow ValueMatcher.matchesLike
+ * (:318-331, :599-604): `%` = any run of code units, `_` = exactly one, neither matches a
+ * line terminator (\n \r U+2028 U+2029: the pattern becomes a RegExp without dotAll),
+ * everything else is literal (no escape character), whole-string, case-sensitive, false on
+ * NULL for both LIKE and NOT LIKE. The other operators behave as on numeric columns.
+ * Every distinct string is tested once per text leaf on the GPU (dict_match_kernel), the
+ * row pass looks the row's code up in the resulting bitmap. ---- */
+/* strings: row i = units [offsets[i], offsets[i + 1]) — n + 1 offsets, in code units,
+ * absolute into `units`. is_null as for tsc_index_column_append (a NULL row's range is
+ * ignored). HOST buffers. Values are stored as given (the host applies the field's
+ * convertValue, i.e. trim(), model/table_schema.dart:1421-1442, before calling). */
+int32_t tsc_index_column_append_text(uint64_t handle, uint32_t column_id,
+                                     uint64_t first_node_id, const uint16_t *units,
+                                     const uint64_t *offsets, const uint8_t *is_null,
+                                     uint64_t n);
+/* tsc_index_filter_where for programs with leaves on text columns. Text operand t of the
+ * program is text_units [text_offsets[t], text_offsets[t + 1]) (n_texts + 1 offsets,
+ * <= 4096 operands). A leaf on a text column names its operand(s) by index: i_lo (and
+ * i_hi for BETWEEN's end); the in_args entries of its IN / NOT IN list are operand
+ * indices (uint64). LIKE / NOT LIKE on a numeric column are rejected
+ * (TSC_ERR_UNSUPPORTED). */
+int32_t tsc_index_filter_where_text(uint64_t handle, const tsc_where_op *ops, uint32_t n_ops,
+                                    const void *in_args, uint32_t n_in_args,
+                                    const uint16_t *text_units, const uint64_t *text_offsets,
+                                    uint32_t n_texts, uint64_t *out_matched);
 
 /* ---- search ---- */
 /* queries: [nq, dims] fp32, already padded/truncated to dims and, for cosine,
@@ -389,6 +421,19 @@ int32_t tsc_selftest_where(const tsc_where_op *ops, uint32_t n_ops, const void *
                            uint32_t n_in_args, uint32_t n_cols, const uint32_t *col_ids,
                            const uint8_t *col_types, const uint64_t *col_values,
                            const uint8_t *col_is_null, uint64_t n_rows, uint8_t *out_match);
+/* the same with text columns: row r of text column c is row_units
+ * [row_offsets[c * (n_rows + 1) + r], row_offsets[c * (n_rows + 1) + r + 1]) (entries of
+ * numeric columns are ignored, as are col_values of text columns). Runs the library's own
+ * dictionary builder, the per-string test dict_match_kernel shares (text_leaf_match) and
+ * the row evaluator — on the host, for the CPU test tier. */
+int32_t tsc_selftest_where_text(const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
+                                uint32_t n_in_args, const uint16_t *text_units,
+                                const uint64_t *text_offsets, uint32_t n_texts,
+                                uint32_t n_cols, const uint32_t *col_ids,
+                                const uint8_t *col_types, const uint64_t *col_values,
+                                const uint8_t *col_is_null, const uint16_t *row_units,
+                                const uint64_t *row_offsets, uint64_t n_rows,
+                                uint8_t *out_match);
 
 /* self-test hooks (no GPU, not fallbacks): the host-side query preparation (_toFloat32 +
  * _normalizeFloat32) and score mapping (_distanceToScore) of tsc_vector_search. */

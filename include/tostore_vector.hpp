@@ -41,7 +41,7 @@ namespace tostore {
 enum class VectorPrecision : uint8_t { float64 = 0, float32 = 1, int8 = 2 };        // enum order :2481-2498
 enum class VectorDistanceMetric : uint8_t { l2 = 0, innerProduct = 1, cosine = 2 }; // enum order :2511-2531
 enum class DeviceDType : uint8_t { float32 = 0, bfloat16 = 1, float16 = 2 };         // new: storage in HBM
-enum class DataType : uint8_t { integer = 0, doubleType = 1 };                       // attribute fields
+enum class DataType : uint8_t { integer = 0, doubleType = 1, text = 2 };             // attribute fields
 
 struct TscError : std::runtime_error {
   int32_t status;
@@ -75,8 +75,56 @@ struct VectorSearchResult {
   double score = 0.0;
 };
 
-// ---- QueryCondition: builds the postfix program tsc_index_filter_where evaluates ----------
-using Value = std::variant<std::monostate, int64_t, double>;   // monostate = null
+// ---- text values: UTF-8 at this layer, UTF-16 code units (a Dart String's own form) below ----
+inline std::u16string utf8ToUtf16(const std::string &s) {
+  std::u16string out;
+  for (size_t i = 0; i < s.size();) {
+    const unsigned char c = (unsigned char)s[i];
+    uint32_t cp = 0xFFFD;
+    size_t n = 1;
+    if (c < 0x80) cp = c;
+    else if ((c & 0xE0) == 0xC0) { cp = c & 0x1F; n = 2; }
+    else if ((c & 0xF0) == 0xE0) { cp = c & 0x0F; n = 3; }
+    else if ((c & 0xF8) == 0xF0) { cp = c & 0x07; n = 4; }
+    if (i + n > s.size()) { cp = 0xFFFD; n = 1; }
+    for (size_t j = 1; j < n; j++) {
+      const unsigned char d = (unsigned char)s[i + j];
+      if ((d & 0xC0) != 0x80) { cp = 0xFFFD; n = 1; break; }
+      cp = (cp << 6) | (d & 0x3F);
+    }
+    i += n;
+    if (cp >= 0x10000) {
+      cp -= 0x10000;
+      out.push_back((char16_t)(0xD800 + (cp >> 10)));
+      out.push_back((char16_t)(0xDC00 + (cp & 0x3FF)));
+    } else {
+      out.push_back((char16_t)cp);
+    }
+  }
+  return out;
+}
+// String.trim(): Unicode White_Space plus the byte-order mark
+inline std::u16string dartTrim(const std::u16string &s) {
+  auto ws = [](char16_t c) {
+    return (c >= 0x09 && c <= 0x0D) || c == 0x20 || c == 0x85 || c == 0xA0 || c == 0x1680 ||
+           (c >= 0x2000 && c <= 0x200A) || c == 0x2028 || c == 0x2029 || c == 0x202F || c == 0x205F ||
+           c == 0x3000 || c == 0xFEFF;
+  };
+  size_t a = 0, b = s.size();
+  while (a < b && ws(s[a])) a++;
+  while (b > a && ws(s[b - 1])) b--;
+  return s.substr(a, b - a);
+}
+
+// ---- QueryCondition: builds the postfix program tsc_index_filter_where[_text] evaluates ----
+using Value = std::variant<std::monostate, int64_t, double, std::string>;   // monostate = null; string = UTF-8
+
+// convertValue for DataType.text (table_schema.dart:1421-1442): toString().trim()
+inline std::u16string convertText(const Value &v) {
+  if (std::holds_alternative<std::string>(v)) return dartTrim(utf8ToUtf16(std::get<std::string>(v)));
+  if (std::holds_alternative<int64_t>(v)) return utf8ToUtf16(std::to_string(std::get<int64_t>(v)));
+  throw std::invalid_argument("text field operand must be a string or an integer");
+}
 
 class QueryCondition {
  public:
@@ -113,6 +161,14 @@ class QueryCondition {
   struct Program {
     std::vector<tsc_where_op> ops;
     std::vector<uint64_t> in_args;   // raw 8-byte values typed like the leaf's column
+    std::u16string text_units;       // operand pool of the text leaves ...
+    std::vector<uint64_t> text_offsets{0};   // ... operand t = units [offsets[t], offsets[t + 1])
+    uint32_t n_texts() const { return (uint32_t)text_offsets.size() - 1; }
+    int64_t addText(const std::u16string &s) {
+      text_units += s;
+      text_offsets.push_back(text_units.size());
+      return (int64_t)text_offsets.size() - 2;
+    }
   };
   // columns: field name -> (column id, type). Operands are converted to the field's type
   // exactly like FieldSchema.convertValue (table_schema.dart:1371-1421): integer fields
@@ -161,8 +217,10 @@ class QueryCondition {
     if (r >= 9223372036854775808.0) return x >= 0 ? INT64_MAX : INT64_MIN;
     return x >= 0 ? (int64_t)r : -(int64_t)r;
   }
-  static void setOperand(tsc_where_op *o, DataType t, const Value &v, bool hi) {
-    if (t == DataType::integer) {
+  static void setOperand(tsc_where_op *o, DataType t, const Value &v, bool hi, Program *p) {
+    if (t == DataType::text) {
+      (hi ? o->i_hi : o->i_lo) = p->addText(convertText(v));
+    } else if (t == DataType::integer) {
       const int64_t x = std::holds_alternative<double>(v) ? dartRound(std::get<double>(v)) : std::get<int64_t>(v);
       (hi ? o->i_hi : o->i_lo) = x;
     } else {
@@ -191,15 +249,15 @@ class QueryCondition {
         }
       } else {
         o.op = s->second;
-        setOperand(&o, t, leaf.args[0], false);
+        setOperand(&o, t, leaf.args[0], false, p);
       }
     } else if (leaf.op == "BETWEEN") {
       if (leaf.args.size() != 2 || null0 || std::holds_alternative<std::monostate>(leaf.args[1])) {
         o.op = TSC_OP_FALSE;
       } else {
         o.op = TSC_OP_BETWEEN;
-        setOperand(&o, t, leaf.args[0], false);
-        setOperand(&o, t, leaf.args[1], true);
+        setOperand(&o, t, leaf.args[0], false, p);
+        setOperand(&o, t, leaf.args[1], true, p);
       }
     } else if (leaf.op == "IN" || leaf.op == "NOT IN") {
       o.op = leaf.op == "IN" ? TSC_OP_IN : TSC_OP_NOT_IN;
@@ -207,9 +265,9 @@ class QueryCondition {
       for (auto &v : leaf.args) {
         if (std::holds_alternative<std::monostate>(v)) continue;   // never equal to a non-null value
         tsc_where_op tmp = node(TSC_W_LEAF, 0);
-        setOperand(&tmp, t, v, false);
+        setOperand(&tmp, t, v, false, p);
         uint64_t raw;
-        if (t == DataType::integer) std::memcpy(&raw, &tmp.i_lo, 8);
+        if (t != DataType::doubleType) std::memcpy(&raw, &tmp.i_lo, 8);   // text: the operand's pool index
         else std::memcpy(&raw, &tmp.f_lo, 8);
         p->in_args.push_back(raw);
         o.n++;
@@ -218,8 +276,16 @@ class QueryCondition {
       o.op = null0 ? TSC_OP_IS_NULL : TSC_OP_FALSE;
     } else if (leaf.op == "IS NOT") {
       o.op = null0 ? TSC_OP_IS_NOT_NULL : TSC_OP_FALSE;
+    } else if (leaf.op == "LIKE" || leaf.op == "NOT LIKE") {   // value_matcher.dart:599-604
+      if (t != DataType::text) throw std::invalid_argument(leaf.op + " on a numeric field has no columnar GPU form");
+      if (null0) {
+        o.op = TSC_OP_FALSE;
+      } else {
+        o.op = leaf.op == "LIKE" ? TSC_OP_LIKE : TSC_OP_NOT_LIKE;
+        setOperand(&o, t, leaf.args[0], false, p);
+      }
     } else {
-      throw std::invalid_argument("operator '" + leaf.op + "' has no columnar GPU form (numeric fields only)");
+      throw std::invalid_argument("operator '" + leaf.op + "' has no columnar GPU form");
     }
     p->ops.push_back(o);
   }
@@ -229,7 +295,7 @@ class QueryCondition {
 struct Record {
   std::string id;                          // primary key ("" -> skipped, like prepareVectorBatchChunk)
   std::optional<VectorData> embedding;     // absent -> skipped
-  std::map<std::string, Value> fields;     // attribute fields (numeric); absent / monostate -> NULL
+  std::map<std::string, Value> fields;     // attribute fields; absent / monostate -> NULL
 };
 
 // ---- the slice of ToStore / VectorIndexManager that serves vectorSearch --------------------
@@ -250,7 +316,8 @@ class GpuVectorStore {
   GpuVectorStore &operator=(const GpuVectorStore &) = delete;
 
   // TableSchema vector field + IndexSchema(type: IndexType.vector). attributeFields (new,
-  // additive): numeric table fields mirrored column-wise on the GPU for vectorSearch(where:).
+  // additive): integer / double / text table fields mirrored column-wise on the GPU (text:
+  // dictionary-encoded) for vectorSearch(where:).
   void createVectorIndex(const std::string &tableName, const std::string &fieldName,
                          const VectorFieldConfig &fieldConfig, const VectorIndexConfig &indexConfig = {},
                          const std::map<std::string, DataType> &attributeFields = {}) {
@@ -316,6 +383,22 @@ class GpuVectorStore {
       for (auto &a : ix.attributes) {
         std::vector<uint64_t> vals(kept.size(), 0);
         std::vector<uint8_t> nulls(kept.size(), 1);
+        if (a.second.second == DataType::text) {   // stored like convertValue stores it: trimmed
+          std::u16string units;
+          std::vector<uint64_t> toffs{0};
+          for (size_t i = 0; i < kept.size(); i++) {
+            auto f = kept[i]->fields.find(a.first);
+            if (f != kept[i]->fields.end() && !std::holds_alternative<std::monostate>(f->second)) {
+              nulls[i] = 0;
+              units += convertText(f->second);
+            }
+            toffs.push_back(units.size());
+          }
+          check(tsc_index_column_append_text(ix.handle, a.second.first, start, (const uint16_t *)units.data(),
+                                             toffs.data(), nulls.data(), kept.size()),
+                "tsc_index_column_append_text");
+          continue;
+        }
         for (size_t i = 0; i < kept.size(); i++) {
           auto f = kept[i]->fields.find(a.first);
           if (f == kept[i]->fields.end() || std::holds_alternative<std::monostate>(f->second)) continue;
@@ -353,6 +436,13 @@ class GpuVectorStore {
         auto f = r.fields.find(a.first);
         if (f == r.fields.end()) continue;
         const uint8_t isnull = std::holds_alternative<std::monostate>(f->second) ? 1 : 0;
+        if (a.second.second == DataType::text) {
+          const std::u16string units = isnull ? std::u16string() : convertText(f->second);
+          const uint64_t toffs[2] = {0, units.size()};
+          check(tsc_index_column_append_text(ix.handle, a.second.first, nid, (const uint16_t *)units.data(), toffs,
+                                             &isnull, 1), "tsc_index_column_append_text");
+          continue;
+        }
         const uint64_t raw = isnull ? 0 : rawValue(f->second, a.second.second);
         check(tsc_index_column_append(ix.handle, a.second.first, nid, &raw, &isnull, 1), "tsc_index_column_append");
       }
@@ -424,8 +514,14 @@ class GpuVectorStore {
     if (where) {
       std::map<std::string, std::pair<uint32_t, DataType>> cols(ix->attributes.begin(), ix->attributes.end());
       auto prog = where->compile(cols);
-      check(tsc_index_filter_where(ix->handle, prog.ops.data(), (uint32_t)prog.ops.size(), prog.in_args.data(),
-                                   (uint32_t)prog.in_args.size(), nullptr), "tsc_index_filter_where");
+      if (prog.n_texts())
+        check(tsc_index_filter_where_text(ix->handle, prog.ops.data(), (uint32_t)prog.ops.size(),
+                                          prog.in_args.data(), (uint32_t)prog.in_args.size(),
+                                          (const uint16_t *)prog.text_units.data(), prog.text_offsets.data(),
+                                          prog.n_texts(), nullptr), "tsc_index_filter_where_text");
+      else
+        check(tsc_index_filter_where(ix->handle, prog.ops.data(), (uint32_t)prog.ops.size(), prog.in_args.data(),
+                                     (uint32_t)prog.in_args.size(), nullptr), "tsc_index_filter_where");
       ix->whereActive = true;
     } else if (ix->whereActive) {
       check(tsc_index_set_filter(ix->handle, nullptr, 0), "tsc_index_set_filter");

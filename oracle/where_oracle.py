@@ -1,5 +1,5 @@
-"""CPU restatement of the reference's structured-condition evaluation for numeric
-fields — TEST INFRASTRUCTURE ONLY (checker for tsc_index_filter_where; never imported
+"""CPU restatement of the reference's structured-condition evaluation for integer,
+double and text fields — TEST INFRASTRUCTURE ONLY (checker for tsc_index_filter_where; never imported
 by the product path).
 
 Follows, relative to /root/reference/lib/src:
@@ -13,6 +13,12 @@ Follows, relative to /root/reference/lib/src:
   * operators        handler/value_matcher.dart:570-612 (_evaluateOperator)
   * numeric order    handler/value_matcher.dart:150-174 -> Dart num.compareTo
                      (-0.0 < 0.0; NaN above everything and equal to itself)
+  * text fields      model/table_schema.dart:1421-1442 (convertValue: toString().trim()),
+                     handler/value_matcher.dart:211-240 (String.compareTo = UTF-16 code-unit
+                     order), :318-331 (matchesLike: LIKE pattern -> anchored RegExp, `%` ->
+                     `.*`, `_` -> `.`, everything else escaped; `.` of a RegExp without dotAll
+                     / unicode is one code unit other than \n \r U+2028 U+2029), :599-604
+                     (LIKE and NOT LIKE are both false on NULL / a non-string pattern)
 Parity is unpinned by the reference (it has no test for any of this and no WHERE for
 vectors); pinned here by hand-written known answers in tests/test_where.py.
 
@@ -22,6 +28,7 @@ driven from column arrays.
 from __future__ import annotations
 
 import math
+import re
 from typing import Dict, List, Optional, Sequence
 
 INT64_MIN, INT64_MAX = -(1 << 63), (1 << 63) - 1
@@ -56,10 +63,53 @@ def dart_round(x: float) -> int:
     return max(INT64_MIN, min(INT64_MAX, v))
 
 
+# ---- Dart strings ----------------------------------------------------------------------
+_TRIM = set([0x09, 0x0A, 0x0B, 0x0C, 0x0D, 0x20, 0x85, 0xA0, 0x1680, 0x2028, 0x2029, 0x202F,
+             0x205F, 0x3000, 0xFEFF]) | set(range(0x2000, 0x200B))
+_NOT_LT = "[^\n\r\u2028\u2029]"
+
+
+def code_units(s: str) -> List[int]:
+    """String.codeUnits (UTF-16; lone surrogates pass through)."""
+    b = s.encode("utf-16-le", "surrogatepass")
+    return [b[i] | (b[i + 1] << 8) for i in range(0, len(b), 2)]
+
+
+def dart_string_compare(a: str, b: str) -> int:
+    """String.compareTo: lexicographic over UTF-16 code units."""
+    ua, ub = code_units(a), code_units(b)
+    return -1 if ua < ub else (1 if ua > ub else 0)
+
+
+def dart_trim(s: str) -> str:
+    u = list(s)
+    while u and ord(u[0]) in _TRIM:
+        u.pop(0)
+    while u and ord(u[-1]) in _TRIM:
+        u.pop()
+    return "".join(u)
+
+
+def matches_like(value: str, pattern: str) -> bool:
+    """ValueMatcher.matchesLike (value_matcher.dart:318-331) through Python's regex engine,
+    one regex character per UTF-16 code unit."""
+    rx = "".join(_NOT_LT + "*" if c == 0x25 else _NOT_LT if c == 0x5F else re.escape(chr(c))
+                 for c in code_units(pattern))
+    return re.fullmatch(rx, "".join(chr(c) for c in code_units(value)), flags=re.S) is not None
+
+
 def convert_value(v, col_type: str):
-    """FieldSchema.convertValue for DataType.integer / DataType.double operands."""
+    """FieldSchema.convertValue for DataType.integer / double / text operands."""
     if v is None:
         return None
+    if col_type == "text":
+        if isinstance(v, bool):
+            v = "true" if v else "false"
+        elif isinstance(v, int):
+            v = str(v)
+        if not isinstance(v, str):
+            raise TypeError(f"unsupported operand {v!r} for a text field")
+        return dart_trim(v)
     if isinstance(v, bool):
         v = 1 if v else 0
     if col_type == "i64":
@@ -79,6 +129,8 @@ def _matcher(a, b) -> int:
     """Nullable numeric matcher (value_matcher.dart:160-174)."""
     if a is None or b is None:
         return 0 if a is b else (-1 if a is None else 1)
+    if isinstance(a, str) and isinstance(b, str):      # text matcher (:225-240)
+        return dart_string_compare(a, b)
     return dart_compare(a, b)
 
 
@@ -109,11 +161,19 @@ def evaluate_operator(value, op: str, cmp):
         if value is None or not isinstance(cmp, dict) or "start" not in cmp or "end" not in cmp:
             return False
         return _matcher(value, cmp["start"]) >= 0 and _matcher(value, cmp["end"]) <= 0
+    if op == "LIKE":
+        if value is None or not isinstance(cmp, str):
+            return False
+        return matches_like(str(value), cmp)
+    if op == "NOT LIKE":
+        if value is None or not isinstance(cmp, str):
+            return False
+        return not matches_like(str(value), cmp)
     if op == "IS":
         return value is None and cmp is None
     if op == "IS NOT":
         return value is not None and cmp is None
-    raise ValueError(f"operator {op!r} is not a numeric operator")
+    raise ValueError(f"unknown operator {op!r}")
 
 
 def normalize_condition(cond, col_types: Dict[str, str]):
@@ -178,7 +238,8 @@ def evaluate_columns(cond, columns: Dict[str, Sequence], col_types: Dict[str, st
         for name, vals in columns.items():
             v = vals[r] if r < len(vals) else None
             if v is not None:
-                v = int(v) if col_types[name] == "i64" else float(v)
+                t = col_types[name]
+                v = int(v) if t == "i64" else (str(v) if t == "text" else float(v))
             rec[name] = v
         out.append(match_record(norm, rec) if norm else True)
     return out

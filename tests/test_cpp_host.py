@@ -15,8 +15,10 @@ from oracle import where_oracle as wo
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NAN, INF = math.nan, math.inf
 COLS = {"price": [5, None, 30, 31, -1, 7, 7, 100, None, 0, 19, 20],
-        "rating": [0.0, -0.0, NAN, None, 2.5, 4.5, -4.5, INF, -INF, 1.0, None, 3.0]}
-TYPES = {"price": "i64", "rating": "f64"}
+        "rating": [0.0, -0.0, NAN, None, 2.5, 4.5, -4.5, INF, -INF, 1.0, None, 3.0],
+        "name": ["alice", "Alice", None, "bob", "al", "alice\nsmith", "a%b", "zo\u00eb", "\U0001F600 grin", "",
+                 "bobby", "a_b"]}
+TYPES = {"price": "i64", "rating": "f64", "name": "text"}
 # the same conditions examples/vector_store_demo.cc builds with the C++ builder, in map form
 CONDITIONS = {
     "empty": {},
@@ -34,6 +36,15 @@ CONDITIONS = {
     "or_groups": {"OR": [{"price": {"<": 0}},
                          {"AND": [{"rating": {">=": 4}}, {"price": {"IS NOT": None}}]},
                          {"price": {"=": 0}}]},
+    "name_eq": {"name": {"=": "  alice "}},
+    "name_ne": {"name": {"!=": "bob"}},
+    "name_gt": {"name": {">": "b"}},
+    "name_in": {"name": {"IN": ["bob", "zo\u00eb", ""]}},
+    "name_like_prefix": {"name": {"LIKE": "al%"}},
+    "name_like_any": {"name": {"LIKE": "%"}},
+    "name_like_one": {"name": {"LIKE": "a_b"}},
+    "name_like_astral": {"name": {"LIKE": "__ grin"}},
+    "name_not_like_and_price": {"AND": [{"name": {"NOT LIKE": "%b%"}}, {"price": {">=": 7}}]},
 }
 
 

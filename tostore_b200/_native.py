@@ -27,6 +27,7 @@ EXPORTS = (
     "tsc_stats_get", "tsc_stats_reset", "tsc_index_device_rows", "tsc_selftest_crc32",
     "tsc_debug_gemm_keys",
     "tsc_index_column_create", "tsc_index_column_append", "tsc_index_filter_where",
+    "tsc_index_column_append_text", "tsc_index_filter_where_text", "tsc_selftest_where_text",
     "tsc_ngh_read_meta", "tsc_index_load_ngh", "tsc_selftest_ngh_walk",
     "tsc_selftest_where", "tsc_selftest_host_index", "tsc_selftest_pk_assemble",
     "tsc_index_set_primary_keys", "tsc_index_get_primary_key", "tsc_vector_search_pk",
@@ -136,6 +137,10 @@ def lib():
     L.tsc_index_column_create.argtypes = [u64, u32, C.c_uint8]
     L.tsc_index_column_append.argtypes = [u64, u32, u64, vp, vp, u64]
     L.tsc_index_filter_where.argtypes = [u64, vp, u32, vp, u32, C.POINTER(u64)]
+    L.tsc_index_column_append_text.argtypes = [u64, u32, u64, vp, vp, vp, u64]
+    L.tsc_index_filter_where_text.argtypes = [u64, vp, u32, vp, u32, vp, vp, u32, C.POINTER(u64)]
+    L.tsc_selftest_where_text.argtypes = [vp, u32, vp, u32, vp, vp, u32, u32, vp, vp, vp, vp, vp,
+                                          vp, u64, vp]
     L.tsc_ngh_read_meta.argtypes = [C.c_char_p, C.POINTER(NghInfo)]
     L.tsc_index_load_ngh.argtypes = [u64, C.c_char_p, u32, C.POINTER(NghInfo)]
     L.tsc_selftest_ngh_walk.argtypes = [C.c_char_p, u32, u64, u64, u32, vp, vp, vp, u32,

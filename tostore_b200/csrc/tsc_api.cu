@@ -249,9 +249,14 @@ void free_index(Index *ix) {
   cudaFree(ix->d_xbuf);
   if (ix->h_xstatus) cudaFreeHost(ix->h_xstatus);
   cudaFree(ix->d_where_args);
+  cudaFree(ix->d_where_text);
   for (auto &c : ix->columns) {
     cudaFree(c.d_values);
     cudaFree(c.d_null);
+    if (c.dict) {
+      cudaFree(c.dict->d_units);
+      cudaFree(c.dict->d_offs);
+    }
   }
   cudaFreeHost(ix->h_queries);
   cudaFreeHost(ix->h_out_block);
@@ -523,7 +528,14 @@ int32_t ix_clear(Index *ix) {
   ix->max_norm2 = 0.0f;
   ix->deleted_rows = 0;
   ix->has_deleted = ix->has_filter = ix->live_dirty = false;
-  for (auto &c : ix->columns) c.rows = 0;
+  for (auto &c : ix->columns) {
+    c.rows = 0;
+    if (c.dict) {   // device arrays are kept for the next strings
+      c.dict->codes.clear();
+      c.dict->n_codes = 0;
+      c.dict->n_units = 0;
+    }
+  }
   ix->pk_off.clear();
   ix->pk_len.clear();
   ix->pk_arena.clear();

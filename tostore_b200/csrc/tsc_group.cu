@@ -289,12 +289,28 @@ int32_t grp_column_append(Group &g, uint32_t column_id, uint64_t first_node_id, 
   });
 }
 
+// every shard keeps its own dictionary of the strings of ITS rows
+int32_t grp_column_append_text(Group &g, uint32_t column_id, uint64_t first_node_id,
+                               const uint16_t *units, const uint64_t *offsets,
+                               const uint8_t *is_null, uint64_t n) {
+  if (n == 0) return TSC_OK;
+  if (!offsets) {
+    set_error("column_append_text: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  return for_shards(g, first_node_id, n, [&](Index *ix, uint64_t lo, uint64_t hi) {
+    const uint64_t o = lo - first_node_id;
+    return ix_column_append_text(ix, column_id, lo, units, offsets + o,
+                                 is_null ? is_null + o : nullptr, hi - lo);
+  });
+}
+
 int32_t grp_filter_where(Group &g, const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
-                         uint32_t n_in_args, uint64_t *out_matched) {
+                         uint32_t n_in_args, const WhereTexts &texts, uint64_t *out_matched) {
   uint64_t total = 0;
   for (auto &s : g.shards) {
     uint64_t m = 0;
-    int32_t rc = ix_filter_where(s.get(), ops, n_ops, in_args, n_in_args, &m);
+    int32_t rc = ix_filter_where(s.get(), ops, n_ops, in_args, n_in_args, texts, &m);
     if (rc != TSC_OK) return rc;
     total += m;
   }

@@ -10,6 +10,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/tostore_cuda.h"
@@ -41,12 +42,23 @@ struct ScanConfig {
 };
 
 // numeric table field kept column-wise next to the embedding column (tsc_where.cuh)
+// dictionary of a TSC_COL_TEXT column: every distinct string once, UTF-16 code units
+struct TextDict {
+  std::unordered_map<std::u16string, uint32_t> codes;   // string -> code (host, for appends)
+  uint64_t n_units = 0;             // code units stored so far
+  uint32_t n_codes = 0;
+  uint16_t *d_units = nullptr;      // [units_cap] all strings back to back
+  uint64_t *d_offs = nullptr;       // [codes_cap + 1] string c = units [offs[c], offs[c + 1])
+  uint64_t units_cap = 0, codes_cap = 0;
+};
+
 struct AttrColumn {
   uint32_t id = 0;
-  uint8_t type = 0;              // TSC_COL_I64 / TSC_COL_F64
-  uint64_t *d_values = nullptr;  // [capacity] raw 8-byte values
+  uint8_t type = 0;              // TSC_COL_I64 / TSC_COL_F64 / TSC_COL_TEXT
+  uint64_t *d_values = nullptr;  // [capacity] raw 8-byte values (text: the dictionary code)
   uint32_t *d_null = nullptr;    // [mask_words] bit r = row r is NULL (allocated on first NULL)
   uint64_t rows = 0;             // rows appended so far
+  std::shared_ptr<TextDict> dict;   // text columns only
 };
 
 struct Index {
@@ -167,6 +179,8 @@ struct Index {
   std::vector<AttrColumn> columns;
   uint64_t *d_where_args = nullptr;   // IN-list keys
   size_t where_args_cap = 0;
+  uint8_t *d_where_text = nullptr;    // text leaves: operand pool, IN-list pairs, bitmaps over codes
+  size_t where_text_cap = 0;
 
   // sharding
   void *nccl_comm = nullptr;
@@ -257,8 +271,17 @@ int32_t ix_stats_reset(Index *ix);
 int32_t ix_column_create(Index *ix, uint32_t column_id, uint8_t col_type);
 int32_t ix_column_append(Index *ix, uint32_t column_id, uint64_t first_node_id, const void *values,
                          const uint8_t *is_null, uint64_t n);
+int32_t ix_column_append_text(Index *ix, uint32_t column_id, uint64_t first_node_id,
+                              const uint16_t *units, const uint64_t *offsets,
+                              const uint8_t *is_null, uint64_t n);
+// text operands of a program: string t = text_units [text_offsets[t], text_offsets[t + 1])
+struct WhereTexts {
+  const uint16_t *units = nullptr;
+  const uint64_t *offsets = nullptr;
+  uint32_t n = 0;
+};
 int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
-                        uint32_t n_in_args, uint64_t *out_matched);
+                        uint32_t n_in_args, const WhereTexts &texts, uint64_t *out_matched);
 int32_t ix_set_primary_keys(Index *ix, uint64_t first_node_id, const uint8_t *utf8,
                             const uint64_t *offsets, uint64_t n);
 int32_t ix_get_primary_key(Index *ix, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
@@ -293,8 +316,11 @@ int32_t grp_stats_reset(Group &g);
 int32_t grp_column_create(Group &g, uint32_t column_id, uint8_t col_type);
 int32_t grp_column_append(Group &g, uint32_t column_id, uint64_t first_node_id, const void *values,
                           const uint8_t *is_null, uint64_t n);
+int32_t grp_column_append_text(Group &g, uint32_t column_id, uint64_t first_node_id,
+                               const uint16_t *units, const uint64_t *offsets,
+                               const uint8_t *is_null, uint64_t n);
 int32_t grp_filter_where(Group &g, const tsc_where_op *ops, uint32_t n_ops, const void *in_args,
-                         uint32_t n_in_args, uint64_t *out_matched);
+                         uint32_t n_in_args, const WhereTexts &texts, uint64_t *out_matched);
 int32_t grp_set_primary_keys(Group &g, uint64_t first_node_id, const uint8_t *utf8,
                              const uint64_t *offsets, uint64_t n);
 int32_t grp_get_primary_key(Group &g, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,

@@ -16,6 +16,14 @@
 //     -0.0 < 0.0, NaN is above +inf and equal to itself
 // Both column types are mapped to uint64 keys whose unsigned order is that order, so
 // one kernel serves int and double fields; operands are converted on the host.
+//
+// TEXT fields (DataType.text) are dictionary-encoded: the distinct strings of a column live
+// once in HBM as UTF-16 code units (Dart's own string form, so String.compareTo
+// (:211-240) is a code-unit comparison and LIKE's `_` is one code unit), rows hold the
+// 32-bit code. A text leaf is evaluated in two steps, both on the GPU: dict_match_kernel
+// tests every DISTINCT string once (comparison / IN / BETWEEN / LIKE, :570-604 and
+// matchesLike :318-331) into a bitmap over codes, and the row pass turns a row's code into
+// that bit — a 12.5M-row column with 1000 distinct values costs 1000 string tests.
 #pragma once
 
 #include "tsc_common.cuh"
@@ -25,8 +33,10 @@ namespace tsc {
 enum : uint8_t { kWLeaf = 0, kWAnd = 1, kWOr = 2 };
 enum : uint8_t {
   kOpEq = 0, kOpNe, kOpGt, kOpGe, kOpLt, kOpLe, kOpBetween, kOpIn, kOpNotIn, kOpIsNull,
-  kOpIsNotNull, kOpTrue, kOpFalse, kOpCount
+  kOpIsNotNull, kOpTrue, kOpFalse, kOpLike, kOpNotLike, kOpCount,
+  kOpDict = 32   // device form of every text leaf except IS [NOT] NULL: bit `code` of a bitmap
 };
+constexpr uint64_t kDictNeg = 1, kDictOnNull = 2;   // WhereDevOp::lo of a kOpDict leaf
 constexpr int kWhereMaxOps = 64;     // program length / bit-stack depth
 constexpr int kWhereMaxCols = 16;
 
@@ -35,7 +45,7 @@ struct WhereDevOp {        // 32 bytes, operands already in key space
   uint16_t n;              // children of AND / OR, or length of the IN list
   uint32_t col;            // slot in WhereCols
   uint64_t lo, hi;         // operand keys (BETWEEN: start, end)
-  uint32_t args_off;       // IN list: first key in `args`
+  uint32_t args_off;       // IN list: first key in `args`; kOpDict: first word in `dict_bits`
   uint32_t pad;
 };
 
@@ -67,9 +77,12 @@ __host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
 // evaluation code.
 // Stack = uint32_t for programs of up to 32 steps (the bit-stack cannot get deeper than the
 // program is long; 64-bit shifts cost two instructions each), uint64_t otherwise.
-template <int U, class Stack, class Load>
+// TEXT: the program holds kOpDict leaves (numeric-only programs keep the instantiation the
+// round-2 measurements were made with).
+template <int U, class Stack, bool TEXT, class Load>
 __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &prog,
-                                                           const uint64_t *args, Load load,
+                                                           const uint64_t *args,
+                                                           const uint32_t *dict_bits, Load load,
                                                            bool (&out)[U]) {
   Stack stack[U];
   uint64_t key[U];
@@ -84,7 +97,7 @@ __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &p
   for (uint32_t i = 0; i < prog.n_ops; i++) {
     const WhereDevOp &op = prog.ops[i];
     if (op.kind == kWLeaf) {
-      if (op.op < kOpTrue && op.col != last_col) {
+      if ((op.op < kOpTrue || (TEXT && op.op == kOpDict)) && op.col != last_col) {
         last_col = op.col;
         load(op.col, key, isnull);
       }
@@ -94,7 +107,7 @@ __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &p
       // if-converted by the compiler into ~80 instructions per row and leaf: the kernel was
       // issue-bound at 21 % of HBM, profiles/r02_where_*.)
       uint64_t lo = op.lo, hi = op.lo;
-      bool neg = false, on_null = false, list = false;
+      bool neg = false, on_null = false, list = false, dict = false;
       switch (op.op) {
         case kOpEq: break;
         case kOpNe: neg = true; on_null = true; break;
@@ -108,6 +121,13 @@ __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &p
         case kOpIsNull: lo = 1; hi = 0; on_null = true; break;
         case kOpIsNotNull: lo = 0; hi = ~0ull; break;
         case kOpTrue: lo = 0; hi = ~0ull; on_null = true; break;
+        case kOpDict:
+          if (TEXT) {
+            dict = true;
+            neg = (op.lo & kDictNeg) != 0;
+            on_null = (op.lo & kDictOnNull) != 0;
+          }
+          break;
         default: lo = 1; hi = 0; break;
       }
 #pragma unroll
@@ -117,6 +137,10 @@ __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &p
         if (list) {
           in = false;
           for (uint32_t j = 0; j < op.n; j++) in |= (k == args[op.args_off + j]);
+        } else if (TEXT && dict) {
+          // the key's low 32 bits are the row's dictionary code; a NULL row holds no code
+          const uint32_t code = (uint32_t)k;
+          in = !isnull[u] && ((dict_bits[op.args_off + (code >> 5)] >> (code & 31)) & 1u);
         } else {
           in = k >= lo && k <= hi;
         }
@@ -138,24 +162,26 @@ __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &p
 #pragma unroll
   for (int u = 0; u < U; u++) out[u] = prog.n_ops == 0 || (stack[u] & 1);
 }
-template <int U, class Load>
+template <int U, bool TEXT, class Load>
 __host__ __device__ __forceinline__ void where_eval_rows(const WhereProgram &prog,
-                                                         const uint64_t *args, Load load,
+                                                         const uint64_t *args,
+                                                         const uint32_t *dict_bits, Load load,
                                                          bool (&out)[U]) {
-  if (prog.n_ops < 32) where_eval_rows_t<U, uint32_t>(prog, args, load, out);
-  else where_eval_rows_t<U, uint64_t>(prog, args, load, out);
+  if (prog.n_ops < 32) where_eval_rows_t<U, uint32_t, TEXT>(prog, args, dict_bits, load, out);
+  else where_eval_rows_t<U, uint64_t, TEXT>(prog, args, dict_bits, load, out);
 }
 
 // one row: `load(slot, key, isnull)`
 template <class Load>
 __host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog,
-                                                        const uint64_t *args, Load load) {
+                                                        const uint64_t *args,
+                                                        const uint32_t *dict_bits, Load load) {
   bool out[1];
-  where_eval_rows<1>(prog, args,
-                     [&](uint32_t c, uint64_t (&key)[1], bool (&isnull)[1]) {
-                       load(c, key[0], isnull[0]);
-                     },
-                     out);
+  where_eval_rows<1, true>(prog, args, dict_bits,
+                           [&](uint32_t c, uint64_t (&key)[1], bool (&isnull)[1]) {
+                             load(c, key[0], isnull[0]);
+                           },
+                           out);
   return out[0];
 }
 
@@ -165,10 +191,12 @@ __host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog
 // profiles/r02_first_call.log; L2 prefetching two steps ahead did not help.)
 // HBM traffic: 8 bytes per row per distinct column + 4 bytes per 32 rows written.
 constexpr int kWhereWords = 4;
+template <bool TEXT>
 __global__ void __launch_bounds__(256)
 where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_constant__ WhereCols cols,
-                  const uint64_t *__restrict__ args, uint64_t n_rows, uint32_t n_slots,
-                  uint32_t *__restrict__ out_bits, unsigned long long *__restrict__ matched) {
+                  const uint64_t *__restrict__ args, const uint32_t *__restrict__ dict_bits,
+                  uint64_t n_rows, uint32_t n_slots, uint32_t *__restrict__ out_bits,
+                  unsigned long long *__restrict__ matched) {
   (void)n_slots;
   const int lane = threadIdx.x & 31;
   const uint64_t n_words = (n_rows + 31) / 32;
@@ -179,8 +207,8 @@ where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_consta
        g += warps) {
     const uint64_t row0 = g * kWhereWords * 32 + lane;
     bool res[kWhereWords];
-    where_eval_rows<kWhereWords>(
-        prog, args,
+    where_eval_rows<kWhereWords, TEXT>(
+        prog, args, dict_bits,
         [&](uint32_t c, uint64_t (&key)[kWhereWords], bool (&isnull)[kWhereWords]) {
           // all loads first, no branch between them (rows past the end re-read the last row:
           // their result is masked below), then the conversions
@@ -231,6 +259,110 @@ __global__ void pack_null_bits_kernel(const uint8_t *__restrict__ is_null, uint6
     const uint32_t bit = 1u << (row & 31);
     if (is_null[i]) atomicOr(null_bits + (row >> 5), bit);
     else atomicAnd(null_bits + (row >> 5), ~bit);
+  }
+}
+
+// ---- text leaves ---------------------------------------------------------------------------
+// One text leaf as the dictionary pass sees it. Operands live in the program's operand pool
+// (UTF-16 code units); `list` holds (offset, length) pairs of an IN list.
+struct TextLeaf {
+  uint8_t op;              // kOpEq / kOpGt / kOpGe / kOpLt / kOpLe / kOpBetween / kOpIn / kOpLike
+  uint8_t pad[3];
+  uint32_t a_off, a_len;   // operand (BETWEEN: start; LIKE: pattern)
+  uint32_t b_off, b_len;   // BETWEEN: end
+  uint32_t list_off, n;    // IN: first pair in `list`, pairs
+  uint32_t bits_off;       // first word of this leaf's bitmap over codes
+};
+
+// Dart String.compareTo: lexicographic over UTF-16 code units, shorter prefix first
+__host__ __device__ __forceinline__ int text_compare(const uint16_t *a, uint32_t na,
+                                                     const uint16_t *b, uint32_t nb) {
+  const uint32_t n = na < nb ? na : nb;
+  for (uint32_t i = 0; i < n; i++)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+
+// what `.` of a Dart RegExp (no dotAll, no unicode flag) does NOT match
+__host__ __device__ __forceinline__ bool text_line_terminator(uint16_t c) {
+  return c == 0x000A || c == 0x000D || c == 0x2028 || c == 0x2029;
+}
+
+// ValueMatcher.matchesLike (value_matcher.dart:318-331): the pattern becomes the regular
+// expression ^...$ with `%` -> `.*`, `_` -> `.` and every other character literal (there is no
+// escape: a backslash is a literal backslash), matched against the whole string, case-sensitive.
+// `.` is one UTF-16 code unit other than a line terminator, so neither wildcard crosses a line
+// break. Iterative matcher with one backtrack point (the latest `%`): a `%` that would have to
+// absorb a line terminator fails the match — no earlier `%` could absorb it either.
+__host__ __device__ __forceinline__ bool text_like(const uint16_t *s, uint32_t n,
+                                                   const uint16_t *pat, uint32_t m) {
+  uint32_t si = 0, pi = 0, star_p = 0xFFFFFFFFu, star_s = 0;
+  while (si < n) {
+    if (pi < m && pat[pi] == (uint16_t)'%') {
+      star_p = pi++;
+      star_s = si;
+    } else if (pi < m && (pat[pi] == (uint16_t)'_' ? !text_line_terminator(s[si])
+                                                    : pat[pi] == s[si])) {
+      si++;
+      pi++;
+    } else if (star_p != 0xFFFFFFFFu) {
+      if (text_line_terminator(s[star_s])) return false;
+      si = ++star_s;
+      pi = star_p + 1;
+    } else {
+      return false;
+    }
+  }
+  while (pi < m && pat[pi] == (uint16_t)'%') pi++;
+  return pi == m;
+}
+
+// the positive predicate of a text leaf for one string ('!=', NOT IN and NOT LIKE negate it in
+// the row pass, where NULL handling lives)
+__host__ __device__ __forceinline__ bool text_leaf_match(const TextLeaf &lf, const uint16_t *s,
+                                                         uint32_t n, const uint16_t *pool,
+                                                         const uint2 *list) {
+  const uint16_t *a = pool + lf.a_off;
+  switch (lf.op) {
+    case kOpEq: return text_compare(s, n, a, lf.a_len) == 0;
+    case kOpGt: return text_compare(s, n, a, lf.a_len) > 0;
+    case kOpGe: return text_compare(s, n, a, lf.a_len) >= 0;
+    case kOpLt: return text_compare(s, n, a, lf.a_len) < 0;
+    case kOpLe: return text_compare(s, n, a, lf.a_len) <= 0;
+    case kOpBetween:
+      return text_compare(s, n, a, lf.a_len) >= 0 &&
+             text_compare(s, n, pool + lf.b_off, lf.b_len) <= 0;
+    case kOpIn:
+      for (uint32_t j = 0; j < lf.n; j++) {
+        const uint2 e = list[lf.list_off + j];
+        if (text_compare(s, n, pool + e.x, e.y) == 0) return true;
+      }
+      return false;
+    case kOpLike: return text_like(s, n, a, lf.a_len);
+    default: return false;
+  }
+}
+
+// One thread per distinct string of the column; a warp writes one word of the leaf's bitmap.
+// HBM traffic: the dictionary's bytes once per text leaf (strings are read front to back by
+// their own thread: neighbouring threads read neighbouring strings of the arena).
+__global__ void __launch_bounds__(256)
+dict_match_kernel(const __grid_constant__ TextLeaf leaf, const uint16_t *__restrict__ units,
+                  const uint64_t *__restrict__ offs, uint32_t n_codes,
+                  const uint16_t *__restrict__ pool, const uint2 *__restrict__ list,
+                  uint32_t *__restrict__ dict_bits) {
+  const uint32_t n_words = (n_codes + 31) / 32;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words; w += warps) {
+    const uint32_t code = w * 32 + lane;
+    bool r = false;
+    if (code < n_codes) {
+      const uint64_t o = offs[code];
+      r = text_leaf_match(leaf, units + o, (uint32_t)(offs[code + 1] - o), pool, list);
+    }
+    const unsigned bits = __ballot_sync(0xFFFFFFFFu, r);
+    if (lane == 0) dict_bits[leaf.bits_off + w] = bits;
   }
 }
 

@@ -137,7 +137,7 @@ class GpuVectorIndex:
 
     # -- structured WHERE prefilter (attribute columns, evaluated on the GPU) --------
     def column_create(self, column_id: int, col_type: int) -> None:
-        """col_type: where.COL_I64 / where.COL_F64."""
+        """col_type: where.COL_I64 / where.COL_F64 / where.COL_TEXT."""
         N.check(self._lib.tsc_index_column_create(self.handle, int(column_id), int(col_type)),
                 "tsc_index_column_create")
         self._col_types = getattr(self, "_col_types", {})
@@ -150,6 +150,8 @@ class GpuVectorIndex:
         t = getattr(self, "_col_types", {}).get(int(column_id))
         if t is None:
             raise KeyError(f"column {column_id} was not created on this index")
+        if t == 2:
+            return self._column_append_text(column_id, values, is_null, first_node_id)
         if is_null is None and isinstance(values, (list, tuple)) and any(v is None for v in values):
             is_null = np.array([v is None for v in values], dtype=bool)
             values = [0 if v is None else v for v in values]
@@ -168,14 +170,40 @@ class GpuVectorIndex:
         end = int(first_node_id) - self.first_node_id + vals.size
         self._col_rows[int(column_id)] = max(self._col_rows.get(int(column_id), 0), end)
 
+    def _column_append_text(self, column_id: int, values, is_null, first_node_id) -> None:
+        """values: strings (None = NULL), stored as their UTF-16 code units — a Dart String's
+        own form — through tsc_index_column_append_text."""
+        from .where import utf16_pool
+        values = list(values)
+        nulls = np.array([v is None for v in values], dtype=np.uint8)
+        if is_null is not None:
+            nulls |= np.ascontiguousarray(is_null, dtype=np.uint8) != 0
+        units, offsets = utf16_pool(["" if n else v for v, n in zip(values, nulls)])
+        if first_node_id is None:
+            self._col_rows = getattr(self, "_col_rows", {})
+            first_node_id = self.first_node_id + self._col_rows.get(int(column_id), 0)
+        N.check(self._lib.tsc_index_column_append_text(
+            self.handle, int(column_id), int(first_node_id), units.ctypes.data, offsets.ctypes.data,
+            nulls.ctypes.data if nulls.any() else None, len(values)), "tsc_index_column_append_text")
+        self._col_rows = getattr(self, "_col_rows", {})
+        end = int(first_node_id) - self.first_node_id + len(values)
+        self._col_rows[int(column_id)] = max(self._col_rows.get(int(column_id), 0), end)
+
     def filter_where(self, program) -> int:
         """Install the rows matching a compiled `where.WhereProgram` as the filter;
         returns how many rows passed."""
         ops, n_ops, raw, n_args = program.buffers()
         matched = C.c_uint64(0)
-        N.check(self._lib.tsc_index_filter_where(self.handle, C.cast(ops, C.c_void_p), n_ops,
-                                                 raw.ctypes.data, n_args, C.byref(matched)),
-                "tsc_index_filter_where")
+        if program.texts:
+            units, offsets = program.text_buffers()
+            N.check(self._lib.tsc_index_filter_where_text(
+                self.handle, C.cast(ops, C.c_void_p), n_ops, raw.ctypes.data, n_args,
+                units.ctypes.data, offsets.ctypes.data, len(program.texts), C.byref(matched)),
+                "tsc_index_filter_where_text")
+        else:
+            N.check(self._lib.tsc_index_filter_where(self.handle, C.cast(ops, C.c_void_p), n_ops,
+                                                     raw.ctypes.data, n_args, C.byref(matched)),
+                    "tsc_index_filter_where")
         return matched.value
 
     # -- search --------------------------------------------------------------------

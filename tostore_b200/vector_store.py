@@ -99,7 +99,7 @@ class _VectorIndex:
     engine: GpuVectorIndex
     nid2pk: List[Optional[str]] = field(default_factory=list)   # role of `__nid2pk`
     pk2nid: Dict[str, int] = field(default_factory=dict)        # role of `__pk2nid`
-    # numeric table fields mirrored column-wise on the GPU for WHERE: name -> (column id, type)
+    # table fields mirrored column-wise on the GPU for WHERE: name -> (column id, type)
     attributes: Dict[str, tuple] = field(default_factory=dict)
 
 
@@ -120,9 +120,9 @@ class GpuVectorStore:
                           attributeFields: Optional[Dict[str, str]] = None) -> None:
         """`TableSchema` vector field + `IndexSchema(type: IndexType.vector)`.
         Unlike the reference (no validation) bad dims raise.
-        attributeFields (new, additive): numeric fields of the table — name ->
-        'integer' | 'double' (DataType names, model/table_schema.dart) — kept column-wise
-        on the GPU so `vectorSearch(where=...)` can prefilter on them."""
+        attributeFields (new, additive): fields of the table — name -> 'integer' | 'double' |
+        'text' (DataType names, model/table_schema.dart) — kept column-wise on the GPU (text:
+        dictionary-encoded) so `vectorSearch(where=...)` can prefilter on them."""
         cfg = indexConfig or VectorIndexConfig()
         eng = GpuVectorIndex(fieldConfig.dimensions, int(cfg.distanceMetric),
                              capacity_rows=self._capacity, src_precision=1,
@@ -130,9 +130,10 @@ class GpuVectorStore:
                              k_max=self._k_max, nq_max=64)
         ix = _VectorIndex(tableName, fieldName, fieldConfig, cfg, eng)
         for cid, (name, dtype) in enumerate((attributeFields or {}).items()):
-            if dtype not in ("integer", "double"):
-                raise ValueError(f"attribute field {name!r}: only integer / double fields have a GPU column")
-            t = _where.COL_I64 if dtype == "integer" else _where.COL_F64
+            if dtype not in ("integer", "double", "text"):
+                raise ValueError(f"attribute field {name!r}: only integer / double / text fields "
+                                 "have a GPU column")
+            t = {"integer": _where.COL_I64, "double": _where.COL_F64, "text": _where.COL_TEXT}[dtype]
             eng.column_create(cid, t)
             ix.attributes[name] = (cid, t)
         self._indexes.setdefault(tableName, []).append(ix)

@@ -1,8 +1,8 @@
 """Structured WHERE prefilter: condition tree -> postfix program for
-`tsc_index_filter_where` (the GPU evaluates it over attribute columns, tsc_where.cuh).
+`tsc_index_filter_where[_text]` (the GPU evaluates it over attribute columns, tsc_where.cuh).
 
-Host mirror of the reference's condition handling for numeric fields (paths relative
-to /root/reference/lib/src):
+Host mirror of the reference's condition handling for integer / double / text fields (paths
+relative to /root/reference/lib/src):
   * `QueryCondition` map form (`{'AND': [...]}`, `{'OR': [...]}`, leaf
     `{field: {op: value}}` / `{field: value}`)      query/query_condition.dart:24-55, :486-520
   * operand normalisation to the field's type       query/query_condition.dart:743-815,
@@ -11,8 +11,14 @@ to /root/reference/lib/src):
 An operator map with several entries is an OR of them (value_matcher.dart:552-563);
 several fields in one leaf are an AND (:499-510).
 
+Text fields: operands go through `convertValue` for DataType.text — `toString().trim()`
+(model/table_schema.dart:1421-1442; this includes LIKE patterns, which the reference trims
+like any other operand) — and travel as UTF-16 code units, a Dart String's own form, so the
+GPU's comparisons are `String.compareTo` (value_matcher.dart:211-240) and LIKE is
+`ValueMatcher.matchesLike` (:318-331).
+
 The reference has no WHERE for `vectorSearch`; this is the additive prefilter of
-BASELINE config 5. Text operators (LIKE ...) have no columnar form here and raise.
+BASELINE config 5.
 """
 from __future__ import annotations
 
@@ -22,11 +28,11 @@ from typing import Dict, List, Tuple
 
 import numpy as np
 
-COL_I64, COL_F64 = 0, 1
+COL_I64, COL_F64, COL_TEXT = 0, 1, 2
 W_LEAF, W_AND, W_OR = 0, 1, 2
 (OP_EQ, OP_NE, OP_GT, OP_GE, OP_LT, OP_LE, OP_BETWEEN, OP_IN, OP_NOT_IN, OP_IS_NULL,
- OP_IS_NOT_NULL, OP_TRUE, OP_FALSE) = range(13)
-MAX_OPS, MAX_IN_ARGS = 64, 4096
+ OP_IS_NOT_NULL, OP_TRUE, OP_FALSE, OP_LIKE, OP_NOT_LIKE) = range(15)
+MAX_OPS, MAX_IN_ARGS, MAX_TEXTS = 64, 4096, 4096
 _INT64_MIN, _INT64_MAX = -(1 << 63), (1 << 63) - 1
 _SIMPLE = {"=": OP_EQ, "!=": OP_NE, "<>": OP_NE, ">": OP_GT, ">=": OP_GE, "<": OP_LT, "<=": OP_LE}
 
@@ -47,8 +53,53 @@ def _dart_round(x: float) -> int:
     return max(_INT64_MIN, min(_INT64_MAX, v))
 
 
+# String.trim(): Unicode White_Space plus the byte-order mark (dart:core String.trim)
+_DART_WS = frozenset([0x09, 0x0A, 0x0B, 0x0C, 0x0D, 0x20, 0x85, 0xA0, 0x1680, 0x2028, 0x2029,
+                      0x202F, 0x205F, 0x3000, 0xFEFF] + list(range(0x2000, 0x200B)))
+
+
+def dart_trim(s: str) -> str:
+    a, b = 0, len(s)
+    while a < b and ord(s[a]) in _DART_WS:
+        a += 1
+    while b > a and ord(s[b - 1]) in _DART_WS:
+        b -= 1
+    return s[a:b]
+
+
+def convert_text(v) -> str:
+    """`convertValue` for DataType.text (table_schema.dart:1421-1442): toString().trim()."""
+    if isinstance(v, (bool, np.bool_)):
+        v = "true" if v else "false"
+    elif isinstance(v, (int, np.integer)):
+        v = str(int(v))
+    elif not isinstance(v, str):
+        raise TypeError(f"operand {v!r} has no exact Dart toString() here (pass a string)")
+    return dart_trim(v)
+
+
+def utf16_units(s: str) -> np.ndarray:
+    """A string's UTF-16 code units (`String.codeUnits`); lone surrogates pass through."""
+    return np.frombuffer(s.encode("utf-16-le", "surrogatepass"), dtype=np.uint16)
+
+
+def utf16_pool(strings):
+    """strings -> (units uint16 [total], offsets uint64 [n + 1]) as the C ABI takes them."""
+    parts = [utf16_units(s) for s in strings]
+    offsets = np.zeros(len(parts) + 1, dtype=np.uint64)
+    if parts:
+        offsets[1:] = np.cumsum([p.size for p in parts], dtype=np.uint64)
+    units = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint16)
+    if units.size == 0:
+        units = np.zeros(1, dtype=np.uint16)      # a valid address for an empty pool
+    return np.ascontiguousarray(units), offsets
+
+
 def _convert(v, col_type: int):
-    """`FieldSchema.convertValue` for integer / double fields (table_schema.dart:1371-1421)."""
+    """`FieldSchema.convertValue` for integer / double / text fields
+    (table_schema.dart:1371-1442)."""
+    if col_type == COL_TEXT:
+        return convert_text(v)
     if isinstance(v, (bool, np.bool_)):
         v = 1 if v else 0
     if isinstance(v, np.integer):
@@ -75,12 +126,20 @@ class WhereProgram:
 
     def __init__(self):
         self.ops: List[WhereOp] = []
-        self.args: List[Tuple[int, object]] = []     # (col_type, value)
+        self.args: List[Tuple[int, object]] = []     # (col_type, value); text: index into texts
+        self.texts: List[str] = []                   # operand pool of the text leaves
+
+    def _text(self, s: str) -> int:
+        self.texts.append(s)
+        return len(self.texts) - 1
 
     def _leaf(self, op: int, col: int = 0, col_type: int = COL_I64, lo=0, hi=0, n: int = 0,
               args_offset: int = 0) -> None:
         o = WhereOp(kind=W_LEAF, op=op, n=n, column_id=col, args_offset=args_offset)
-        if col_type == COL_I64:
+        if col_type == COL_TEXT:                     # operands are named by pool index
+            o.i_lo = self._text(lo) if isinstance(lo, str) else 0
+            o.i_hi = self._text(hi) if isinstance(hi, str) else 0
+        elif col_type == COL_I64:
             o.i_lo, o.i_hi = int(lo), int(hi)
         else:
             o.f_lo, o.f_hi = float(lo), float(hi)
@@ -95,11 +154,17 @@ class WhereProgram:
         if len(self.args) > MAX_IN_ARGS:
             raise ValueError(f"IN lists hold {len(self.args)} values (limit {MAX_IN_ARGS})")
         ops = (WhereOp * max(len(self.ops), 1))(*self.ops)
+        if len(self.texts) > MAX_TEXTS:
+            raise ValueError(f"text operands: {len(self.texts)} (limit {MAX_TEXTS})")
         raw = np.zeros(max(len(self.args), 1), dtype=np.uint64)
         for i, (t, v) in enumerate(self.args):
-            raw[i] = (np.array([v], dtype=np.int64) if t == COL_I64
+            raw[i] = (np.array([v], dtype=np.int64) if t in (COL_I64, COL_TEXT)
                       else np.array([v], dtype=np.float64)).view(np.uint64)[0]
         return ops, len(self.ops), raw, len(self.args)
+
+    def text_buffers(self):
+        """(units, offsets) of the text operand pool for tsc_index_filter_where_text."""
+        return utf16_pool(self.texts)
 
 
 def compile_condition(cond: Dict[str, object], columns: Dict[str, Tuple[int, int]]) -> WhereProgram:
@@ -166,14 +231,23 @@ def _emit_operator(op: str, ov, col: int, t: int, prog: WhereProgram) -> None:
         else:
             vals = [_convert(x, t) for x in ov if x is not None]
             off = len(prog.args)
+            if t == COL_TEXT:
+                vals = [prog._text(v) for v in vals]
             prog.args.extend((t, v) for v in vals)
             prog._leaf(OP_IN if up == "IN" else OP_NOT_IN, col, t, n=len(vals), args_offset=off)
     elif up == "IS":
         prog._leaf(OP_IS_NULL if ov is None else OP_FALSE, col, t)
     elif up == "IS NOT":
         prog._leaf(OP_IS_NOT_NULL if ov is None else OP_FALSE, col, t)
+    elif up in ("LIKE", "NOT LIKE"):
+        if t != COL_TEXT:
+            raise NotImplementedError(f"{up} on a numeric field has no columnar GPU form")
+        if ov is None:
+            prog._leaf(OP_FALSE)                        # `compareValue is! String` (:599-604)
+        else:
+            prog._leaf(OP_LIKE if up == "LIKE" else OP_NOT_LIKE, col, t, _convert(ov, t))
     else:
-        raise NotImplementedError(f"operator {op!r} has no columnar GPU form (numeric fields only)")
+        raise NotImplementedError(f"operator {op!r} has no columnar GPU form")
 
 
 class QueryCondition:
