@@ -432,7 +432,7 @@ def run_b200(args):
         # headline region: device ms, achieved GB/s or TFLOP/s and fraction of the measured peak
         try:
             from tools.bench_configs import measure_all
-            line["configs"] = measure_all(("c1", "c3", "c4", "c5", "c5w"))
+            line["configs"] = measure_all(("c1", "c3", "c4", "c5", "c5w", "c5t"))
         except Exception as e:  # noqa: BLE001
             line["configs"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)

@@ -354,7 +354,7 @@ class TostoreCuda {
       calloc.free(done);
     }
   }
-  /// Attribute column for the GPU WHERE prefilter: `colType` 0 = integer, 1 = double
+  /// Attribute column for the GPU WHERE prefilter: `colType` 0 = integer, 1 = double, 2 = text
   /// (DataType.integer / DataType.double fields of the table).
   static bool columnCreate(int handle, int columnId, int colType) {
     final lib = _open();
@@ -399,6 +399,75 @@ class TostoreCuda {
     } finally {
       calloc.free(v);
       calloc.free(nulls);
+    }
+  }
+
+  /// Text attribute column (`colType` 2, DataType.text): values travel as their UTF-16 code
+  /// units (`String.codeUnits`), so the GPU's comparisons are `String.compareTo` and LIKE is
+  /// `ValueMatcher.matchesLike` (handler/value_matcher.dart:211-240, :318-331). Pass the values
+  /// the table stores, i.e. after `FieldSchema.convertValue` (trim()). `null` -> NULL.
+  static bool columnAppendText(int handle, int columnId, int firstNodeId, List<String?> values) {
+    final lib = _open();
+    if (lib == null || values.isEmpty) return lib != null;
+    final fn = lib.lookupFunction<
+        Int32 Function(Uint64, Uint32, Uint64, Pointer<Uint16>, Pointer<Uint64>, Pointer<Uint8>, Uint64),
+        int Function(int, int, int, Pointer<Uint16>, Pointer<Uint64>, Pointer<Uint8>,
+            int)>('tsc_index_column_append_text');
+    final total = values.fold<int>(0, (a, s) => a + (s?.length ?? 0));
+    final units = calloc<Uint16>(total == 0 ? 1 : total);
+    final offs = calloc<Uint64>(values.length + 1);
+    final nulls = calloc<Uint8>(values.length);
+    try {
+      var o = 0;
+      for (var i = 0; i < values.length; i++) {
+        offs[i] = o;
+        final s = values[i];
+        nulls[i] = s == null ? 1 : 0;
+        if (s != null) {
+          units.asTypedList(total == 0 ? 1 : total).setRange(o, o + s.length, s.codeUnits);
+          o += s.length;
+        }
+      }
+      offs[values.length] = o;
+      return fn(handle, columnId, firstNodeId, units, offs, nulls, values.length) == 0;
+    } finally {
+      calloc.free(units);
+      calloc.free(offs);
+      calloc.free(nulls);
+    }
+  }
+
+  /// `filterWhere` for conditions with leaves on text columns: `texts` is the operand pool
+  /// (already normalised: `condition.normalize` trims text operands); a text leaf names its
+  /// operand by index in `i_lo` (`i_hi`: BETWEEN end), its IN list holds indices.
+  static int filterWhereText(int handle, Pointer<TscWhereOp> ops, int nOps, Pointer<Void> inArgs,
+      int nInArgs, List<String> texts) {
+    final lib = _open();
+    if (lib == null) return -1;
+    final fn = lib.lookupFunction<
+        Int32 Function(Uint64, Pointer<TscWhereOp>, Uint32, Pointer<Void>, Uint32, Pointer<Uint16>,
+            Pointer<Uint64>, Uint32, Pointer<Uint64>),
+        int Function(int, Pointer<TscWhereOp>, int, Pointer<Void>, int, Pointer<Uint16>,
+            Pointer<Uint64>, int, Pointer<Uint64>)>('tsc_index_filter_where_text');
+    final total = texts.fold<int>(0, (a, s) => a + s.length);
+    final units = calloc<Uint16>(total == 0 ? 1 : total);
+    final offs = calloc<Uint64>(texts.length + 1);
+    final matched = calloc<Uint64>();
+    try {
+      var o = 0;
+      for (var i = 0; i < texts.length; i++) {
+        offs[i] = o;
+        units.asTypedList(total == 0 ? 1 : total).setRange(o, o + texts[i].length, texts[i].codeUnits);
+        o += texts[i].length;
+      }
+      offs[texts.length] = o;
+      return fn(handle, ops, nOps, inArgs, nInArgs, units, offs, texts.length, matched) == 0
+          ? matched.value
+          : -1;
+    } finally {
+      calloc.free(units);
+      calloc.free(offs);
+      calloc.free(matched);
     }
   }
 

@@ -70,13 +70,30 @@ int main(void) {
   for (int r = 0; r < N; r++) year[r] = 2000 + r % 25;
   CHECK(tsc_index_column_create(h, 0, TSC_COL_I64));
   CHECK(tsc_index_column_append(h, 0, 0, year, NULL, N));
-  tsc_where_op prog[3];
+  /* a text field (UTF-16 code units, as a Dart String holds them): "en" / "de" / "en-GB" */
+  static const uint16_t kLang[] = {'e', 'n', 'd', 'e', 'e', 'n', '-', 'G', 'B'};
+  static const uint64_t kLangOff[4] = {0, 2, 4, 9};
+  uint16_t *lang_units = (uint16_t *)malloc(sizeof(uint16_t) * 5 * N);
+  uint64_t *lang_off = (uint64_t *)malloc(sizeof(uint64_t) * (N + 1));
+  uint64_t lu = 0;
+  for (int r = 0; r < N; r++) {
+    lang_off[r] = lu;
+    for (uint64_t i = kLangOff[r % 3]; i < kLangOff[r % 3 + 1]; i++) lang_units[lu++] = kLang[i];
+  }
+  lang_off[N] = lu;
+  CHECK(tsc_index_column_create(h, 1, TSC_COL_TEXT));
+  CHECK(tsc_index_column_append_text(h, 1, 0, lang_units, lang_off, NULL, N));
+  /* WHERE year >= 2020 AND year != 2022 AND lang LIKE 'en%' (text operand 0 of the pool) */
+  static const uint16_t kPattern[] = {'e', 'n', '%'};
+  static const uint64_t kPatternOff[2] = {0, 3};
+  tsc_where_op prog[4];
   memset(prog, 0, sizeof prog);
   prog[0].kind = TSC_W_LEAF; prog[0].op = TSC_OP_GE; prog[0].column_id = 0; prog[0].i_lo = 2020;
   prog[1].kind = TSC_W_LEAF; prog[1].op = TSC_OP_NE; prog[1].column_id = 0; prog[1].i_lo = 2022;
-  prog[2].kind = TSC_W_AND;  prog[2].n = 2;
+  prog[2].kind = TSC_W_LEAF; prog[2].op = TSC_OP_LIKE; prog[2].column_id = 1; prog[2].i_lo = 0;
+  prog[3].kind = TSC_W_AND;  prog[3].n = 3;
   uint64_t matched = 0;
-  CHECK(tsc_index_filter_where(h, prog, 3, NULL, 0, &matched));
+  CHECK(tsc_index_filter_where_text(h, prog, 4, NULL, 0, kPattern, kPatternOff, 1, &matched));
   printf("WHERE matched %llu of %d rows\n", (unsigned long long)matched, N);
 
   /* ToStore.vectorSearch: fp64 query of any length, topK, optional threshold */
@@ -89,9 +106,10 @@ int main(void) {
   uint32_t count = 0;
   CHECK(tsc_vector_search_pk(h, query, D, K, NAN, ids, dist, score, pks, sizeof pks, offs, &count));
   for (uint32_t j = 0; j < count; j++)
-    printf("%u  %.*s  node=%lld year=%lld distance=%.12g score=%.6f\n", j,
+    printf("%u  %.*s  node=%lld year=%lld lang=%s distance=%.12g score=%.6f\n", j,
            (int)(offs[j + 1] - offs[j]), (const char *)pks + offs[j], (long long)ids[j],
-           (long long)year[ids[j]], dist[j], score[j]);
+           (long long)year[ids[j]], ids[j] % 3 == 0 ? "en" : (ids[j] % 3 == 1 ? "de" : "en-GB"), dist[j],
+           score[j]);
 
   tsc_stats st;
   memset(&st, 0, sizeof st);
@@ -104,6 +122,6 @@ int main(void) {
          (unsigned long long)st.certified_queries, (unsigned long long)st.retried_queries,
          (unsigned long long)st.uncertified_queries);
   CHECK(tsc_index_destroy(h));
-  free(rows); free(pk_bytes); free(pk_off); free(year);
+  free(rows); free(pk_bytes); free(pk_off); free(year); free(lang_units); free(lang_off);
   return 0;
 }

@@ -30,5 +30,5 @@ trap 'cp $OUT/libtostore_cuda.so.orig tostore_b200/libtostore_cuda.so' EXIT
 cp $OUT/libtostore_cuda.so tostore_b200/libtostore_cuda.so
 LD_PRELOAD="$PRE" TSAN_OPTIONS=report_signal_unsafe=0 \
 ASAN_OPTIONS=detect_leaks=0 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
-  python -m pytest tests/test_where.py tests/test_pk_table.py tests/test_ngh_loader.py tests/test_abi.py tests/test_host_prep.py \
+  python -m pytest tests/test_where.py tests/test_where_text.py tests/test_pk_table.py tests/test_ngh_loader.py tests/test_abi.py tests/test_host_prep.py \
   -x -q -m "not gpu" -p no:cacheprovider

@@ -87,6 +87,47 @@ def measure(name, n, d, metric, dt, nq, k, reps, mask_frac=None, warm=3, where=F
         return out
 
 
+def measure_where_text(name, n, distinct, reps=20, device_id=0):
+    """WHERE over a TEXT column on one GPU: `category LIKE 'cat-1%' AND price < 500` over n rows
+    whose category is one of `distinct` strings ("cat-" + 7 digits). Times tsc_index_filter_where_text
+    (dictionary pass + row pass + count read-back, wall clock incl. the sync) and the column append
+    (host interning + upload)."""
+    import ctypes as C
+    from tostore_b200 import GpuVectorIndex, _native as N, where as W
+    rng = np.random.default_rng(11)
+    with GpuVectorIndex(16, 0, capacity_rows=n, k_max=16, nq_max=8, device_id=device_id) as ix:
+        ix.append_synthetic(7, n)
+        ix.column_create(0, W.COL_I64)
+        ix.column_create(1, W.COL_TEXT)
+        ix.column_append(0, rng.integers(0, 1000, n))
+        codes = rng.integers(0, distinct, n)
+        # "cat-" + zero-padded number spread over [0, 10^7): fixed 11 code units per row, built with numpy
+        num = (codes * (10_000_000 // distinct)).astype(np.int64)
+        units = np.empty((n, 11), dtype=np.uint16)
+        units[:, :4] = np.frombuffer("cat-".encode("utf-16-le"), dtype=np.uint16)
+        for j in range(7):
+            units[:, 10 - j] = 48 + (num // 10 ** j) % 10
+        offsets = np.arange(n + 1, dtype=np.uint64) * 11
+        t0 = time.perf_counter()
+        N.check(ix._lib.tsc_index_column_append_text(ix.handle, 1, 0, units.ctypes.data, offsets.ctypes.data,
+                                                     None, n), "tsc_index_column_append_text")
+        append_s = time.perf_counter() - t0
+        prog = W.compile_condition({"AND": [{"category": {"LIKE": "cat-1%"}}, {"price": {"<": 500}}]},
+                                   {"price": (0, W.COL_I64), "category": (1, W.COL_TEXT)})
+        matched = ix.filter_where(prog)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            matched = ix.filter_where(prog)
+        ms = (time.perf_counter() - t0) / reps * 1e3
+        want = int(((num // 1_000_000 == 1) & (np.random.default_rng(11).integers(0, 1000, n) < 500)).sum())
+        n_distinct = int(np.unique(codes).size)
+        # row pass: two 8-byte columns + one bit per row; dictionary pass: the distinct strings once
+        bytes_moved = n * 16.125 + n_distinct * (11 * 2 + 8)
+        return {"config": name, "n": n, "distinct_strings": n_distinct, "where_ms_incl_sync": ms,
+                "where_matched": int(matched), "where_matched_expected": want, "where_gbs": bytes_moved / ms / 1e6,
+                "column_append_s": append_s, "column_append_mrows_s": n / append_s / 1e6}
+
+
 CONFIGS = {
     "c1": lambda: [measure("c1 brute-force L2 10k x 128 fp32 k=10", 10_000, 128, 0, 0, 1, 10, 200)],
     "c2": lambda: [measure("c2 single-query L2 10M x 768 fp32 k=10", 10_000_000, 768, 0, 0, 1, 10, 30)],
@@ -106,13 +147,20 @@ CONFIGS = {
     "c5s1": lambda: [measure("c5s1 shard: 1% mask", 12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.01)],
     "c5w": lambda: [measure("c5w shard: L2 12.5M x 384 fp32 k=10, WHERE price<316 AND rating<0.316 (~10%) "
                             "evaluated on the GPU", 12_500_000, 384, 0, 0, 1, 10, 20, mask_frac=0.10, where=True)],
+    "c5t": lambda: [measure_where_text("c5t WHERE category LIKE 'cat-1%' AND price < 500 over 12.5M rows, "
+                                       "1000 distinct strings (text column, dictionary-encoded)", 12_500_000, 1000),
+                    measure_where_text("c5t same, 1M distinct strings", 12_500_000, 1_000_000, reps=10)],
 }
 
 
 def measure_all(which=("c1", "c3", "c4", "c5")):
+    """One failing config does not take the others' numbers with it."""
     out = []
     for w in which:
-        out.extend(CONFIGS[w]())
+        try:
+            out.extend(CONFIGS[w]())
+        except Exception as e:     # noqa: BLE001
+            out.append({"config": w, "error": repr(e)})
     return out
 
 
