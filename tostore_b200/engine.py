@@ -70,6 +70,7 @@ class GpuVectorIndex:
 
     def clear(self) -> None:
         N.check(self._lib.tsc_index_clear(self.handle), "tsc_index_clear")
+        self._col_rows = {}            # attribute columns restart at the first node id too
 
     # -- ingestion -------------------------------------------------------------
     def append_rows(self, rows, first_node_id: Optional[int] = None) -> None:
