@@ -25,3 +25,7 @@ timeout 60 /tmp/vsdemo 2>&1 | tail -22 | tee -a $L
 echo "== short headline bench" | tee -a $L
 timeout 200 python bench.py --steps 50 --warmup 3 --no-cpu-baseline --no-configs --recall-queries 1 2>gpurun_out/${T}_bench.err | tee gpurun_out/${T}_bench.json | cut -c1-420 | tee -a $L
 tail -2 gpurun_out/${T}_bench.err | tee -a $L
+echo "== memcheck: WHERE kernels (numeric + text), last steps of short columns included" | tee -a $L
+timeout 100 /usr/local/cuda/bin/compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_where_text.py::test_gpu_text_where_equals_oracle tests/test_where.py::test_gpu_filter_where_equals_oracle -m gpu -q -x --timeout 90 -p no:cacheprovider > gpurun_out/${T}_memcheck.txt 2>&1
+echo "exit $?" | tee -a $L
+grep -E "passed|failed|ERROR SUMMARY|Invalid|Error" gpurun_out/${T}_memcheck.txt | head -12 | tee -a $L

@@ -61,7 +61,6 @@ static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *
     const tsc_where_op &o = ops[i];
     WhereDevOp &d = prog->ops[i];
     d.kind = o.kind;
-    d.op = o.op;
     d.n = o.n;
     if (o.kind == TSC_W_AND || o.kind == TSC_W_OR) {
       if ((int)o.n > depth || o.n > 63) {
@@ -79,7 +78,10 @@ static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *
       set_error("filter_where: stack deeper than %d", kWhereMaxOps);
       return TSC_ERR_BAD_ARG;
     }
-    if (o.op == TSC_OP_TRUE || o.op == TSC_OP_FALSE) continue;
+    if (o.op == TSC_OP_TRUE || o.op == TSC_OP_FALSE) {
+      where_decode_leaf(o.op, 0, 0, &d);
+      continue;
+    }
     const WhereColInfo *c = nullptr;
     for (uint32_t j = 0; j < n_cinfo; j++)
       if (cinfo[j].id == o.column_id) c = &cinfo[j];
@@ -92,15 +94,18 @@ static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *
     if (s == n_slots) slot_ids[n_slots++] = o.column_id;
     d.col = s;
     if (c->type == TSC_COL_TEXT) {
-      if (o.op == TSC_OP_IS_NULL || o.op == TSC_OP_IS_NOT_NULL) continue;   // the NULL bitmap answers
+      if (o.op == TSC_OP_IS_NULL || o.op == TSC_OP_IS_NOT_NULL) {   // the NULL bitmap answers
+        where_decode_leaf(o.op, 0, 0, &d);
+        continue;
+      }
       // positive predicate over the dictionary + how the row pass reads it
       TextLeaf lf;
       memset(&lf, 0, sizeof lf);
-      uint64_t flags = 0;
+      uint8_t flags = kLfDict;
       switch (o.op) {
-        case TSC_OP_NE: lf.op = kOpEq; flags = kDictNeg | kDictOnNull; break;
-        case TSC_OP_NOT_IN: lf.op = kOpIn; flags = kDictNeg | kDictOnNull; break;
-        case TSC_OP_NOT_LIKE: lf.op = kOpLike; flags = kDictNeg; break;   // false on NULL (:602-604)
+        case TSC_OP_NE: lf.op = kOpEq; flags |= kLfNeg | kLfOnNull; break;
+        case TSC_OP_NOT_IN: lf.op = kOpIn; flags |= kLfNeg | kLfOnNull; break;
+        case TSC_OP_NOT_LIKE: lf.op = kOpLike; flags |= kLfNeg; break;   // false on NULL (:602-604)
         default: lf.op = o.op; break;
       }
       uint2 r;
@@ -132,8 +137,7 @@ static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *
       plan->bits_words += (c->n_codes + 31) / 32 + 1;   // never empty: a NULL row may read word 0
       plan->leaves.push_back(lf);
       plan->leaf_slot.push_back(s);
-      d.op = kOpDict;
-      d.lo = flags;
+      d.flags = flags;
       d.args_off = lf.bits_off;
       continue;
     }
@@ -148,8 +152,8 @@ static int32_t where_build(const tsc_where_op *ops, uint32_t n_ops, const void *
       memcpy(&b, &v, 8);
       return where_key_f64_bits(b);
     };
-    d.lo = f64 ? fkey(o.f_lo) : where_key_i64(o.i_lo);
-    d.hi = f64 ? fkey(o.f_hi) : where_key_i64(o.i_hi);
+    where_decode_leaf(o.op, f64 ? fkey(o.f_lo) : where_key_i64(o.i_lo),
+                      f64 ? fkey(o.f_hi) : where_key_i64(o.i_hi), &d);
     if (o.op == TSC_OP_IN || o.op == TSC_OP_NOT_IN) {
       if ((uint64_t)o.args_offset + o.n > n_in_args) {
         set_error("filter_where: step %u IN list [%u, %u) outside in_args (%u)", i, o.args_offset,

@@ -33,19 +33,22 @@ namespace tsc {
 enum : uint8_t { kWLeaf = 0, kWAnd = 1, kWOr = 2 };
 enum : uint8_t {
   kOpEq = 0, kOpNe, kOpGt, kOpGe, kOpLt, kOpLe, kOpBetween, kOpIn, kOpNotIn, kOpIsNull,
-  kOpIsNotNull, kOpTrue, kOpFalse, kOpLike, kOpNotLike, kOpCount,
-  kOpDict = 32   // device form of every text leaf except IS [NOT] NULL: bit `code` of a bitmap
+  kOpIsNotNull, kOpTrue, kOpFalse, kOpLike, kOpNotLike, kOpCount
 };
-constexpr uint64_t kDictNeg = 1, kDictOnNull = 2;   // WhereDevOp::lo of a kOpDict leaf
 constexpr int kWhereMaxOps = 64;     // program length / bit-stack depth
 constexpr int kWhereMaxCols = 16;
 
+// A leaf as the row pass sees it: already a range test in key space,
+//   r = NULL ? on_null : ((lo <= key <= hi) != neg)
+// (or a list / dictionary-bitmap membership instead of the range). The operator is decoded into
+// this form ONCE, on the host (where_decode_leaf), so the row pass carries no operator switch.
+enum : uint8_t { kLfNeg = 1, kLfOnNull = 2, kLfList = 4, kLfDict = 8, kLfConst = 16 };
 struct WhereDevOp {        // 32 bytes, operands already in key space
-  uint8_t kind, op;
+  uint8_t kind, flags;     // kW*; kLf* (leaves)
   uint16_t n;              // children of AND / OR, or length of the IN list
   uint32_t col;            // slot in WhereCols
-  uint64_t lo, hi;         // operand keys (BETWEEN: start, end)
-  uint32_t args_off;       // IN list: first key in `args`; kOpDict: first word in `dict_bits`
+  uint64_t lo, hi;         // the range (lo > hi: empty)
+  uint32_t args_off;       // kLfList: first key in `args`; kLfDict: first word in `dict_bits`
   uint32_t pad;
 };
 
@@ -69,6 +72,32 @@ __host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
   return (b & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull ? 0xFFFFFFFFFFFFFFFFull : k;
 }
 
+// Operator (numeric column, operand keys a / b) -> the row pass's range form
+// (value_matcher.dart:570-612: '!=' and NOT IN are true on NULL, every ordering operator, IN and
+// BETWEEN false; IN / NOT IN keep their list and use no range).
+inline void where_decode_leaf(uint8_t op, uint64_t a, uint64_t b, WhereDevOp *d) {
+  uint64_t lo = a, hi = a;
+  uint8_t fl = 0;
+  switch (op) {
+    case kOpEq: break;
+    case kOpNe: fl = kLfNeg | kLfOnNull; break;
+    case kOpGt: if (a == ~0ull) { lo = 1; hi = 0; } else { lo = a + 1; hi = ~0ull; } break;
+    case kOpGe: hi = ~0ull; break;
+    case kOpLt: if (a == 0) { lo = 1; hi = 0; } else { lo = 0; hi = a - 1; } break;
+    case kOpLe: lo = 0; break;
+    case kOpBetween: hi = b; break;
+    case kOpIn: fl = kLfList; break;
+    case kOpNotIn: fl = kLfList | kLfNeg | kLfOnNull; break;
+    case kOpIsNull: lo = 1; hi = 0; fl = kLfOnNull; break;
+    case kOpIsNotNull: lo = 0; hi = ~0ull; break;
+    case kOpTrue: lo = 0; hi = ~0ull; fl = kLfOnNull | kLfConst; break;
+    default: lo = 1; hi = 0; fl = kLfConst; break;   // kOpFalse
+  }
+  d->lo = lo;
+  d->hi = hi;
+  d->flags = fl;
+}
+
 // U rows of the program side by side. `load(slot, key[U], isnull[U])` fetches the U rows' values
 // of a column as order-preserving keys. The program is walked ONCE for all U rows, so the U loads
 // a leaf needs are independent of each other and in flight together (on the device: U
@@ -77,8 +106,7 @@ __host__ __device__ __forceinline__ uint64_t where_key_f64_bits(uint64_t b) {
 // evaluation code.
 // Stack = uint32_t for programs of up to 32 steps (the bit-stack cannot get deeper than the
 // program is long; 64-bit shifts cost two instructions each), uint64_t otherwise.
-// TEXT: the program holds kOpDict leaves (numeric-only programs keep the instantiation the
-// round-2 measurements were made with).
+// TEXT: the program holds dictionary leaves (kLfDict).
 template <int U, class Stack, bool TEXT, class Load>
 __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &prog,
                                                            const uint64_t *args,
@@ -97,54 +125,40 @@ __host__ __device__ __forceinline__ void where_eval_rows_t(const WhereProgram &p
   for (uint32_t i = 0; i < prog.n_ops; i++) {
     const WhereDevOp &op = prog.ops[i];
     if (op.kind == kWLeaf) {
-      if ((op.op < kOpTrue || (TEXT && op.op == kOpDict)) && op.col != last_col) {
+      const uint32_t fl = op.flags;   // uniform over the warp
+      if (!(fl & kLfConst) && op.col != last_col) {
         last_col = op.col;
         load(op.col, key, isnull);
       }
-      // Every comparison is a range test in key space: r = NULL ? on_null : (lo <= key <= hi) ^ neg.
-      // The operator is decoded ONCE per leaf (uniform over the warp) and the per-row work is two
-      // 64-bit compares; IN / NOT IN walk their list. (A per-row switch over the operators was
-      // if-converted by the compiler into ~80 instructions per row and leaf: the kernel was
-      // issue-bound at 21 % of HBM, profiles/r02_where_*.)
-      uint64_t lo = op.lo, hi = op.lo;
-      bool neg = false, on_null = false, list = false, dict = false;
-      switch (op.op) {
-        case kOpEq: break;
-        case kOpNe: neg = true; on_null = true; break;
-        case kOpGt: hi = ~0ull; if (lo == ~0ull) { lo = 1; hi = 0; } else lo = lo + 1; break;
-        case kOpGe: hi = ~0ull; break;
-        case kOpLt: if (hi == 0) { lo = 1; hi = 0; } else { hi = hi - 1; lo = 0; } break;
-        case kOpLe: lo = 0; break;
-        case kOpBetween: hi = op.hi; break;
-        case kOpIn: list = true; break;
-        case kOpNotIn: list = true; neg = true; on_null = true; break;
-        case kOpIsNull: lo = 1; hi = 0; on_null = true; break;
-        case kOpIsNotNull: lo = 0; hi = ~0ull; break;
-        case kOpTrue: lo = 0; hi = ~0ull; on_null = true; break;
-        case kOpDict:
-          if (TEXT) {
-            dict = true;
-            neg = (op.lo & kDictNeg) != 0;
-            on_null = (op.lo & kDictOnNull) != 0;
-          }
-          break;
-        default: lo = 1; hi = 0; break;
+      // Per row and leaf: two 64-bit compares. (A per-row switch over the operators was
+      // if-converted by the compiler into ~80 instructions per row and leaf — 21 % of HBM,
+      // profiles/r02_where_*; decoding it per leaf in the kernel still cost ~1/3 of the
+      // instructions of a two-leaf program, so the decode moved to the host.)
+      const bool neg = (fl & kLfNeg) != 0, on_null = (fl & kLfOnNull) != 0;
+      bool in[U];
+      if (fl & kLfList) {
+#pragma unroll
+        for (int u = 0; u < U; u++) in[u] = false;
+        for (uint32_t j = 0; j < op.n; j++) {
+          const uint64_t a = args[op.args_off + j];
+#pragma unroll
+          for (int u = 0; u < U; u++) in[u] |= (key[u] == a);
+        }
+      } else if (TEXT && (fl & kLfDict)) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          // the key's low 32 bits are the row's dictionary code; a NULL row holds no code
+          const uint32_t code = (uint32_t)key[u];
+          in[u] = !isnull[u] && ((dict_bits[op.args_off + (code >> 5)] >> (code & 31)) & 1u);
+        }
+      } else {
+        const uint64_t lo = op.lo, hi = op.hi;
+#pragma unroll
+        for (int u = 0; u < U; u++) in[u] = key[u] >= lo && key[u] <= hi;
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const uint64_t k = key[u];
-        bool in;
-        if (list) {
-          in = false;
-          for (uint32_t j = 0; j < op.n; j++) in |= (k == args[op.args_off + j]);
-        } else if (TEXT && dict) {
-          // the key's low 32 bits are the row's dictionary code; a NULL row holds no code
-          const uint32_t code = (uint32_t)k;
-          in = !isnull[u] && ((dict_bits[op.args_off + (code >> 5)] >> (code & 31)) & 1u);
-        } else {
-          in = k >= lo && k <= hi;
-        }
-        const bool r = isnull[u] ? on_null : (in != neg);
+        const bool r = isnull[u] ? on_null : (in[u] != neg);
         stack[u] = (Stack)(stack[u] << 1) | (Stack)(r ? 1 : 0);
       }
     } else {
@@ -191,6 +205,85 @@ __host__ __device__ __forceinline__ bool where_eval_row(const WhereProgram &prog
 // profiles/r02_first_call.log; L2 prefetching two steps ahead did not help.)
 // HBM traffic: 8 bytes per row per distinct column + 4 bytes per 32 rows written.
 constexpr int kWhereWords = 4;
+
+// One step of a warp: rows [g * 128, g * 128 + 128). FULL: all of them exist — one base address
+// per column with immediate offsets, the four NULL words as one 16-byte load, the four result
+// words as one 16-byte store. Otherwise (the last step of the column) rows past the end re-read
+// the last row and are masked out of the result.
+template <bool TEXT, bool FULL>
+__device__ __forceinline__ unsigned where_step(const WhereProgram &prog, const WhereCols &cols,
+                                               const uint64_t *__restrict__ args,
+                                               const uint32_t *__restrict__ dict_bits,
+                                               uint64_t n_rows, uint64_t n_words, uint64_t g, int lane,
+                                               uint32_t *__restrict__ out_bits) {
+  const uint64_t row0 = g * kWhereWords * 32 + lane;
+  uint64_t rowc[kWhereWords];
+#pragma unroll
+  for (int u = 0; u < kWhereWords; u++) {
+    const uint64_t row = row0 + (uint64_t)u * 32;
+    rowc[u] = FULL || row < n_rows ? row : n_rows - 1;
+  }
+  bool res[kWhereWords];
+  where_eval_rows<kWhereWords, TEXT>(
+      prog, args, dict_bits,
+      [&](uint32_t c, uint64_t (&key)[kWhereWords], bool (&isnull)[kWhereWords]) {
+        // all loads first, no branch between them, then the conversions
+        uint64_t raw[kWhereWords];
+        uint32_t nb[kWhereWords];
+        const uint64_t *vals = cols.values[c];
+        const uint32_t *nulls = cols.nulls[c];
+        if (FULL) {
+          const uint64_t *vp = vals + row0;
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) raw[u] = __ldg(vp + u * 32);
+          static_assert(kWhereWords == 4, "the NULL words of a step are one uint4");
+          const uint4 nw = __ldg(reinterpret_cast<const uint4 *>(nulls) + g);
+          nb[0] = nw.x >> lane;
+          nb[1] = nw.y >> lane;
+          nb[2] = nw.z >> lane;
+          nb[3] = nw.w >> lane;
+        } else {
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) {
+            raw[u] = __ldg(vals + rowc[u]);
+            nb[u] = __ldg(nulls + (rowc[u] >> 5)) >> (rowc[u] & 31);
+          }
+        }
+        if (cols.is_f64[c] != 0) {   // uniform
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) key[u] = where_key_f64_bits(raw[u]);
+        } else {
+#pragma unroll
+          for (int u = 0; u < kWhereWords; u++) key[u] = raw[u] ^ 0x8000000000000000ull;
+        }
+#pragma unroll
+        for (int u = 0; u < kWhereWords; u++) isnull[u] = nb[u] & 1u;
+      },
+      res);
+  unsigned bits[kWhereWords];
+#pragma unroll
+  for (int u = 0; u < kWhereWords; u++)
+    bits[u] = __ballot_sync(0xFFFFFFFFu, res[u] && (FULL || row0 + (uint64_t)u * 32 < n_rows));
+  unsigned count = 0;
+  if (lane == 0) {
+    if (FULL) {
+      reinterpret_cast<uint4 *>(out_bits)[g] = make_uint4(bits[0], bits[1], bits[2], bits[3]);
+#pragma unroll
+      for (int u = 0; u < kWhereWords; u++) count += __popc(bits[u]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < kWhereWords; u++) {
+        const uint64_t w = g * kWhereWords + u;
+        if (w < n_words) {
+          out_bits[w] = bits[u];
+          count += __popc(bits[u]);
+        }
+      }
+    }
+  }
+  return count;
+}
+
 template <bool TEXT>
 __global__ void __launch_bounds__(256)
 where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_constant__ WhereCols cols,
@@ -201,49 +294,15 @@ where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_consta
   const int lane = threadIdx.x & 31;
   const uint64_t n_words = (n_rows + 31) / 32;
   const uint64_t n_groups = (n_words + kWhereWords - 1) / kWhereWords;
+  const uint64_t full_groups = n_rows / (kWhereWords * 32);
   const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   unsigned long long local = 0;
   for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups;
        g += warps) {
-    const uint64_t row0 = g * kWhereWords * 32 + lane;
-    bool res[kWhereWords];
-    where_eval_rows<kWhereWords, TEXT>(
-        prog, args, dict_bits,
-        [&](uint32_t c, uint64_t (&key)[kWhereWords], bool (&isnull)[kWhereWords]) {
-          // all loads first, no branch between them (rows past the end re-read the last row:
-          // their result is masked below), then the conversions
-          uint64_t raw[kWhereWords];
-          uint32_t nb[kWhereWords];
-          const uint64_t *vals = cols.values[c];
-          const uint32_t *nulls = cols.nulls[c];
-#pragma unroll
-          for (int u = 0; u < kWhereWords; u++) {
-            uint64_t row = row0 + (uint64_t)u * 32;
-            row = row < n_rows ? row : n_rows - 1;
-            raw[u] = __ldg(vals + row);
-            nb[u] = __ldg(nulls + (row >> 5)) >> (row & 31);
-          }
-          if (cols.is_f64[c] != 0) {   // uniform
-#pragma unroll
-            for (int u = 0; u < kWhereWords; u++) key[u] = where_key_f64_bits(raw[u]);
-          } else {
-#pragma unroll
-            for (int u = 0; u < kWhereWords; u++) key[u] = raw[u] ^ 0x8000000000000000ull;
-          }
-#pragma unroll
-          for (int u = 0; u < kWhereWords; u++) isnull[u] = nb[u] & 1u;
-        },
-        res);
-#pragma unroll
-    for (int u = 0; u < kWhereWords; u++) {
-      const uint64_t row = row0 + (uint64_t)u * 32;
-      const unsigned bits = __ballot_sync(0xFFFFFFFFu, res[u] && row < n_rows);
-      const uint64_t w = g * kWhereWords + u;
-      if (lane == 0 && w < n_words) {
-        out_bits[w] = bits;
-        local += __popc(bits);
-      }
-    }
+    if (g < full_groups)
+      local += where_step<TEXT, true>(prog, cols, args, dict_bits, n_rows, n_words, g, lane, out_bits);
+    else
+      local += where_step<TEXT, false>(prog, cols, args, dict_bits, n_rows, n_words, g, lane, out_bits);
   }
   if (lane == 0 && local) atomicAdd(matched, local);
 }
