@@ -531,7 +531,7 @@ int32_t ix_clear(Index *ix) {
   for (auto &c : ix->columns) {
     c.rows = 0;
     if (c.dict) {   // device arrays are kept for the next strings
-      c.dict->codes.clear();
+      c.dict->truncate(0);
       c.dict->n_codes = 0;
       c.dict->n_units = 0;
     }

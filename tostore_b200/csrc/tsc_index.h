@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <condition_variable>
 #include <memory>
@@ -10,7 +11,6 @@
 #include <new>
 #include <string>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/tostore_cuda.h"
@@ -42,14 +42,73 @@ struct ScanConfig {
 };
 
 // numeric table field kept column-wise next to the embedding column (tsc_where.cuh)
-// dictionary of a TSC_COL_TEXT column: every distinct string once, UTF-16 code units
+// dictionary of a TSC_COL_TEXT column: every distinct string once, UTF-16 code units. The host
+// keeps a mirror of the arena and an open-addressing table over it (no per-string allocation:
+// interning a row is one hash, one probe run and at most one memcmp); the device copy is what
+// dict_match_kernel reads.
 struct TextDict {
-  std::unordered_map<std::u16string, uint32_t> codes;   // string -> code (host, for appends)
-  uint64_t n_units = 0;             // code units stored so far
-  uint32_t n_codes = 0;
-  uint16_t *d_units = nullptr;      // [units_cap] all strings back to back
-  uint64_t *d_offs = nullptr;       // [codes_cap + 1] string c = units [offs[c], offs[c + 1])
+  std::vector<uint16_t> h_units;    // all strings back to back (host mirror)
+  std::vector<uint64_t> h_offs{0};  // string c = h_units [h_offs[c], h_offs[c + 1])
+  std::vector<uint64_t> slots;      // (hash >> 32) << 32 | code + 1; 0 = empty; power-of-two size
+  uint64_t n_units = 0;             // code units / strings present on the DEVICE (the host
+  uint32_t n_codes = 0;             // vectors run ahead of them only inside an append)
+  uint16_t *d_units = nullptr;      // [units_cap]
+  uint64_t *d_offs = nullptr;       // [codes_cap + 1]
   uint64_t units_cap = 0, codes_cap = 0;
+
+  static uint64_t hash(const uint16_t *p, size_t n) {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xFF51AFD7ED558CCDull);
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+      uint64_t w;
+      memcpy(&w, p + i, 8);
+      h = (h ^ w) * 0x9FB21C651E98DF25ull;
+      h ^= h >> 32;
+    }
+    uint64_t w = 0;
+    if (n > i) memcpy(&w, p + i, (n - i) * 2);
+    h = (h ^ w) * 0x9FB21C651E98DF25ull;
+    return h ^ (h >> 29);
+  }
+  uint32_t host_codes() const { return (uint32_t)(h_offs.size() - 1); }
+  void rebuild() {   // table over the strings of the host mirror
+    size_t cap = 1024;
+    while (cap < (size_t)host_codes() * 2 + 2) cap *= 2;
+    slots.assign(cap, 0);
+    for (uint32_t c = 0; c < host_codes(); c++)
+      place(hash(h_units.data() + h_offs[c], (size_t)(h_offs[c + 1] - h_offs[c])), c);
+  }
+  void place(uint64_t h, uint32_t code) {
+    const size_t mask = slots.size() - 1;
+    size_t i = (size_t)h & mask;
+    while (slots[i]) i = (i + 1) & mask;
+    slots[i] = (h & 0xFFFFFFFF00000000ull) | ((uint64_t)code + 1);
+  }
+  // code of the string, interning it when it is new
+  uint32_t intern(const uint16_t *p, size_t n) {
+    if (slots.empty() || ((size_t)host_codes() + 1) * 2 > slots.size()) rebuild();
+    const uint64_t h = hash(p, n);
+    const size_t mask = slots.size() - 1;
+    for (size_t i = (size_t)h & mask;; i = (i + 1) & mask) {
+      const uint64_t v = slots[i];
+      if (!v) break;
+      if ((v ^ h) >> 32) continue;
+      const uint32_t c = (uint32_t)v - 1;
+      if (h_offs[c + 1] - h_offs[c] == n && (n == 0 || memcmp(h_units.data() + h_offs[c], p, n * 2) == 0))
+        return c;
+    }
+    const uint32_t c = host_codes();
+    h_units.insert(h_units.end(), p, p + n);
+    h_offs.push_back(h_units.size());
+    place(h, c);
+    return c;
+  }
+  void truncate(uint32_t codes) {   // forget the strings interned after the first `codes`
+    if (codes >= host_codes()) return;
+    h_offs.resize((size_t)codes + 1);
+    h_units.resize((size_t)h_offs.back());
+    rebuild();
+  }
 };
 
 struct AttrColumn {

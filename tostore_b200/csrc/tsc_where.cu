@@ -8,6 +8,18 @@
 
 using namespace tsc;
 
+// how many of its own steps ahead a warp of where_eval_kernel prefetches into L2 (0 = off)
+constexpr uint32_t kWherePrefetchSteps = 1;
+#ifdef TSC_DIAG
+#include <stdlib.h>
+static uint32_t where_prefetch_steps() {   // diagnostics build only: TSC_WHERE_PF = 0 / 1 / 2 ...
+  const char *v = getenv("TSC_WHERE_PF");
+  return v && *v ? (uint32_t)atoi(v) : kWherePrefetchSteps;
+}
+#else
+static uint32_t where_prefetch_steps() { return kWherePrefetchSteps; }
+#endif
+
 static AttrColumn *find_column(Index *ix, uint32_t id) {
   for (auto &c : ix->columns)
     if (c.id == id) return &c;
@@ -327,13 +339,10 @@ static int32_t dict_reserve(Index *ix, TextDict *d, uint64_t units, uint64_t cod
 }
 
 // Intern the strings of rows [0, n): codes[i] <- the row's code; strings seen for the first
-// time are appended to new_units / new_offs (end offsets, absolute). Shared by the device
-// path and the host self-test. A NULL row gets code 0 and stores nothing.
+// time extend the dictionary's host mirror. Shared by the device path and the host self-test.
+// A NULL row gets code 0 and stores nothing.
 static int32_t dict_intern(TextDict *d, const uint16_t *units, const uint64_t *offsets,
-                           const uint8_t *is_null, uint64_t n, uint64_t *codes,
-                           std::vector<uint16_t> *new_units, std::vector<uint64_t> *new_offs) {
-  uint64_t end = d->n_units;
-  uint32_t next = d->n_codes;
+                           const uint8_t *is_null, uint64_t n, uint64_t *codes) {
   for (uint64_t i = 0; i < n; i++) {
     codes[i] = 0;
     if (is_null && is_null[i]) continue;
@@ -342,21 +351,11 @@ static int32_t dict_intern(TextDict *d, const uint16_t *units, const uint64_t *o
       set_error("column_append_text: row %llu has a bad string range", (unsigned long long)i);
       return TSC_ERR_BAD_ARG;
     }
-    std::u16string s(reinterpret_cast<const char16_t *>(units) + a, (size_t)(b - a));
-    auto it = d->codes.find(s);
-    if (it != d->codes.end()) {
-      codes[i] = it->second;
-      continue;
-    }
-    if (next == 0xFFFFFFFFu) {
-      set_error("column_append_text: more than 2^32 - 1 distinct strings");
+    if (d->host_codes() == 0xFFFFFFFEu) {
+      set_error("column_append_text: more than 2^32 - 2 distinct strings");
       return TSC_ERR_UNSUPPORTED;
     }
-    new_units->insert(new_units->end(), units + a, units + b);
-    end += b - a;
-    new_offs->push_back(end);
-    codes[i] = next;
-    d->codes.emplace(std::move(s), next++);
+    codes[i] = d->intern(units + a, (size_t)(b - a));
   }
   return TSC_OK;
 }
@@ -377,40 +376,35 @@ int32_t ix_column_append_text(Index *ix, uint32_t column_id, uint64_t first_node
   }
   TextDict *d = c->dict.get();
   std::vector<uint64_t> codes(n);
-  std::vector<uint16_t> new_units;
-  std::vector<uint64_t> new_offs;
-  const uint32_t codes_before = d->n_codes;
-  int32_t rc = dict_intern(d, units, offsets, is_null, n, codes.data(), &new_units, &new_offs);
-  auto roll_back = [&]() {   // forget the strings interned by this call
-    for (auto it = d->codes.begin(); it != d->codes.end();)
-      it = it->second >= codes_before ? d->codes.erase(it) : std::next(it);
-  };
+  int32_t rc = dict_intern(d, units, offsets, is_null, n, codes.data());
   if (rc != TSC_OK) {
-    roll_back();
+    d->truncate(d->n_codes);   // forget the strings interned by this call
     return rc;
   }
-  if (!new_offs.empty()) {
+  if (d->host_codes() > d->n_codes) {   // upload the new tail of the dictionary
     TSC_CUDA(cudaSetDevice(ix->device));
-    rc = dict_reserve(ix, d, d->n_units + new_units.size(), (uint64_t)d->n_codes + new_offs.size());
+    rc = dict_reserve(ix, d, d->h_units.size(), d->host_codes());
     if (rc != TSC_OK) {
-      roll_back();
+      d->truncate(d->n_codes);
       return rc;
     }
     cudaError_t e = cudaSuccess;
-    if (!new_units.empty())
-      e = cudaMemcpyAsync(d->d_units + d->n_units, new_units.data(), new_units.size() * 2,
-                          cudaMemcpyHostToDevice, ix->stream);
+    if (d->h_units.size() > d->n_units)
+      e = cudaMemcpyAsync(d->d_units + d->n_units, d->h_units.data() + d->n_units,
+                          (d->h_units.size() - d->n_units) * 2, cudaMemcpyHostToDevice, ix->stream);
     if (e == cudaSuccess)
-      e = cudaMemcpyAsync(d->d_offs + d->n_codes + 1, new_offs.data(), new_offs.size() * 8,
-                          cudaMemcpyHostToDevice, ix->stream);
+      e = cudaMemcpyAsync(d->d_offs + d->n_codes + 1, d->h_offs.data() + d->n_codes + 1,
+                          (size_t)(d->host_codes() - d->n_codes) * 8, cudaMemcpyHostToDevice,
+                          ix->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
     if (e != cudaSuccess) {
-      roll_back();
+      d->truncate(d->n_codes);
       set_error("column_append_text: dictionary upload failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
       return TSC_ERR_CUDA;
     }
-    d->n_units += new_units.size();
-    d->n_codes += (uint32_t)new_offs.size();
+    d->n_units = d->h_units.size();
+    d->n_codes = d->host_codes();
   }
   return column_write_locked(ix, c, first_node_id, codes.data(), is_null, n);
 }
@@ -503,12 +497,12 @@ int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, cons
     const unsigned blocks = (unsigned)(want < (uint64_t)ix->sm_count * 8 ? want : ix->sm_count * 8);
     if (d_dict_bits)
       where_eval_kernel<true><<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, d_dict_bits,
-                                                      ix->rows, n_slots, ix->d_filter,
-                                                      ix->d_live_count);
+                                                      ix->rows, n_slots, where_prefetch_steps(),
+                                                      ix->d_filter, ix->d_live_count);
     else
       where_eval_kernel<false><<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, nullptr,
-                                                       ix->rows, n_slots, ix->d_filter,
-                                                       ix->d_live_count);
+                                                       ix->rows, n_slots, where_prefetch_steps(),
+                                                       ix->d_filter, ix->d_live_count);
     TSC_CUDA(cudaGetLastError());
     ix->launches++;
     TSC_CUDA(cudaMemcpyAsync(&matched, ix->d_live_count, 8, cudaMemcpyDeviceToHost, st));
@@ -599,8 +593,6 @@ int32_t tsc_selftest_where_text(const tsc_where_op *ops, uint32_t n_ops, const v
   // text columns: intern the rows like tsc_index_column_append_text does
   struct HostDict {
     TextDict d;
-    std::vector<uint16_t> units;
-    std::vector<uint64_t> offs{0};
     std::vector<uint64_t> codes;
   };
   std::vector<HostDict> dicts(n_cols);
@@ -614,10 +606,9 @@ int32_t tsc_selftest_where_text(const tsc_where_op *ops, uint32_t n_ops, const v
       HostDict &h = dicts[i];
       h.codes.resize(n_rows);
       int32_t rc = dict_intern(&h.d, row_units, row_offsets + (size_t)i * (n_rows + 1),
-                               col_is_null + (size_t)i * n_rows, n_rows, h.codes.data(), &h.units,
-                               &h.offs);
+                               col_is_null + (size_t)i * n_rows, n_rows, h.codes.data());
       if (rc != TSC_OK) return rc;
-      h.d.n_codes = (uint32_t)h.offs.size() - 1;
+      h.d.n_codes = h.d.host_codes();
     }
     info.push_back({col_ids[i], col_types[i], dicts[i].d.n_codes});
   }
@@ -643,8 +634,8 @@ int32_t tsc_selftest_where_text(const tsc_where_op *ops, uint32_t n_ops, const v
   for (size_t l = 0; l < plan.leaves.size(); l++) {
     const HostDict &h = dicts[src[plan.leaf_slot[l]]];
     for (uint32_t code = 0; code < h.d.n_codes; code++)
-      if (text_leaf_match(plan.leaves[l], h.units.data() + h.offs[code],
-                          (uint32_t)(h.offs[code + 1] - h.offs[code]), text_units,
+      if (text_leaf_match(plan.leaves[l], h.d.h_units.data() + h.d.h_offs[code],
+                          (uint32_t)(h.d.h_offs[code + 1] - h.d.h_offs[code]), text_units,
                           plan.list.data()))
         bits[plan.leaves[l].bits_off + (code >> 5)] |= 1u << (code & 31);
   }
