@@ -1,7 +1,11 @@
 """A/B of the WHERE row pass's L2 prefetch distance (diagnostics build: TSC_WHERE_PF) on one
 GPU, plus the text-column append rate. One index, 12.5M rows; numeric program = config c5w's,
 text program = config c5t's. Prints one JSON line.
-  python tools/where_ab.py            (needs `make diag`)"""
+  python tools/where_ab.py            (needs `make diag`)
+
+HISTORY: ran once (profiles/r02f_where_prefetch_ab.json). The prefetch lost at every distance
+(numeric call 88 us without, 95-101 us with), so the kernel code and the TSC_WHERE_PF switch it
+drove were deleted again; kept as the record of how the A/B was made (it ran from tools/)."""
 import json
 import os
 import sys

@@ -8,18 +8,6 @@
 
 using namespace tsc;
 
-// how many of its own steps ahead a warp of where_eval_kernel prefetches into L2 (0 = off)
-constexpr uint32_t kWherePrefetchSteps = 1;
-#ifdef TSC_DIAG
-#include <stdlib.h>
-static uint32_t where_prefetch_steps() {   // diagnostics build only: TSC_WHERE_PF = 0 / 1 / 2 ...
-  const char *v = getenv("TSC_WHERE_PF");
-  return v && *v ? (uint32_t)atoi(v) : kWherePrefetchSteps;
-}
-#else
-static uint32_t where_prefetch_steps() { return kWherePrefetchSteps; }
-#endif
-
 static AttrColumn *find_column(Index *ix, uint32_t id) {
   for (auto &c : ix->columns)
     if (c.id == id) return &c;
@@ -497,12 +485,12 @@ int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, cons
     const unsigned blocks = (unsigned)(want < (uint64_t)ix->sm_count * 8 ? want : ix->sm_count * 8);
     if (d_dict_bits)
       where_eval_kernel<true><<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, d_dict_bits,
-                                                      ix->rows, n_slots, where_prefetch_steps(),
-                                                      ix->d_filter, ix->d_live_count);
+                                                      ix->rows, n_slots, ix->d_filter,
+                                                      ix->d_live_count);
     else
       where_eval_kernel<false><<<blocks, 256, 0, st>>>(prog, cols, ix->d_where_args, nullptr,
-                                                       ix->rows, n_slots, where_prefetch_steps(),
-                                                       ix->d_filter, ix->d_live_count);
+                                                       ix->rows, n_slots, ix->d_filter,
+                                                       ix->d_live_count);
     TSC_CUDA(cudaGetLastError());
     ix->launches++;
     TSC_CUDA(cudaMemcpyAsync(&matched, ix->d_live_count, 8, cudaMemcpyDeviceToHost, st));

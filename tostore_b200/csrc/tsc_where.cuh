@@ -284,15 +284,13 @@ __device__ __forceinline__ unsigned where_step(const WhereProgram &prog, const W
   return count;
 }
 
-// pf_steps > 0: before a step, the warp asks L2 for the column data of the step it will run
-// pf_steps rounds later — one prefetch instruction per column (lane l names sector l of the
-// step's 1 KB), so that step's loads find their lines in L2 instead of waiting for DRAM.
 template <bool TEXT>
 __global__ void __launch_bounds__(256)
 where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_constant__ WhereCols cols,
                   const uint64_t *__restrict__ args, const uint32_t *__restrict__ dict_bits,
-                  uint64_t n_rows, uint32_t n_slots, uint32_t pf_steps,
-                  uint32_t *__restrict__ out_bits, unsigned long long *__restrict__ matched) {
+                  uint64_t n_rows, uint32_t n_slots, uint32_t *__restrict__ out_bits,
+                  unsigned long long *__restrict__ matched) {
+  (void)n_slots;
   const int lane = threadIdx.x & 31;
   const uint64_t n_words = (n_rows + 31) / 32;
   const uint64_t n_groups = (n_words + kWhereWords - 1) / kWhereWords;
@@ -301,14 +299,6 @@ where_eval_kernel(const __grid_constant__ WhereProgram prog, const __grid_consta
   unsigned long long local = 0;
   for (uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups;
        g += warps) {
-    if (pf_steps) {
-      const uint64_t gp = g + (uint64_t)pf_steps * warps;
-      if (gp < full_groups)
-        for (uint32_t c = 0; c < n_slots; c++) {
-          const char *p = reinterpret_cast<const char *>(cols.values[c] + gp * (kWhereWords * 32)) + lane * 32;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-        }
-    }
     if (g < full_groups)
       local += where_step<TEXT, true>(prog, cols, args, dict_bits, n_rows, n_words, g, lane, out_bits);
     else
