@@ -347,3 +347,85 @@ def test_store_vector_search_with_text_where():
         assert [r.primaryKey for r in res] == [f"pk{i}" for i in oi2] and oi2[0] != oi[0]
     finally:
         st.close()
+
+
+# ---- committed golden fixtures (tests/golden/golden_where_text.json) --------------------------
+def _dec(v):
+    if isinstance(v, dict) and set(v) == {"u"}:
+        return "".join(chr(c) for c in v["u"])           # one str character per UTF-16 code unit
+    if isinstance(v, list):
+        return [_dec(x) for x in v]
+    if isinstance(v, dict):
+        return {k: _dec(x) for k, x in v.items()}
+    return v
+
+
+def _join_surrogates(v):
+    """The fixture holds code units; Python strings want surrogate PAIRS joined (a lone
+    surrogate stays as it is)."""
+    if isinstance(v, str):
+        return v.encode("utf-16-le", "surrogatepass").decode("utf-16-le", "surrogatepass")
+    if isinstance(v, list):
+        return [_join_surrogates(x) for x in v]
+    if isinstance(v, dict):
+        return {k: _join_surrogates(x) for k, x in v.items()}
+    return v
+
+
+def test_golden_text_where_fixtures_pin_oracle_and_library():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_where_text.json")) as f:
+        g = json.load(f)
+    cols = _join_surrogates(_dec(g["columns"]))
+    cmap = {"title": (0, TEXT), "lang": (1, TEXT), "year": (2, I64)}
+    assert len(g["cases"]) >= 40
+    for case in g["cases"]:
+        cond = _join_surrogates(_dec(case["cond"]))
+        want = [c == "1" for c in case["match"]]
+        assert wo.evaluate_columns(cond, cols, g["types"], n_rows=g["rows"]) == want, cond
+        assert _selftest(W.compile_condition(cond, cmap), cols, g["rows"], col_map=cmap) == want, cond
+
+
+# ---- property test: random trees over text + integer fields (host) -----------------------------
+from hypothesis import HealthCheck, given, settings, strategies as st   # noqa: E402
+
+_ALPHA = ["a", "b", "B", "%", "_", "\n", " ", "é", "\U0001F600", "0"]
+_text = st.lists(st.sampled_from(_ALPHA), max_size=5).map("".join)
+_ints = st.integers(-3, 80)
+
+
+def _text_leaf():
+    simple = st.tuples(st.sampled_from(["=", "!=", "<>", ">", ">=", "<", "<="]), _text | st.none())
+    between = st.tuples(st.just("BETWEEN"), st.fixed_dictionaries({"start": _text, "end": _text}))
+    inlist = st.tuples(st.sampled_from(["IN", "NOT IN"]), st.lists(_text | st.none(), max_size=4))
+    like = st.tuples(st.sampled_from(["LIKE", "NOT LIKE"]), _text | st.none())
+    isnull = st.tuples(st.sampled_from(["IS", "IS NOT"]), st.none())
+    opmap = st.lists(simple | between | inlist | like | isnull, min_size=0, max_size=3).map(dict)
+    return st.dictionaries(st.sampled_from(["name", "tag"]), opmap | _text | st.none(), min_size=1, max_size=2)
+
+
+def _int_leaf():
+    simple = st.tuples(st.sampled_from(["=", "!=", ">", "<="]), _ints | st.none())
+    return st.fixed_dictionaries({"age": st.lists(simple, min_size=1, max_size=2).map(dict) | _ints})
+
+
+_tree = st.recursive(_text_leaf() | _int_leaf(),
+                     lambda kids: st.fixed_dictionaries({"AND": st.lists(kids, max_size=3)})
+                     | st.fixed_dictionaries({"OR": st.lists(kids, max_size=3)}), max_leaves=6)
+
+
+@settings(max_examples=300, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(_tree, st.lists(_text | st.none(), min_size=1, max_size=40), st.integers(0, 1000))
+def test_property_random_text_trees_library_equals_oracle(cond, names, seed):
+    rng = np.random.default_rng(seed)
+    n = len(names)
+    names = [None if v is None else wo.dart_trim(v) for v in names]      # stored values are trimmed
+    cols = {"age": [None if rng.random() < 0.1 else int(rng.integers(0, 80)) for _ in range(n)],
+            "name": names,
+            "tag": [names[int(rng.integers(0, n))] for _ in range(max(n - 3, 0))]}
+    prog = W.compile_condition(cond, COLS)
+    if len(prog.ops) > W.MAX_OPS:
+        return
+    want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
+    assert _selftest(prog, cols, n) == want
