@@ -102,6 +102,16 @@ def convert_value(v, col_type: str):
     """FieldSchema.convertValue for DataType.integer / double / text operands."""
     if v is None:
         return None
+    if col_type == "bool":        # table_schema.dart:1450-1459
+        if isinstance(v, bool):
+            return v
+        if isinstance(v, int):
+            return v != 0
+        if isinstance(v, float):
+            return v != 0.0
+        if isinstance(v, str):
+            return v.lower() in ("true", "1", "yes")
+        raise TypeError(f"unsupported operand {v!r} for a boolean field")
     if col_type == "text":
         if isinstance(v, bool):
             v = "true" if v else "false"
@@ -131,6 +141,8 @@ def _matcher(a, b) -> int:
         return 0 if a is b else (-1 if a is None else 1)
     if isinstance(a, str) and isinstance(b, str):      # text matcher (:225-240)
         return dart_string_compare(a, b)
+    if isinstance(a, bool) and isinstance(b, bool):    # boolean matcher (:242-253): false < true
+        return 0 if a == b else (1 if a else -1)
     return dart_compare(a, b)
 
 
@@ -239,7 +251,8 @@ def evaluate_columns(cond, columns: Dict[str, Sequence], col_types: Dict[str, st
             v = vals[r] if r < len(vals) else None
             if v is not None:
                 t = col_types[name]
-                v = int(v) if t == "i64" else (str(v) if t == "text" else float(v))
+                v = (int(v) if t == "i64" else str(v) if t == "text" else bool(v) if t == "bool"
+                     else float(v))
             rec[name] = v
         out.append(match_record(norm, rec) if norm else True)
     return out

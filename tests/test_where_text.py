@@ -429,3 +429,35 @@ def test_property_random_text_trees_library_equals_oracle(cond, names, seed):
         return
     want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
     assert _selftest(prog, cols, n) == want
+
+
+# ---- boolean fields: 0 / 1 int64 column on the device, convertValue on the host ----------------
+def test_boolean_field_conditions_equal_oracle():
+    """DataType.boolean (convertValue table_schema.dart:1450-1459, matcher value_matcher.dart:242-253:
+    false < true): the host maps values and operands to 0 / 1, the device sees an int64 column."""
+    rng = np.random.default_rng(12)
+    n = 200
+    active = [None if rng.random() < 0.15 else bool(rng.integers(0, 2)) for _ in range(n)]
+    name = [NAMES[int(rng.integers(0, len(NAMES)))] for _ in range(n)]
+    cols = {"active": active, "name": name}
+    types = {"active": "bool", "name": "text"}
+    compile_map = {"active": (5, W.COL_BOOL), "name": (3, TEXT)}
+    device_map = {"active": (5, I64), "name": (3, TEXT)}
+    device_cols = {"active": [None if v is None else int(v) for v in active], "name": name}
+    conds = [{"active": True}, {"active": False}, {"active": {"=": 1}}, {"active": {"=": 0.0}},
+             {"active": {"=": "yes"}}, {"active": {"=": "TRUE"}}, {"active": {"=": "no"}},
+             {"active": {"!=": True}}, {"active": {">": False}}, {"active": {"<=": False}},
+             {"active": {"IN": [True, None]}}, {"active": {"NOT IN": [False]}}, {"active": None},
+             {"active": {"IS NOT": None}}, {"active": {"BETWEEN": {"start": False, "end": True}}},
+             {"active": {">": None}}, {"active": 7},
+             {"AND": [{"active": True}, {"name": {"LIKE": "a%"}}]},
+             {"OR": [{"active": {"IS": None}}, {"AND": [{"active": False}, {"name": {">": "b"}}]}]}]
+    for cond in conds:
+        want = wo.evaluate_columns(cond, cols, types, n_rows=n)
+        got = _selftest(W.compile_condition(cond, compile_map), device_cols, n, col_map=device_map)
+        assert got == want, cond
+    assert 0 < sum(wo.evaluate_columns({"active": True}, cols, types, n_rows=n)) < n
+    with pytest.raises(NotImplementedError):
+        W.compile_condition({"active": {"LIKE": "t%"}}, compile_map)
+    with pytest.raises(TypeError):
+        W.compile_condition({"active": {"=": [1]}}, compile_map)

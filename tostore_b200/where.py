@@ -29,6 +29,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 COL_I64, COL_F64, COL_TEXT = 0, 1, 2
+COL_BOOL = 16     # host-side only: a boolean field is an int64 column of 0 / 1 on the device
 W_LEAF, W_AND, W_OR = 0, 1, 2
 (OP_EQ, OP_NE, OP_GT, OP_GE, OP_LT, OP_LE, OP_BETWEEN, OP_IN, OP_NOT_IN, OP_IS_NULL,
  OP_IS_NOT_NULL, OP_TRUE, OP_FALSE, OP_LIKE, OP_NOT_LIKE) = range(15)
@@ -78,6 +79,20 @@ def convert_text(v) -> str:
     return dart_trim(v)
 
 
+def convert_bool(v) -> int:
+    """`convertValue` for DataType.boolean (table_schema.dart:1450-1459) as the 0 / 1 the
+    device column holds; the boolean matcher orders false < true (value_matcher.dart:242-253)."""
+    if isinstance(v, (bool, np.bool_)):
+        return 1 if v else 0
+    if isinstance(v, (int, np.integer)):
+        return 1 if int(v) != 0 else 0
+    if isinstance(v, (float, np.floating)):
+        return 1 if float(v) != 0.0 else 0
+    if isinstance(v, str):
+        return 1 if v.lower() in ("true", "1", "yes") else 0
+    raise TypeError(f"operand {v!r} cannot be converted for a boolean field")
+
+
 def utf16_units(s: str) -> np.ndarray:
     """A string's UTF-16 code units (`String.codeUnits`); lone surrogates pass through."""
     return np.frombuffer(s.encode("utf-16-le", "surrogatepass"), dtype=np.uint16)
@@ -100,6 +115,8 @@ def _convert(v, col_type: int):
     (table_schema.dart:1371-1442)."""
     if col_type == COL_TEXT:
         return convert_text(v)
+    if col_type == COL_BOOL:
+        return convert_bool(v)
     if isinstance(v, (bool, np.bool_)):
         v = 1 if v else 0
     if isinstance(v, np.integer):
@@ -194,6 +211,9 @@ def _emit(cond, columns, prog: WhereProgram) -> None:
         if name not in columns:
             raise KeyError(f"WHERE names field {field!r} which has no attribute column")
         col, t = columns[name]
+        if t == COL_BOOL:
+            c = _bool_operands(c)
+            t = COL_I64
         if isinstance(c, dict):
             n_ops = 0
             for op, ov in c.items():                   # operators of one field: OR
@@ -208,6 +228,25 @@ def _emit(cond, columns, prog: WhereProgram) -> None:
         n_fields += 1
     if n_fields != 1:
         prog._node(W_AND, n_fields)
+
+
+def _bool_operands(c):
+    """Operands of a condition on a boolean field -> 0 / 1 (None stays None)."""
+    cv = lambda x: None if x is None else convert_bool(x)   # noqa: E731
+    if not isinstance(c, dict):
+        return cv(c)
+    out = {}
+    for op, ov in c.items():
+        up = op.upper()
+        if up == "BETWEEN" and isinstance(ov, dict) and "start" in ov and "end" in ov:
+            out[op] = {"start": cv(ov["start"]), "end": cv(ov["end"])}
+        elif up in ("IN", "NOT IN") and isinstance(ov, (list, tuple)):
+            out[op] = [cv(x) for x in ov]
+        elif up in ("LIKE", "NOT LIKE"):
+            raise NotImplementedError(f"{up} on a boolean field has no columnar GPU form")
+        else:
+            out[op] = cv(ov)
+    return out
 
 
 def _emit_operator(op: str, ov, col: int, t: int, prog: WhereProgram) -> None:
