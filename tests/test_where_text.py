@@ -461,3 +461,29 @@ def test_boolean_field_conditions_equal_oracle():
         W.compile_condition({"active": {"LIKE": "t%"}}, compile_map)
     with pytest.raises(TypeError):
         W.compile_condition({"active": {"=": [1]}}, compile_map)
+
+
+def test_datetime_field_is_a_text_column_of_iso_strings():
+    """DataType.datetime: stored as DateTime.toIso8601String(), compared as a string (the datetime
+    matcher is the text matcher, value_matcher.dart:211-240)."""
+    import datetime as dt
+    cv = W.convert_datetime
+    assert cv(dt.datetime(2024, 1, 2, 3, 4, 5, 6000)) == "2024-01-02T03:04:05.006"
+    assert cv(dt.datetime(2024, 1, 2, 3, 4, 5, 6007)) == "2024-01-02T03:04:05.006007"
+    assert cv(dt.datetime(2024, 1, 2, 3, 4, 5)) == "2024-01-02T03:04:05.000"
+    assert cv(dt.datetime(987, 12, 31, 23, 59, 59, 999000, tzinfo=dt.timezone.utc)) == "0987-12-31T23:59:59.999Z"
+    assert cv("2024-01-02T03:04:05.000") == "2024-01-02T03:04:05.000"
+    with pytest.raises(ValueError):
+        cv(dt.datetime(2024, 1, 2, tzinfo=dt.timezone(dt.timedelta(hours=2))))
+    days = [None if i % 9 == 0 else cv(dt.datetime(2024, 1 + i % 12, 1 + i % 28, i % 24)) for i in range(150)]
+    cols = {"created": days}
+    compile_map, device_map = {"created": (6, W.COL_DATETIME)}, {"created": (6, TEXT)}
+    for cond in ({"created": {">=": dt.datetime(2024, 6, 1)}},
+                 {"created": {"BETWEEN": {"start": dt.datetime(2024, 3, 1), "end": "2024-04-30T23:59:59.999"}}},
+                 {"created": {"LIKE": "2024-02-%"}}, {"created": {"!=": days[1]}}, {"created": None},
+                 {"created": {"IN": [days[1], days[2], dt.datetime(1999, 1, 1)]}}):
+        as_text = {"created": W._map_operands(cond["created"], cv, "datetime")}
+        want = wo.evaluate_columns(as_text, cols, {"created": "text"}, n_rows=150)
+        got = _selftest(W.compile_condition(cond, compile_map), cols, 150, col_map=device_map)
+        assert got == want, cond
+    assert sum(wo.evaluate_columns({"created": {"LIKE": "2024-02-%"}}, cols, {"created": "text"}, n_rows=150)) > 0

@@ -121,9 +121,10 @@ class GpuVectorStore:
         """`TableSchema` vector field + `IndexSchema(type: IndexType.vector)`.
         Unlike the reference (no validation) bad dims raise.
         attributeFields (new, additive): fields of the table — name -> 'integer' | 'double' |
-        'text' | 'boolean' (DataType names, model/table_schema.dart) — kept column-wise on the
-        GPU (text: dictionary-encoded; boolean: 0 / 1) so `vectorSearch(where=...)` can
-        prefilter on them."""
+        'text' | 'boolean' | 'datetime' (DataType names, model/table_schema.dart) — kept
+        column-wise on the GPU (text: dictionary-encoded; boolean: 0 / 1; datetime: its stored
+        ISO-8601 string, compared as text like the reference does) so
+        `vectorSearch(where=...)` can prefilter on them."""
         cfg = indexConfig or VectorIndexConfig()
         eng = GpuVectorIndex(fieldConfig.dimensions, int(cfg.distanceMetric),
                              capacity_rows=self._capacity, src_precision=1,
@@ -131,12 +132,13 @@ class GpuVectorStore:
                              k_max=self._k_max, nq_max=64)
         ix = _VectorIndex(tableName, fieldName, fieldConfig, cfg, eng)
         for cid, (name, dtype) in enumerate((attributeFields or {}).items()):
-            if dtype not in ("integer", "double", "text", "boolean"):
-                raise ValueError(f"attribute field {name!r}: only integer / double / text / boolean "
-                                 "fields have a GPU column")
-            t = {"integer": _where.COL_I64, "double": _where.COL_F64, "text": _where.COL_TEXT,
-                 "boolean": _where.COL_BOOL}[dtype]
-            eng.column_create(cid, _where.COL_I64 if t == _where.COL_BOOL else t)
+            kinds = {"integer": _where.COL_I64, "double": _where.COL_F64, "text": _where.COL_TEXT,
+                     "boolean": _where.COL_BOOL, "datetime": _where.COL_DATETIME}
+            if dtype not in kinds:
+                raise ValueError(f"attribute field {name!r}: only {' / '.join(kinds)} fields have a GPU column")
+            t = kinds[dtype]
+            eng.column_create(cid, {_where.COL_BOOL: _where.COL_I64,
+                                    _where.COL_DATETIME: _where.COL_TEXT}.get(t, t))
             ix.attributes[name] = (cid, t)
         self._indexes.setdefault(tableName, []).append(ix)
 

@@ -30,6 +30,7 @@ import numpy as np
 
 COL_I64, COL_F64, COL_TEXT = 0, 1, 2
 COL_BOOL = 16     # host-side only: a boolean field is an int64 column of 0 / 1 on the device
+COL_DATETIME = 17  # host-side only: a datetime field is a text column of ISO-8601 strings
 W_LEAF, W_AND, W_OR = 0, 1, 2
 (OP_EQ, OP_NE, OP_GT, OP_GE, OP_LT, OP_LE, OP_BETWEEN, OP_IN, OP_NOT_IN, OP_IS_NULL,
  OP_IS_NOT_NULL, OP_TRUE, OP_FALSE, OP_LIKE, OP_NOT_LIKE) = range(15)
@@ -93,6 +94,32 @@ def convert_bool(v) -> int:
     raise TypeError(f"operand {v!r} cannot be converted for a boolean field")
 
 
+def convert_datetime(v) -> str:
+    """DataType.datetime is stored as `DateTime.toIso8601String()` and compared as a STRING
+    (the datetime matcher is the text matcher, value_matcher.dart:211-240). A `datetime` is
+    formatted the way Dart does (`yyyy-MM-ddTHH:mm:ss.mmm[uuu][Z]`: milliseconds always,
+    microseconds only when non-zero, `Z` for UTC); a string is taken to be in that stored form
+    already — the reference would re-parse it (`DateTime.parse`, table_schema.dart:1462-1475),
+    which has no exact restatement here."""
+    import datetime as _dt
+    if isinstance(v, str):
+        return v
+    if isinstance(v, _dt.datetime):
+        utc = False
+        if v.tzinfo is not None:
+            if v.utcoffset() != _dt.timedelta(0):
+                raise ValueError("a Dart DateTime is local or UTC: convert the operand to UTC first")
+            utc = True
+        if not 0 <= v.year <= 9999:
+            raise ValueError("year outside 0..9999")
+        s = "%04d-%02d-%02dT%02d:%02d:%02d.%03d" % (v.year, v.month, v.day, v.hour, v.minute, v.second,
+                                                    v.microsecond // 1000)
+        if v.microsecond % 1000:
+            s += "%03d" % (v.microsecond % 1000)
+        return s + ("Z" if utc else "")
+    raise TypeError(f"operand {v!r} cannot be converted for a datetime field")
+
+
 def utf16_units(s: str) -> np.ndarray:
     """A string's UTF-16 code units (`String.codeUnits`); lone surrogates pass through."""
     return np.frombuffer(s.encode("utf-16-le", "surrogatepass"), dtype=np.uint16)
@@ -117,6 +144,8 @@ def _convert(v, col_type: int):
         return convert_text(v)
     if col_type == COL_BOOL:
         return convert_bool(v)
+    if col_type == COL_DATETIME:
+        return convert_datetime(v)
     if isinstance(v, (bool, np.bool_)):
         v = 1 if v else 0
     if isinstance(v, np.integer):
@@ -212,8 +241,11 @@ def _emit(cond, columns, prog: WhereProgram) -> None:
             raise KeyError(f"WHERE names field {field!r} which has no attribute column")
         col, t = columns[name]
         if t == COL_BOOL:
-            c = _bool_operands(c)
+            c = _map_operands(c, convert_bool, "boolean")
             t = COL_I64
+        elif t == COL_DATETIME:
+            c = _map_operands(c, convert_datetime, "datetime")
+            t = COL_TEXT
         if isinstance(c, dict):
             n_ops = 0
             for op, ov in c.items():                   # operators of one field: OR
@@ -230,9 +262,10 @@ def _emit(cond, columns, prog: WhereProgram) -> None:
         prog._node(W_AND, n_fields)
 
 
-def _bool_operands(c):
-    """Operands of a condition on a boolean field -> 0 / 1 (None stays None)."""
-    cv = lambda x: None if x is None else convert_bool(x)   # noqa: E731
+def _map_operands(c, conv, what):
+    """Operands of a condition on a host-mapped field (boolean -> 0 / 1, datetime -> ISO-8601
+    string) through `conv`; None stays None."""
+    cv = lambda x: None if x is None else conv(x)   # noqa: E731
     if not isinstance(c, dict):
         return cv(c)
     out = {}
@@ -242,7 +275,7 @@ def _bool_operands(c):
             out[op] = {"start": cv(ov["start"]), "end": cv(ov["end"])}
         elif up in ("IN", "NOT IN") and isinstance(ov, (list, tuple)):
             out[op] = [cv(x) for x in ov]
-        elif up in ("LIKE", "NOT LIKE"):
+        elif up in ("LIKE", "NOT LIKE") and what == "boolean":
             raise NotImplementedError(f"{up} on a boolean field has no columnar GPU form")
         else:
             out[op] = cv(ov)
