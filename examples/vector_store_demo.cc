@@ -88,7 +88,7 @@ int main() {
   evaluate("name_ne", QueryCondition().where("name", "!=", std::string("bob")));        // NULL != x is true
   evaluate("name_gt", QueryCondition().where("name", ">", std::string("b")));
   evaluate("name_in", QueryCondition().whereIn("name", {std::string("bob"), std::string("zo\xc3\xab"), std::string("")}));
-  evaluate("name_like_prefix", QueryCondition().where("name", "LIKE", std::string("al%")));
+  evaluate("name_like_prefix", QueryCondition().whereStartsWith("name", "al"));
   evaluate("name_like_any", QueryCondition().where("name", "LIKE", std::string("%")));  // not across a line break
   evaluate("name_like_one", QueryCondition().where("name", "LIKE", std::string("a_b")));
   evaluate("name_like_astral", QueryCondition().where("name", "LIKE", std::string("__ grin")));

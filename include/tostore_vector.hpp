@@ -150,6 +150,17 @@ class QueryCondition {
     groups_.back().push_back(Leaf{field, "BETWEEN", {std::move(start), std::move(end)}});
     return *this;
   }
+  // convenience forms, one `where` each (query_condition.dart:574-656); text fields only
+  QueryCondition &whereLike(const std::string &field, const std::string &pattern) { return where(field, "LIKE", pattern); }
+  QueryCondition &whereNotLike(const std::string &field, const std::string &pattern) {
+    return where(field, "NOT LIKE", pattern);
+  }
+  QueryCondition &whereContains(const std::string &field, const std::string &v) { return where(field, "LIKE", "%" + v + "%"); }
+  QueryCondition &whereNotContains(const std::string &field, const std::string &v) {
+    return where(field, "NOT LIKE", "%" + v + "%");
+  }
+  QueryCondition &whereStartsWith(const std::string &field, const std::string &v) { return where(field, "LIKE", v + "%"); }
+  QueryCondition &whereEndsWith(const std::string &field, const std::string &v) { return where(field, "LIKE", "%" + v); }
   QueryCondition &whereNull(const std::string &field) { return where(field, "IS"); }
   QueryCondition &whereNotNull(const std::string &field) { return where(field, "IS NOT"); }
   bool isEmpty() const {

@@ -487,3 +487,27 @@ def test_datetime_field_is_a_text_column_of_iso_strings():
         got = _selftest(W.compile_condition(cond, compile_map), cols, 150, col_map=device_map)
         assert got == want, cond
     assert sum(wo.evaluate_columns({"created": {"LIKE": "2024-02-%"}}, cols, {"created": "text"}, n_rows=150)) > 0
+
+
+def test_query_condition_convenience_builders():
+    """whereLike / whereContains / whereStartsWith / whereEndsWith / whereEmpty / whereContainsAny ...
+    (query/query_condition.dart:574-678) produce the same maps as the spelled-out `where` calls."""
+    Q = W.QueryCondition
+    assert Q().whereContains("name", "li").build() == {"name": {"LIKE": "%li%"}}
+    assert Q().whereNotContains("name", "li").build() == {"name": {"NOT LIKE": "%li%"}}
+    assert Q().whereStartsWith("name", "al").build() == {"name": {"LIKE": "al%"}}
+    assert Q().whereEndsWith("name", "b").build() == {"name": {"LIKE": "%b"}}
+    assert Q().whereLike("name", "a_b").whereGreaterThan("age", 3).build() == \
+        {"AND": [{"name": {"LIKE": "a_b"}}, {"age": {">": 3}}]}
+    assert Q().whereEmpty("name").build() == {"OR": [{"name": {"IS": None}}, {"name": {"=": ""}}]}
+    assert Q().whereNotEmpty("name").build() == {"AND": [{"name": {"IS NOT": None}}, {"name": {"!=": ""}}]}
+    cols = _columns()
+    n = len(cols["age"])
+    for qc in (Q().whereContains("name", "li").whereLessThanOrEqualTo("age", 40),
+               Q().whereEmpty("name").whereNotEqual("tag", "red"),
+               Q().where("age", ">", 70).orWhere("name", "LIKE", "z%").whereContainsAny("tag", ["ee", "lu"]),
+               Q().whereContainsAny("name", ["ob", "\n", "%"])):
+        cond = qc.build()
+        want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
+        assert _selftest(W.compile_condition(cond, COLS), cols, n) == want, cond
+        assert any(want) and not all(want), cond

@@ -353,6 +353,69 @@ class QueryCondition:
     def whereNotNull(self, field):
         return self.where(field, "IS NOT", None)
 
+    # convenience forms, one `where` each (query_condition.dart:574-678)
+    def whereLike(self, field, pattern):
+        return self.where(field, "LIKE", pattern)
+
+    def whereNotLike(self, field, pattern):
+        return self.where(field, "NOT LIKE", pattern)
+
+    def whereContains(self, field, value):
+        return self.where(field, "LIKE", f"%{value}%")
+
+    def whereNotContains(self, field, value):
+        return self.where(field, "NOT LIKE", f"%{value}%")
+
+    def whereStartsWith(self, field, prefix):
+        return self.where(field, "LIKE", f"{prefix}%")
+
+    def whereEndsWith(self, field, suffix):
+        return self.where(field, "LIKE", f"%{suffix}")
+
+    def whereEqual(self, field, value):
+        return self.where(field, "=", value)
+
+    def whereNotEqual(self, field, value):
+        return self.where(field, "!=", value)
+
+    def whereGreaterThan(self, field, value):
+        return self.where(field, ">", value)
+
+    def whereGreaterThanOrEqualTo(self, field, value):
+        return self.where(field, ">=", value)
+
+    def whereLessThan(self, field, value):
+        return self.where(field, "<", value)
+
+    def whereLessThanOrEqualTo(self, field, value):
+        return self.where(field, "<=", value)
+
+    def whereTrue(self, field):
+        return self.where(field, "=", True)
+
+    def whereFalse(self, field):
+        return self.where(field, "=", False)
+
+    def whereNotEmpty(self, field):
+        return self.whereNotNull(field).where(field, "!=", "")
+
+    def condition(self, other: "QueryCondition") -> "QueryCondition":
+        """AND a whole sub-condition onto the current group (`condition`, :290-367)."""
+        if not other.isEmpty:
+            self._groups[-1].append(other.build())
+        return self
+
+    def whereEmpty(self, field):
+        """NULL or the empty string (:659-663)."""
+        return self.condition(QueryCondition().whereNull(field).orWhere(field, "=", ""))
+
+    def whereContainsAny(self, field, values):
+        """LIKE '%v%' for any of the values (:585-597)."""
+        sub = QueryCondition()
+        for i, v in enumerate(values):
+            (sub.orWhere if i else sub.where)(field, "LIKE", f"%{v}%")
+        return self.condition(sub)
+
     @property
     def isEmpty(self) -> bool:
         return not any(self._groups)
