@@ -94,6 +94,11 @@ def c_oracle():
                                       C.POINTER(C.c_uint32)]
     lib.tso_node_location.restype = None
     lib.tso_max_threads.restype = C.c_int
+    _u16p = np.ctypeslib.ndpointer(dtype=np.uint16, flags="C_CONTIGUOUS")
+    lib.tso_string_compare.argtypes = [_u16p, C.c_uint32, _u16p, C.c_uint32]
+    lib.tso_string_compare.restype = C.c_int
+    lib.tso_like_match.argtypes = [_u16p, C.c_uint32, _u16p, C.c_uint32]
+    lib.tso_like_match.restype = C.c_int
     _LIB = lib
     return lib
 

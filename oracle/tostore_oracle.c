@@ -490,6 +490,43 @@ void tso_node_location(uint64_t node_id, uint32_t per_page, uint32_t pages_per_p
   *slot = (uint32_t)(node_id % per_page);
 }
 
+/* ---- text fields of the WHERE prefilter (handler/value_matcher.dart) ------------------ */
+/* String.compareTo: lexicographic over UTF-16 code units (:211-240) */
+int tso_string_compare(const uint16_t *a, uint32_t na, const uint16_t *b, uint32_t nb) {
+  uint32_t n = na < nb ? na : nb;
+  for (uint32_t i = 0; i < n; i++)
+    if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+  return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+
+/* ValueMatcher.matchesLike (:318-331): ^pattern$ with % -> .* and _ -> . (a RegExp `.` is
+ * one code unit other than \n \r U+2028 U+2029), every other character literal. Restated
+ * as the textbook dynamic programme over (value prefix, pattern prefix) — deliberately a
+ * different algorithm from both the library's two-pointer matcher and the regex restatement
+ * in where_oracle.py, so the three pin each other. */
+int tso_like_match(const uint16_t *s, uint32_t n, const uint16_t *pat, uint32_t m) {
+  uint8_t *prev = (uint8_t *)calloc((size_t)m + 1, 1), *cur = (uint8_t *)calloc((size_t)m + 1, 1);
+  if (!prev || !cur) { free(prev); free(cur); return -1; }
+  /* row 0: the empty value is matched by a pattern prefix made of % only */
+  prev[0] = 1;
+  for (uint32_t j = 1; j <= m; j++) prev[j] = prev[j - 1] && pat[j - 1] == '%';
+  for (uint32_t i = 1; i <= n; i++) {
+    uint16_t c = s[i - 1];
+    int lt = c == 0x000A || c == 0x000D || c == 0x2028 || c == 0x2029;
+    cur[0] = 0;
+    for (uint32_t j = 1; j <= m; j++) {
+      uint16_t p = pat[j - 1];
+      if (p == '%') cur[j] = cur[j - 1] || (!lt && prev[j]);       /* % takes nothing / takes c */
+      else if (p == '_') cur[j] = !lt && prev[j - 1];
+      else cur[j] = p == c && prev[j - 1];
+    }
+    uint8_t *t = prev; prev = cur; cur = t;
+  }
+  int r = prev[m];
+  free(prev); free(cur);
+  return r;
+}
+
 int tso_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -136,6 +136,10 @@ int32_t tso_parse_graph_page_flags(const uint8_t *page, uint32_t page_size,
 void tso_node_location(uint64_t node_id, uint32_t per_page, uint32_t pages_per_partition,
                        uint64_t *partition, uint32_t *local_page, uint32_t *slot);
 
+/* text fields of the WHERE prefilter: String.compareTo (value_matcher.dart:211-240) and
+ * ValueMatcher.matchesLike (:318-331) over UTF-16 code units; like: 1 / 0, -1 = out of memory */
+int tso_string_compare(const uint16_t *a, uint32_t na, const uint16_t *b, uint32_t nb);
+int tso_like_match(const uint16_t *s, uint32_t n, const uint16_t *pat, uint32_t m);
 int tso_max_threads(void);
 
 #ifdef __cplusplus

@@ -511,3 +511,29 @@ def test_query_condition_convenience_builders():
         want = wo.evaluate_columns(cond, cols, TYPES, n_rows=n)
         assert _selftest(W.compile_condition(cond, COLS), cols, n) == want, cond
         assert any(want) and not all(want), cond
+
+
+def test_c_oracle_like_and_compare_equal_the_python_restatement():
+    """Three independent LIKE implementations pin each other: the C oracle's dynamic programme,
+    where_oracle's regex, and (through the other tests) the library's two-pointer matcher."""
+    import oracle
+    lib = oracle.c_oracle()
+    rng = np.random.default_rng(99)
+    alpha = ["a", "b", "%", "_", "\n", "\r", " ", " ", "é", "\U0001F600"]
+
+    def rnd(maxlen):
+        return "".join(alpha[int(i)] for i in rng.integers(0, len(alpha), int(rng.integers(0, maxlen))))
+
+    def units(s):
+        u = np.array(wo.code_units(s), dtype=np.uint16)
+        return (u if u.size else np.zeros(1, dtype=np.uint16)), len(wo.code_units(s))
+
+    for _ in range(3000):
+        s, p = rnd(9), rnd(7)
+        (us, ns), (up, npat) = units(s), units(p)
+        assert lib.tso_like_match(us, ns, up, npat) == int(wo.matches_like(s, p)), (s, p)
+        assert lib.tso_string_compare(us, ns, up, npat) == wo.dart_string_compare(s, p), (s, p)
+    for s, p, want in (("alice", "al%", 1), ("alice\nsmith", "%", 0), ("alice\nsmith", "%\n%", 1), ("", "", 1),
+                       ("", "%%", 1), ("a", "", 0), ("\U0001F600", "__", 1), ("a%b", "a\\%b", 0)):
+        (us, ns), (up, npat) = units(s), units(p)
+        assert lib.tso_like_match(us, ns, up, npat) == want, (s, p)
