@@ -512,6 +512,38 @@ class TostoreCuda {
     }
   }
 
+  /// WHERE prefilter from a set of primary keys (the result of any `db.query(...)`): the rows
+  /// whose key is in `pks` stay searchable for the following searches. Replaces the
+  /// `__pk2nid` lookups (vector_index_manager.dart:1350-1363) + `setFilter`. Returns the number
+  /// of rows selected, -1 on error.
+  static int filterPrimaryKeys(int handle, List<String> pks) {
+    final lib = _open();
+    if (lib == null) return -1;
+    final fn = lib.lookupFunction<
+        Int32 Function(Uint64, Pointer<Uint8>, Pointer<Uint64>, Uint64, Pointer<Uint64>),
+        int Function(int, Pointer<Uint8>, Pointer<Uint64>, int,
+            Pointer<Uint64>)>('tsc_index_filter_primary_keys');
+    final enc = [for (final p in pks) utf8.encode(p)];
+    final total = enc.fold<int>(0, (a, b) => a + b.length);
+    final bytes = calloc<Uint8>(total == 0 ? 1 : total);
+    final offs = calloc<Uint64>(pks.length + 1);
+    final matched = calloc<Uint64>();
+    try {
+      var o = 0;
+      for (var i = 0; i < enc.length; i++) {
+        offs[i] = o;
+        bytes.asTypedList(total == 0 ? 1 : total).setRange(o, o + enc[i].length, enc[i]);
+        o += enc[i].length;
+      }
+      offs[pks.length] = o;
+      return fn(handle, bytes, offs, pks.length, matched) == 0 ? matched.value : -1;
+    } finally {
+      calloc.free(bytes);
+      calloc.free(offs);
+      calloc.free(matched);
+    }
+  }
+
   /// Whole `VectorIndexManager.vectorSearch` body after the precondition checks
   /// (vector_index_manager.dart:514-588) in one call: query prep, exact search, nodeId -> PK,
   /// score. Returns (primaryKey, distance, score) triples, ascending distance; [] on error.

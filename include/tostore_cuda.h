@@ -349,6 +349,17 @@ int32_t tsc_index_set_primary_keys(uint64_t handle, uint64_t first_node_id,
  * key does not fit `capacity` (out_len still reports the needed size). */
 int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *out_utf8,
                                   uint32_t capacity, uint32_t *out_len);
+/* WHERE prefilter from a SET OF PRIMARY KEYS — what any ToStore query returns, so every
+ * condition the reference's own executor can evaluate becomes a vector prefilter: the rows
+ * whose key (tsc_index_set_primary_keys) is in the set stay searchable, as after
+ * tsc_index_set_filter with the corresponding bitmap. Replaces the `<index>__pk2nid` lookups
+ * (core/vector_index_manager.dart:1350-1363) with a hash lookup in the library. Unknown and
+ * empty keys are ignored; a key mapped by several node ids selects the highest. keys: n
+ * utf-8 strings, key i = utf8 [offsets[i], offsets[i + 1]). out_matched (optional): rows
+ * selected. HOST buffers. */
+int32_t tsc_index_filter_primary_keys(uint64_t handle, const uint8_t *utf8,
+                                      const uint64_t *offsets, uint64_t n,
+                                      uint64_t *out_matched);
 /* tsc_vector_search + the reference's result assembly (:576-587): results whose node
  * has no mapping are dropped, the rest stay in ascending distance order. out_pk_utf8
  * receives the concatenated keys, out_pk_offsets [k+1] their boundaries. */
@@ -456,6 +467,12 @@ int32_t tsc_selftest_host_index(uint64_t capacity_rows, uint64_t first_node_id,
 int32_t tsc_selftest_pk_assemble(uint64_t handle, uint32_t k, int64_t *ids, double *dist,
                                  double *score, uint8_t *out_pk_utf8, uint64_t pk_capacity,
                                  uint64_t *out_pk_offsets, uint32_t *inout_count);
+/* self-test hook (no GPU): the bitmap tsc_index_filter_primary_keys would install (64-bit
+ * words, LSB first), computed over the handle's primary-key table; works on a host-only
+ * index. */
+int32_t tsc_selftest_pk_filter_bitmap(uint64_t handle, const uint8_t *utf8,
+                                      const uint64_t *offsets, uint64_t n, uint64_t *out_words,
+                                      uint64_t n_words, uint64_t *out_matched);
 
 #ifdef __cplusplus
 }

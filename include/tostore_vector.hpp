@@ -512,6 +512,29 @@ class GpuVectorStore {
     return n;
   }
 
+  // WHERE prefilter from a set of primary keys (new, additive) — e.g. the result of any query the
+  // reference's executor ran: restrict the next searches of (tableName, fieldName) to these rows;
+  // std::nullopt clears it. Returns the number of rows selected.
+  uint64_t setWhereFilter(const std::string &tableName, const std::string &fieldName,
+                          const std::optional<std::vector<std::string>> &primaryKeys) {
+    Index *ix = find(tableName, fieldName);
+    if (!ix) return 0;
+    if (!primaryKeys) {
+      check(tsc_index_set_filter(ix->handle, nullptr, 0), "tsc_index_set_filter");
+      return 0;
+    }
+    std::string bytes;
+    std::vector<uint64_t> offs{0};
+    for (auto &pk : *primaryKeys) {
+      bytes += pk;
+      offs.push_back(bytes.size());
+    }
+    uint64_t matched = 0;
+    check(tsc_index_filter_primary_keys(ix->handle, (const uint8_t *)bytes.data(), offs.data(), primaryKeys->size(),
+                                        &matched), "tsc_index_filter_primary_keys");
+    return matched;
+  }
+
   // ToStore.vectorSearch (tostore.dart:493-511). `where` (new, additive) is evaluated on the
   // GPU into the prefilter bitmap; nullptr searches every live row.
   std::vector<VectorSearchResult> vectorSearch(const std::string &tableName, const std::string &fieldName,

@@ -137,3 +137,41 @@ def test_concurrent_callers_share_one_handle_safely():
         for t in threads:
             t.join()
     assert not errors, errors[:3]
+
+
+def _pk_bitmap(ix, pks, n_rows):
+    """tsc_selftest_pk_filter_bitmap: the bitmap tsc_index_filter_primary_keys would install."""
+    blob, offs, n = ix._key_blob(pks)
+    words = np.zeros((n_rows + 63) // 64 + 2, dtype=np.uint64)
+    matched = C.c_uint64(0)
+    N.check(ix._lib.tsc_selftest_pk_filter_bitmap(ix.handle, blob.ctypes.data, offs.ctypes.data, n,
+                                                  words.ctypes.data, words.size, C.byref(matched)),
+            "pk_filter_bitmap")
+    bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:n_rows].astype(bool)
+    assert not np.unpackbits(words.view(np.uint8), bitorder="little")[n_rows:].any()
+    return bits, matched.value
+
+
+def test_filter_by_primary_keys_bitmap():
+    """The `__pk2nid` role (core/vector_index_manager.dart:1350-1363): a set of primary keys -> the
+    rows that stay searchable. Unknown / empty keys are ignored, duplicates count once, tombstoned
+    mappings are not selectable, a re-mapped key selects the highest node id, and the reverse map
+    follows later changes of the table."""
+    n = 300
+    with HostIndex(400, first_node_id=50) as ix:
+        pks = [f"k{i}" if i % 7 else f"键-{i}" for i in range(n)]
+        ix.set_primary_keys(pks, first_node_id=50)
+        rng = np.random.default_rng(4)
+        pick = sorted(set(int(i) for i in rng.integers(0, n, 90)))
+        bits, matched = _pk_bitmap(ix, [pks[i] for i in pick] + ["nobody", "", None, pks[pick[0]]], n)
+        assert matched == len(pick) and np.nonzero(bits)[0].tolist() == pick
+        bits, matched = _pk_bitmap(ix, [], n)
+        assert matched == 0 and not bits.any()
+        # tombstone a selected row, re-map another key to a later node id
+        ix.set_primary_keys([""], first_node_id=50 + pick[1])
+        ix.set_primary_keys([pks[pick[2]]], first_node_id=50 + n)          # same key, node id 350
+        bits, matched = _pk_bitmap(ix, [pks[i] for i in pick], n + 1)
+        want = [i for i in pick if i not in (pick[1], pick[2])] + [n]
+        assert np.nonzero(bits)[0].tolist() == sorted(want) and matched == len(want)
+        with pytest.raises(TscError):                                       # device entry point: no GPU behind it
+            ix.filter_primary_keys(["k1"])

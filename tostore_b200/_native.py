@@ -31,6 +31,7 @@ EXPORTS = (
     "tsc_ngh_read_meta", "tsc_index_load_ngh", "tsc_selftest_ngh_walk",
     "tsc_selftest_where", "tsc_selftest_host_index", "tsc_selftest_pk_assemble",
     "tsc_index_set_primary_keys", "tsc_index_get_primary_key", "tsc_vector_search_pk",
+    "tsc_index_filter_primary_keys", "tsc_selftest_pk_filter_bitmap",
 )
 
 TSC_OK = 0
@@ -150,6 +151,8 @@ def lib():
     L.tsc_selftest_pk_assemble.argtypes = [u64, u32, vp, vp, vp, vp, u64, vp, C.POINTER(u32)]
     L.tsc_index_set_primary_keys.argtypes = [u64, u64, vp, vp, u64]
     L.tsc_index_get_primary_key.argtypes = [u64, u64, vp, u32, C.POINTER(u32)]
+    L.tsc_index_filter_primary_keys.argtypes = [u64, vp, vp, u64, C.POINTER(u64)]
+    L.tsc_selftest_pk_filter_bitmap.argtypes = [u64, vp, vp, u64, vp, u64, C.POINTER(u64)]
     L.tsc_vector_search_pk.argtypes = [u64, vp, u64, u32, C.c_double, vp, vp, vp, vp, u64, vp,
                                        C.POINTER(u32)]
     L.tsc_selftest_crc32.argtypes = [vp, u32]

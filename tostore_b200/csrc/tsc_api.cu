@@ -539,6 +539,8 @@ int32_t ix_clear(Index *ix) {
   ix->pk_off.clear();
   ix->pk_len.clear();
   ix->pk_arena.clear();
+  ix->pk_rev.clear();
+  ix->pk_rev_valid = false;
   return TSC_OK;
 }
 

@@ -330,6 +330,20 @@ int32_t grp_set_primary_keys(Group &g, uint64_t first_node_id, const uint8_t *ut
   });
 }
 
+// every shard looks the keys up in ITS table and installs its part of the filter
+int32_t grp_filter_primary_keys(Group &g, const uint8_t *utf8, const uint64_t *offsets, uint64_t n,
+                                uint64_t *out_matched) {
+  uint64_t total = 0;
+  for (auto &s : g.shards) {
+    uint64_t m = 0;
+    int32_t rc = ix_filter_primary_keys(s.get(), utf8, offsets, n, &m);
+    if (rc != TSC_OK) return rc;
+    total += m;
+  }
+  if (out_matched) *out_matched = total;
+  return TSC_OK;
+}
+
 int32_t grp_get_primary_key(Group &g, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
                             uint32_t *out_len) {
   if (!out_len) {

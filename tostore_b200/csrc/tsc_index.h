@@ -11,6 +11,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/tostore_cuda.h"
@@ -233,6 +234,10 @@ struct Index {
   std::vector<uint64_t> pk_off;       // per shard row: start in pk_arena
   std::vector<uint32_t> pk_len;       // per shard row: byte length, 0 = unmapped / tombstone
   std::vector<char> pk_arena;         // append-only utf-8 bytes
+  // key -> shard row (the role of `<index>__pk2nid`), rebuilt from the table above when a filter
+  // by primary keys needs it after the table changed
+  std::unordered_map<std::string, uint64_t> pk_rev;
+  bool pk_rev_valid = false;
 
   // attribute columns for the WHERE prefilter
   std::vector<AttrColumn> columns;
@@ -343,6 +348,8 @@ int32_t ix_filter_where(Index *ix, const tsc_where_op *ops, uint32_t n_ops, cons
                         uint32_t n_in_args, const WhereTexts &texts, uint64_t *out_matched);
 int32_t ix_set_primary_keys(Index *ix, uint64_t first_node_id, const uint8_t *utf8,
                             const uint64_t *offsets, uint64_t n);
+int32_t ix_filter_primary_keys(Index *ix, const uint8_t *utf8, const uint64_t *offsets, uint64_t n,
+                               uint64_t *out_matched);
 int32_t ix_get_primary_key(Index *ix, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
                            uint32_t *out_len);
 int32_t ix_load_ngh(Index *ix, const char *index_dir, uint32_t flags, tsc_ngh_info *out);
@@ -382,6 +389,8 @@ int32_t grp_filter_where(Group &g, const tsc_where_op *ops, uint32_t n_ops, cons
                          uint32_t n_in_args, const WhereTexts &texts, uint64_t *out_matched);
 int32_t grp_set_primary_keys(Group &g, uint64_t first_node_id, const uint8_t *utf8,
                              const uint64_t *offsets, uint64_t n);
+int32_t grp_filter_primary_keys(Group &g, const uint8_t *utf8, const uint64_t *offsets, uint64_t n,
+                                uint64_t *out_matched);
 int32_t grp_get_primary_key(Group &g, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
                             uint32_t *out_len);
 int32_t grp_load_ngh(Group &g, const char *index_dir, uint32_t flags, tsc_ngh_info *out);

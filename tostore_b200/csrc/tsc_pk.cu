@@ -1,6 +1,8 @@
 // tsc_pk.cu — nodeId -> primary key side table and PK-returning search
 // (include/tostore_cuda.h: tsc_index_set_primary_keys / _get_primary_key,
-// tsc_vector_search_pk). Host memory only; the reference keeps this mapping in the
+// tsc_vector_search_pk), and the WHERE prefilter from a set of primary keys
+// (tsc_index_filter_primary_keys: the role of the `<index>__pk2nid` lookup,
+// core/vector_index_manager.dart:1350-1363). Host memory only; the reference keeps this mapping in the
 // `<index>__nid2pk` B+Tree (core/vector_index_manager.dart:553-588, :1276-1293).
 #include <string.h>
 
@@ -42,7 +44,61 @@ int32_t ix_set_primary_keys(Index *ix, uint64_t first_node_id, const uint8_t *ut
     ix->pk_off[row0 + i] = arena0 + (offsets[i] - offsets[0]);
     ix->pk_len[row0 + i] = (uint32_t)(offsets[i + 1] - offsets[i]);
   }
+  ix->pk_rev_valid = false;
   return TSC_OK;
+}
+
+// Bitmap over the shard's rows: bit r is set iff the key of row r is one of the n given keys
+// (64-bit words, LSB first: the form tsc_index_set_filter takes). The reverse map is rebuilt from
+// the nodeId -> key table when that table changed; when a key is mapped by several rows the
+// highest node id wins (the latest insert, like an upsert of `__pk2nid`), tombstoned (empty)
+// mappings are not searchable. ix->mu held.
+static int32_t pk_filter_bitmap_locked(Index *ix, const uint8_t *utf8, const uint64_t *offsets,
+                                       uint64_t n, std::vector<uint64_t> *words,
+                                       uint64_t *out_matched) {
+  if (n && (!offsets || (!utf8 && offsets[n] != offsets[0]))) {
+    set_error("filter_primary_keys: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  for (uint64_t i = 0; i < n; i++)
+    if (offsets[i + 1] < offsets[i]) {
+      set_error("filter_primary_keys: offsets must be non-decreasing (entry %llu)",
+                (unsigned long long)i);
+      return TSC_ERR_BAD_ARG;
+    }
+  if (!ix->pk_rev_valid) {
+    ix->pk_rev.clear();
+    ix->pk_rev.reserve(ix->pk_len.size());
+    for (uint64_t r = 0; r < ix->pk_len.size(); r++)
+      if (ix->pk_len[r])
+        ix->pk_rev[std::string(ix->pk_arena.data() + ix->pk_off[r], ix->pk_len[r])] = r;
+    ix->pk_rev_valid = true;
+  }
+  const uint64_t rows = ix->rows > ix->pk_len.size() ? ix->rows : ix->pk_len.size();
+  words->assign((rows + 63) / 64 + 1, 0);
+  uint64_t matched = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (offsets[i + 1] == offsets[i]) continue;   // the empty key is the tombstone mapping
+    auto it = ix->pk_rev.find(std::string((const char *)utf8 + offsets[i], offsets[i + 1] - offsets[i]));
+    if (it == ix->pk_rev.end()) continue;
+    uint64_t &w = (*words)[it->second >> 6];
+    const uint64_t bit = 1ull << (it->second & 63);
+    matched += !(w & bit);
+    w |= bit;
+  }
+  if (out_matched) *out_matched = matched;
+  return TSC_OK;
+}
+
+int32_t ix_filter_primary_keys(Index *ix, const uint8_t *utf8, const uint64_t *offsets, uint64_t n,
+                               uint64_t *out_matched) {
+  std::vector<uint64_t> words;
+  {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int32_t rc = pk_filter_bitmap_locked(ix, utf8, offsets, n, &words, out_matched);
+    if (rc != TSC_OK) return rc;
+  }
+  return ix_set_filter(ix, words.data(), words.size());   // takes the lock itself
 }
 
 int32_t ix_get_primary_key(Index *ix, uint64_t node_id, uint8_t *out_utf8, uint32_t capacity,
@@ -131,6 +187,44 @@ int32_t tsc_index_get_primary_key(uint64_t handle, uint64_t node_id, uint8_t *ou
   IndexRef ref = lookup_index(handle);
   if (!ref) return TSC_ERR_BAD_HANDLE;
   return ix_get_primary_key(ref.get(), node_id, out_utf8, capacity, out_len);
+  TSC_API_CATCH
+}
+
+int32_t tsc_index_filter_primary_keys(uint64_t handle, const uint8_t *utf8, const uint64_t *offsets,
+                                      uint64_t n, uint64_t *out_matched) {
+  TSC_API_TRY
+  if (GroupRef g = lookup_group(handle)) {
+    std::lock_guard<std::mutex> glk(g->mu);
+    return grp_filter_primary_keys(*g, utf8, offsets, n, out_matched);
+  }
+  IndexRef ref = lookup_index(handle);
+  if (!ref) return TSC_ERR_BAD_HANDLE;
+  if (ref->host_only) {
+    set_error("host-only self-test handle: no device entry point works on it");
+    return TSC_ERR_UNSUPPORTED;
+  }
+  return ix_filter_primary_keys(ref.get(), utf8, offsets, n, out_matched);
+  TSC_API_CATCH
+}
+
+// Self-test hook (no GPU): the bitmap tsc_index_filter_primary_keys would install, computed by
+// the same code over the handle's primary-key table (works on a host-only index).
+int32_t tsc_selftest_pk_filter_bitmap(uint64_t handle, const uint8_t *utf8, const uint64_t *offsets,
+                                      uint64_t n, uint64_t *out_words, uint64_t n_words,
+                                      uint64_t *out_matched) {
+  TSC_API_TRY
+  IndexRef ref = lookup_index(handle);
+  if (!ref) return TSC_ERR_BAD_HANDLE;
+  if (!out_words && n_words) {
+    set_error("selftest_pk_filter_bitmap: NULL buffer");
+    return TSC_ERR_BAD_ARG;
+  }
+  std::vector<uint64_t> words;
+  std::lock_guard<std::mutex> lk(ref->mu);
+  int32_t rc = pk_filter_bitmap_locked(ref.get(), utf8, offsets, n, &words, out_matched);
+  if (rc != TSC_OK) return rc;
+  for (uint64_t i = 0; i < n_words; i++) out_words[i] = i < words.size() ? words[i] : 0;
+  return TSC_OK;
   TSC_API_CATCH
 }
 

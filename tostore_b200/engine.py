@@ -313,6 +313,23 @@ class GpuVectorIndex:
                                                      blob.ctypes.data, offs.ctypes.data, len(enc)),
                 "tsc_index_set_primary_keys")
 
+    @staticmethod
+    def _key_blob(pks):
+        enc = [b"" if p is None else str(p).encode("utf-8") for p in pks]
+        offs = np.zeros(len(enc) + 1, dtype=np.uint64)
+        np.cumsum([len(b) for b in enc], out=offs[1:])
+        return np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8), offs, len(enc)
+
+    def filter_primary_keys(self, pks) -> int:
+        """WHERE prefilter from a set of primary keys (what any ToStore query returns): the
+        rows whose key is in the set stay searchable; returns how many rows that is."""
+        blob, offs, n = self._key_blob(pks)
+        matched = C.c_uint64(0)
+        N.check(self._lib.tsc_index_filter_primary_keys(self.handle, blob.ctypes.data, offs.ctypes.data,
+                                                        n, C.byref(matched)),
+                "tsc_index_filter_primary_keys")
+        return matched.value
+
     def get_primary_key(self, node_id: int) -> Optional[str]:
         buf = (C.c_uint8 * 4096)()
         n = C.c_uint32(0)
